@@ -1,0 +1,231 @@
+"""embree_compressed_b200 -- B200-native traversal of Embree's compressed subdivision/displacement BVH.
+
+Python face of the C ABI in include/ecb200.h (libecb200.so: hand-written sm_100a CUDA kernels + a thin C++ host
+layer).  Python is plumbing only: it moves pointers.  There is no CPU or PyTorch fallback -- importing works without
+a GPU (so the library and its symbols can be checked), every traversal call raises EcbError without one.
+
+    scene = Scene.from_image_file("scenes/_built/bomberman_s6c3_leaf.rimg")   # or Scene.import_bvh4(root=..., ...)
+    scene.intersect1M(rayhits)            # numpy (N,20) float32 = RTCRayHit[N], mutated in place (rtcIntersect1M)
+    scene.intersect_device(ptr, n)        # device-resident rays (torch tensor .data_ptr())
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libecb200.so")
+
+INVALID_GEOMETRY_ID = 0xFFFFFFFF
+LEAF_GRID, LEAF_LEAF, LEAF_BOX = 0, 1, 2
+LEAF_KINDS = {"grid": LEAF_GRID, "leaf": LEAF_LEAF, "box": LEAF_BOX}
+ERROR_NO_DEVICE = 100
+
+
+class EcbError(RuntimeError):
+    def __init__(self, code, what, msg):
+        super().__init__("%s failed: %s (%d)%s" % (what, _lib().ecbErrorString(code).decode(), code,
+                                                   (": " + msg) if msg else ""))
+        self.code = code
+
+
+class ImportDesc(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("leaf_kind", C.c_uint32), ("proj_col_major", C.c_uint32),
+                ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32), ("bounds", C.c_float * 6)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("leaf_kind", C.c_uint32), ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32),
+                ("n_top_nodes", C.c_uint32), ("n_blocks", C.c_uint32), ("top_depth", C.c_uint32),
+                ("block_stride", C.c_uint32), ("top_node_bytes", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("reference_bytes", C.c_uint64), ("micro_triangles", C.c_uint64), ("bounds", C.c_float * 6),
+                ("device", C.c_int32)]
+
+
+# every entry point include/ecb200.h declares: (restype, argtypes)
+_vp, _u32, _u64, _sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
+SYMBOLS = {
+    "ecbSceneImportBVH4": (C.c_int, [C.POINTER(ImportDesc), C.POINTER(_vp)]),
+    "ecbSceneImportImage": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "ecbSceneImportImageFile": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "ecbSceneSave": (C.c_int, [_vp, C.c_char_p]),
+    "ecbSceneLoad": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "ecbSceneUpload": (C.c_int, [_vp, C.c_int]),
+    "ecbSceneGetInfo": (C.c_int, [_vp, C.POINTER(SceneInfo)]),
+    "ecbSceneRelease": (None, [_vp]),
+    "ecbIntersect1": (C.c_int, [_vp, _u32, _vp]),
+    "ecbIntersect1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
+    "ecbIntersect16": (C.c_int, [_vp, _vp, _u32, _vp]),
+    "ecbOccluded1": (C.c_int, [_vp, _u32, _vp]),
+    "ecbOccluded1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
+    "ecbIntersectDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
+    "ecbIntersectDeviceEx": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
+    "ecbIntersectDeviceStats": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
+    "ecbOccludedDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
+    "ecbSceneBlockNormals": (C.c_int, [_vp, _vp, _sz]),
+    "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
+    "ecbHostFree": (None, [_vp]),
+    "ecbLaunchCount": (_u64, []),
+    "ecbErrorString": (C.c_char_p, [C.c_int]),
+    "ecbLastErrorMessage": (C.c_char_p, []),
+}
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no fallback implementation)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _check(code, what):
+    if code != 0:
+        raise EcbError(code, what, _lib().ecbLastErrorMessage().decode())
+
+
+def launch_count():
+    return int(_lib().ecbLaunchCount())
+
+
+def host_alloc(n_bytes):
+    """Pinned host memory: returns (numpy uint8 view, pointer); free the pointer with host_free."""
+    p = _vp()
+    _check(_lib().ecbHostAlloc(C.byref(p), n_bytes), "ecbHostAlloc")
+    buf = (C.c_uint8 * n_bytes).from_address(p.value)
+    return np.frombuffer(buf, np.uint8), p.value
+
+
+def host_free(ptr):
+    _lib().ecbHostFree(ptr)
+
+
+class Scene:
+    """A committed compressed-BVH scene in the device format (host copy + lazily uploaded device copy)."""
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keepalive = keepalive
+
+    # -- construction -------------------------------------------------------------------------------------------
+    @classmethod
+    def import_bvh4(cls, root, leaf_kind, comp_level, subdiv_level=0, proj_col_major=1, base=0, bounds=None):
+        """ecbSceneImportBVH4: base = 0 walks live reference memory in this process."""
+        d = ImportDesc()
+        d.base = base
+        d.root = root
+        d.leaf_kind = LEAF_KINDS.get(leaf_kind, leaf_kind)
+        d.proj_col_major = proj_col_major
+        d.subdiv_level = subdiv_level
+        d.comp_level = comp_level
+        for i in range(6):
+            d.bounds[i] = float(bounds[i]) if bounds is not None else 0.0
+        h = _vp()
+        _check(_lib().ecbSceneImportBVH4(C.byref(d), C.byref(h)), "ecbSceneImportBVH4")
+        return cls(h.value)
+
+    @classmethod
+    def from_image(cls, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        h = _vp()
+        _check(_lib().ecbSceneImportImage(image.ctypes.data, image.nbytes, C.byref(h)), "ecbSceneImportImage")
+        return cls(h.value)
+
+    @classmethod
+    def from_image_file(cls, path):
+        h = _vp()
+        _check(_lib().ecbSceneImportImageFile(os.fsencode(path), C.byref(h)), "ecbSceneImportImageFile")
+        return cls(h.value)
+
+    @classmethod
+    def load(cls, path):
+        h = _vp()
+        _check(_lib().ecbSceneLoad(os.fsencode(path), C.byref(h)), "ecbSceneLoad")
+        return cls(h.value)
+
+    def save(self, path):
+        _check(_lib().ecbSceneSave(self._h, os.fsencode(path)), "ecbSceneSave")
+
+    def upload(self, device=-1):
+        _check(_lib().ecbSceneUpload(self._h, device), "ecbSceneUpload")
+        return self
+
+    def release(self):
+        if self._h:
+            _lib().ecbSceneRelease(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # -- queries ------------------------------------------------------------------------------------------------
+    def info(self):
+        i = SceneInfo()
+        _check(_lib().ecbSceneGetInfo(self._h, C.byref(i)), "ecbSceneGetInfo")
+        d = {n: getattr(i, n) for n, _ in SceneInfo._fields_ if n != "bounds"}
+        d["bounds"] = [i.bounds[k] for k in range(6)]
+        d["bytes_per_micro_triangle"] = d["device_bytes"] / max(1, d["micro_triangles"])
+        d["reference_bytes_per_micro_triangle"] = d["reference_bytes"] / max(1, d["micro_triangles"])
+        return d
+
+    def block_normals(self):
+        n = self.info()["n_blocks"]
+        out = np.zeros((n, 3), np.float32)
+        _check(_lib().ecbSceneBlockNormals(self._h, out.ctypes.data, out.size), "ecbSceneBlockNormals")
+        return out
+
+    # -- traversal, host buffers (rtcIntersect1M / rtcOccluded1M / rtcIntersect16 semantics) -----------------------
+    @staticmethod
+    def _host_args(a, width):
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 2 and a.shape[1] >= width
+                and a.strides[1] == 4):
+            raise ValueError("rays must be a float32 array of shape (N, >=%d)" % width)
+        return a.ctypes.data, a.shape[0], a.strides[0]
+
+    def intersect1M(self, rayhits, inst_id=INVALID_GEOMETRY_ID):
+        p, n, stride = self._host_args(rayhits, 20)
+        _check(_lib().ecbIntersect1M(self._h, inst_id, p, n, stride), "ecbIntersect1M")
+
+    def occluded1M(self, rays, inst_id=INVALID_GEOMETRY_ID):
+        p, n, stride = self._host_args(rays, 12)
+        _check(_lib().ecbOccluded1M(self._h, inst_id, p, n, stride), "ecbOccluded1M")
+
+    def intersect1(self, rayhit, inst_id=INVALID_GEOMETRY_ID):
+        _check(_lib().ecbIntersect1(self._h, inst_id, rayhit.ctypes.data), "ecbIntersect1")
+
+    def occluded1(self, ray, inst_id=INVALID_GEOMETRY_ID):
+        _check(_lib().ecbOccluded1(self._h, inst_id, ray.ctypes.data), "ecbOccluded1")
+
+    def intersect16(self, valid, rayhit16, inst_id=INVALID_GEOMETRY_ID):
+        """valid: int32[16] (-1 active / 0 inactive); rayhit16: float32 (20,16) SoA = RTCRayHit16."""
+        valid = np.ascontiguousarray(valid, np.int32)
+        assert rayhit16.dtype == np.float32 and rayhit16.shape == (20, 16) and rayhit16.flags.c_contiguous
+        _check(_lib().ecbIntersect16(valid.ctypes.data, self._h, inst_id, rayhit16.ctypes.data), "ecbIntersect16")
+
+    # -- traversal, device buffers ----------------------------------------------------------------------------------
+    def intersect_device(self, ptr, n, stride=80, stream=0, block_out_ptr=0, inst_id=INVALID_GEOMETRY_ID):
+        if block_out_ptr:
+            _check(_lib().ecbIntersectDeviceEx(self._h, inst_id, ptr, n, stride, block_out_ptr, stream),
+                   "ecbIntersectDeviceEx")
+        else:
+            _check(_lib().ecbIntersectDevice(self._h, inst_id, ptr, n, stride, stream), "ecbIntersectDevice")
+
+    def intersect_device_stats(self, ptr, n, counters_ptr, stride=80, stream=0, inst_id=INVALID_GEOMETRY_ID):
+        """counters_ptr: device uint64[6] = rays, top nodes, blocks, quantized nodes, cells, hits (accumulated)."""
+        _check(_lib().ecbIntersectDeviceStats(self._h, inst_id, ptr, n, stride, counters_ptr, stream),
+               "ecbIntersectDeviceStats")
+
+    def occluded_device(self, ptr, n, stride=48, stream=0, inst_id=INVALID_GEOMETRY_ID):
+        _check(_lib().ecbOccludedDevice(self._h, inst_id, ptr, n, stride, stream), "ecbOccludedDevice")

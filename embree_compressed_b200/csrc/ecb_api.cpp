@@ -1,0 +1,478 @@
+// ecb_api.cpp -- C-ABI host layer of libecb200.so (include/ecb200.h): scene residency, host-buffer staging
+// pipeline, device-buffer launches, serialisation.  No traversal arithmetic lives here and there is no CPU
+// fallback: without a usable CUDA device every traversal entry point fails with ECB_ERROR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ecb_kernels.h"
+#include "ecb_scene.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
+constexpr int kStages = 3;
+constexpr size_t kChunkRays = 1u << 19;  // 512 Ki rays (40 MiB of RTCRayHit) per pipeline stage
+
+ecbError cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice ||
+      e == cudaErrorInvalidDevice)
+    return ECB_ERROR_NO_DEVICE;
+  if (e == cudaErrorMemoryAllocation) return ECB_ERROR_OUT_OF_MEMORY;
+  return ECB_ERROR_CUDA;
+}
+#define CU(call)                                    \
+  do {                                              \
+    cudaError_t e__ = (call);                       \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+}  // namespace
+
+void ecb_set_error(const std::string& msg) { g_last_error = msg; }
+
+// Three-stage H2D -> kernel -> D2H pipeline over fixed device buffers; created lazily per scene.
+struct Staging {
+  int device = -1;
+  cudaStream_t stream[kStages] = {};
+  void* d_buf[kStages] = {};
+  void* h_pin[kStages] = {};  // pinned bounce buffers for pageable caller memory
+  ~Staging() {
+    for (int i = 0; i < kStages; i++) {
+      if (d_buf[i]) cudaFree(d_buf[i]);
+      if (h_pin[i]) cudaFreeHost(h_pin[i]);
+      if (stream[i]) cudaStreamDestroy(stream[i]);
+    }
+  }
+};
+
+namespace {
+
+ecbError ensure_resident(ecbScene* s, int device) {
+  std::lock_guard<std::mutex> lock(s->mutex);
+  if (s->device >= 0) {
+    if (device >= 0 && device != s->device) {
+      g_last_error = "scene is resident on another device";
+      return ECB_ERROR_INVALID_OPERATION;
+    }
+    return ECB_SUCCESS;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_last_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return ECB_ERROR_NO_DEVICE;
+  }
+  if (device < 0) {
+    CU(cudaGetDevice(&device));
+  }
+  CU(cudaSetDevice(device));
+  const size_t top_bytes = s->top.size() * sizeof(EcbTopNode);
+  if (top_bytes) {
+    CU(cudaMalloc(&s->d_top, top_bytes));
+    CU(cudaMemcpy(s->d_top, s->top.data(), top_bytes, cudaMemcpyHostToDevice));
+  }
+  if (!s->blocks.empty()) {
+    CU(cudaMalloc(&s->d_blocks, s->blocks.size()));
+    CU(cudaMemcpy(s->d_blocks, s->blocks.data(), s->blocks.size(), cudaMemcpyHostToDevice));
+  }
+  EcbDeviceScene& d = s->dev;
+  d.top = static_cast<const EcbTopNode*>(s->d_top);
+  d.blocks = static_cast<const uint8_t*>(s->d_blocks);
+  d.root = s->root;
+  d.n_top = (uint32_t)s->top.size();
+  d.n_blocks = s->info.n_blocks;
+  d.block_stride = s->block_stride;
+  d.leaf_offset = s->leaf_offset;
+  d.leaf_kind = s->info.leaf_kind;
+  d.comp_level = s->info.comp_level;
+  d.elems = s->elems;
+  d.grid_width = s->grid_width;
+  d.rcp_edges = s->rcp_edges;
+  s->device = device;
+  s->info.device = device;
+  return ECB_SUCCESS;
+}
+
+ecbError ensure_staging(ecbScene* s) {
+  if (s->staging) return ECB_SUCCESS;
+  Staging* st = new (std::nothrow) Staging;
+  if (!st) return ECB_ERROR_OUT_OF_MEMORY;
+  st->device = s->device;
+  for (int i = 0; i < kStages; i++) {
+    cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRays * kRayHitBytes);
+    if (e != cudaSuccess) {
+      delete st;
+      return cuda_fail(e, "staging allocation");
+    }
+  }
+  s->staging = st;
+  return ECB_SUCCESS;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Shared by intersect (elem = 80) and occluded (elem = 48).
+ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride) {
+  if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
+  const size_t elem = occluded ? kRayBytes : kRayHitBytes;
+  if (stride < elem || (stride & 3)) {
+    g_last_error = "byteStride must be a multiple of 4 and at least the struct size";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  if (M == 0) return ECB_SUCCESS;
+  ecbError err = ensure_resident(s, -1);
+  if (err != ECB_SUCCESS) return err;
+  std::lock_guard<std::mutex> lock(s->mutex);
+  CU(cudaSetDevice(s->device));
+  err = ensure_staging(s);
+  if (err != ECB_SUCCESS) return err;
+  Staging* st = s->staging;
+  const bool pinned = is_pinned(rays);
+  // device-side layout is always densely packed (stride = elem, 16-byte aligned)
+  const size_t chunk = kChunkRays;
+  uint8_t* base = static_cast<uint8_t*>(rays);
+  const uint64_t n_chunks = (M + chunk - 1) / chunk;
+  if (!pinned) {
+    for (int i = 0; i < kStages; i++)
+      if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRays * kRayHitBytes));
+  }
+  for (uint64_t c = 0; c < n_chunks; c++) {
+    const int k = (int)(c % kStages);
+    const uint64_t first = c * chunk;
+    const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
+    uint8_t* src = base + first * stride;
+    cudaStream_t q = st->stream[k];
+    if (pinned) {
+      if (stride == elem) CU(cudaMemcpyAsync(st->d_buf[k], src, n * elem, cudaMemcpyHostToDevice, q));
+      else CU(cudaMemcpy2DAsync(st->d_buf[k], elem, src, stride, elem, n, cudaMemcpyHostToDevice, q));
+    } else {
+      // bounce through pinned memory: wait until this stage's previous round trip has drained
+      CU(cudaStreamSynchronize(q));
+      if (c >= (uint64_t)kStages) {
+        // write back the results of chunk c-kStages that used this bounce buffer
+        const uint64_t pfirst = (c - kStages) * chunk;
+        const size_t pn = (size_t)((M - pfirst) < chunk ? (M - pfirst) : chunk);
+        uint8_t* dst = base + pfirst * stride;
+        const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
+        if (stride == elem) memcpy(dst, hb, pn * elem);
+        else for (size_t i = 0; i < pn; i++) memcpy(dst + i * stride, hb + i * elem, elem);
+      }
+      uint8_t* hb = static_cast<uint8_t*>(st->h_pin[k]);
+      if (stride == elem) memcpy(hb, src, n * elem);
+      else for (size_t i = 0; i < n; i++) memcpy(hb + i * elem, src + i * stride, elem);
+      CU(cudaMemcpyAsync(st->d_buf[k], hb, n * elem, cudaMemcpyHostToDevice, q));
+    }
+    cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, st->d_buf[k], n, elem, q)
+                              : ecb_launch_intersect(s->dev, s->device, st->d_buf[k], n, elem, instID, nullptr, nullptr, q);
+    if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+    g_launches.fetch_add(1);
+    if (pinned) {
+      if (stride == elem) CU(cudaMemcpyAsync(src, st->d_buf[k], n * elem, cudaMemcpyDeviceToHost, q));
+      else CU(cudaMemcpy2DAsync(src, stride, st->d_buf[k], elem, elem, n, cudaMemcpyDeviceToHost, q));
+    } else {
+      CU(cudaMemcpyAsync(st->h_pin[k], st->d_buf[k], n * elem, cudaMemcpyDeviceToHost, q));
+    }
+  }
+  for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
+  if (!pinned) {
+    const uint64_t tail0 = n_chunks > (uint64_t)kStages ? n_chunks - kStages : 0;
+    for (uint64_t c = tail0; c < n_chunks; c++) {
+      const int k = (int)(c % kStages);
+      const uint64_t first = c * chunk;
+      const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
+      uint8_t* dst = base + first * stride;
+      const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
+      if (stride == elem) memcpy(dst, hb, n * elem);
+      else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, hb + i * elem, elem);
+    }
+  }
+  return ECB_SUCCESS;
+}
+
+ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, uint64_t M, size_t stride, uint32_t* d_block_out,
+                    void* stream, unsigned long long* d_counters = nullptr) {
+  if (!s || (!d_rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
+  const size_t elem = occluded ? kRayBytes : kRayHitBytes;
+  if (stride < elem || (stride & 15) || (reinterpret_cast<uintptr_t>(d_rays) & 15)) {
+    g_last_error = "device rays must be 16-byte aligned with a byteStride that is a multiple of 16";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  ecbError err = ensure_resident(s, -1);
+  if (err != ECB_SUCCESS) return err;
+  cudaStream_t q = static_cast<cudaStream_t>(stream);
+  cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, d_rays, M, stride, q)
+                            : ecb_launch_intersect(s->dev, s->device, d_rays, M, stride, instID, d_block_out, d_counters, q);
+  if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+  if (M) g_launches.fetch_add(1);
+  return ECB_SUCCESS;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out) { return ecb_import_bvh4(desc, scene_out); }
+
+ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out) {
+  // header of oracle/rimg.h restated as offsets (plain data: magic[8], 8 x u32, root u64, total u64, bounds[6])
+  if (!image || bytes < 96 || memcmp(image, "ECBRIMG1", 8) != 0) {
+    g_last_error = "not an RIMG image";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(image);
+  uint32_t w[8];
+  memcpy(w, p + 8, sizeof(w));
+  uint64_t root, total;
+  memcpy(&root, p + 40, 8);
+  memcpy(&total, p + 48, 8);
+  if (w[0] != 1 || total > bytes) {
+    g_last_error = "RIMG version/size mismatch";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  ecbImportDesc d;
+  memset(&d, 0, sizeof(d));
+  d.base = image;
+  d.root = root;
+  d.leaf_kind = w[1];
+  d.subdiv_level = w[2];
+  d.comp_level = w[3];
+  d.proj_col_major = w[4];
+  memcpy(d.bounds, p + 56, 24);
+  return ecb_import_bvh4(&d, scene_out);
+}
+
+ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) {
+    g_last_error = std::string("cannot open ") + (path ? path : "(null)");
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  const size_t n = (size_t)f.tellg();
+  std::vector<char> buf(n);
+  f.seekg(0);
+  f.read(buf.data(), (std::streamsize)n);
+  return ecbSceneImportImage(buf.data(), n, scene_out);
+}
+
+ecbError ecbSceneSave(const ecbScene* s, const char* path) {
+  if (!s || !path) return ECB_ERROR_INVALID_ARGUMENT;
+  EcbBlobHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "ECB200S1", 8);
+  h.version = 1;
+  h.leaf_kind = s->info.leaf_kind;
+  h.subdiv_level = s->info.subdiv_level;
+  h.comp_level = s->info.comp_level;
+  h.n_top = (uint32_t)s->top.size();
+  h.n_blocks = s->info.n_blocks;
+  h.block_stride = s->block_stride;
+  h.leaf_offset = s->leaf_offset;
+  h.root = s->root;
+  h.top_depth = s->info.top_depth;
+  h.elems = s->elems;
+  h.grid_width = s->grid_width;
+  h.rcp_edges = s->rcp_edges;
+  memcpy(h.bounds, s->info.bounds, sizeof(h.bounds));
+  h.reference_bytes = s->info.reference_bytes;
+  h.top_bytes = s->top.size() * sizeof(EcbTopNode);
+  h.block_bytes = s->blocks.size();
+  std::ofstream f(path, std::ios::binary);
+  if (!f) {
+    g_last_error = std::string("cannot write ") + path;
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  f.write(reinterpret_cast<const char*>(&h), sizeof(h));
+  f.write(reinterpret_cast<const char*>(s->top.data()), (std::streamsize)h.top_bytes);
+  f.write(reinterpret_cast<const char*>(s->blocks.data()), (std::streamsize)h.block_bytes);
+  return f ? ECB_SUCCESS : ECB_ERROR_UNKNOWN;
+}
+
+ecbError ecbSceneLoad(const char* path, ecbScene** out) {
+  if (!path || !out) return ECB_ERROR_INVALID_ARGUMENT;
+  std::ifstream f(path, std::ios::binary);
+  EcbBlobHeader h;
+  if (!f || !f.read(reinterpret_cast<char*>(&h), sizeof(h)) || memcmp(h.magic, "ECB200S1", 8) != 0 || h.version != 1) {
+    g_last_error = std::string("not an ECB200 scene blob: ") + path;
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  if (h.top_bytes != (uint64_t)h.n_top * sizeof(EcbTopNode) || h.block_bytes != (uint64_t)h.n_blocks * h.block_stride ||
+      h.comp_level < 1 || h.comp_level > ECB_MAX_C || h.leaf_kind > ECB_LEAF_BOX || 3 * h.top_depth + 4 > ECB_MAX_TOP_STACK) {
+    g_last_error = "corrupt scene blob header";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  ecbScene* s = new (std::nothrow) ecbScene;
+  if (!s) return ECB_ERROR_OUT_OF_MEMORY;
+  s->top.resize(h.n_top);
+  s->blocks.resize(h.block_bytes);
+  f.read(reinterpret_cast<char*>(s->top.data()), (std::streamsize)h.top_bytes);
+  f.read(reinterpret_cast<char*>(s->blocks.data()), (std::streamsize)h.block_bytes);
+  if (!f) {
+    delete s;
+    g_last_error = "truncated scene blob";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  // every child reference must stay inside the arrays: the kernels trust the blob
+  for (const EcbTopNode& n : s->top)
+    for (int i = 0; i < 4; i++) {
+      const uint32_t c = n.child[i];
+      const bool ok = c == ECB_REF_EMPTY || ((c & ECB_REF_LEAF) ? (c & ~ECB_REF_LEAF) < h.n_blocks : c < h.n_top);
+      if (!ok) {
+        delete s;
+        g_last_error = "scene blob has an out-of-range child reference";
+        return ECB_ERROR_INVALID_ARGUMENT;
+      }
+    }
+  s->root = h.root;
+  s->block_stride = h.block_stride;
+  s->leaf_offset = h.leaf_offset;
+  s->elems = h.elems;
+  s->grid_width = h.grid_width;
+  s->rcp_edges = h.rcp_edges;
+  ecbSceneInfo& in = s->info;
+  in.leaf_kind = h.leaf_kind;
+  in.subdiv_level = h.subdiv_level;
+  in.comp_level = h.comp_level;
+  in.n_top_nodes = h.n_top;
+  in.n_blocks = h.n_blocks;
+  in.top_depth = h.top_depth;
+  in.block_stride = h.block_stride;
+  in.top_node_bytes = sizeof(EcbTopNode);
+  in.device_bytes = h.top_bytes + h.block_bytes;
+  in.reference_bytes = h.reference_bytes;
+  in.micro_triangles = 2ull * (1ull << (2 * h.comp_level)) * h.n_blocks;
+  memcpy(in.bounds, h.bounds, sizeof(in.bounds));
+  in.device = -1;
+  *out = s;
+  return ECB_SUCCESS;
+}
+
+ecbError ecbSceneUpload(ecbScene* s, int device) {
+  if (!s) return ECB_ERROR_INVALID_ARGUMENT;
+  return ensure_resident(s, device);
+}
+
+ecbError ecbSceneGetInfo(const ecbScene* s, ecbSceneInfo* info) {
+  if (!s || !info) return ECB_ERROR_INVALID_ARGUMENT;
+  *info = s->info;
+  return ECB_SUCCESS;
+}
+
+void ecbSceneRelease(ecbScene* s) {
+  if (!s) return;
+  if (s->device >= 0) {
+    cudaSetDevice(s->device);
+    delete s->staging;
+    if (s->d_top) cudaFree(s->d_top);
+    if (s->d_blocks) cudaFree(s->d_blocks);
+  }
+  delete s;
+}
+
+ecbError ecbIntersect1(ecbScene* s, uint32_t instID, void* rayhit) { return run_host(s, false, instID, rayhit, 1, kRayHitBytes); }
+ecbError ecbIntersect1M(ecbScene* s, uint32_t instID, void* rayhit, uint32_t M, size_t byteStride) {
+  return run_host(s, false, instID, rayhit, M, byteStride);
+}
+ecbError ecbOccluded1(ecbScene* s, uint32_t instID, void* ray) { return run_host(s, true, instID, ray, 1, kRayBytes); }
+ecbError ecbOccluded1M(ecbScene* s, uint32_t instID, void* ray, uint32_t M, size_t byteStride) {
+  return run_host(s, true, instID, ray, M, byteStride);
+}
+
+// RTCRayHit16 (include/embree3/rtcore_ray.h:149-187) is the SoA transpose of 16 RTCRayHit: 20 arrays of 16 words.
+ecbError ecbIntersect16(const int* valid, ecbScene* s, uint32_t instID, void* rayhit16) {
+  if (!valid || !rayhit16) return ECB_ERROR_INVALID_ARGUMENT;
+  alignas(16) uint32_t aos[16][20];
+  uint32_t* soa = static_cast<uint32_t*>(rayhit16);
+  for (int l = 0; l < 16; l++) {
+    for (int f = 0; f < 20; f++) aos[l][f] = soa[f * 16 + l];
+    if (valid[l] != -1) {  // inactive lane -> inactive stream ray (tnear > tfar)
+      const float one = 1.f, zero = 0.f;
+      memcpy(&aos[l][3], &one, 4);
+      memcpy(&aos[l][8], &zero, 4);
+    }
+  }
+  ecbError e = run_host(s, false, instID, aos, 16, kRayHitBytes);
+  if (e != ECB_SUCCESS) return e;
+  for (int l = 0; l < 16; l++) {
+    if (valid[l] != -1) continue;
+    soa[8 * 16 + l] = aos[l][8];
+    for (int f = 12; f < 20; f++) soa[f * 16 + l] = aos[l][f];
+  }
+  return ECB_SUCCESS;
+}
+
+ecbError ecbIntersectDevice(ecbScene* s, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride, void* stream) {
+  return run_device(s, false, instID, d_rayhit, M, byteStride, nullptr, stream);
+}
+ecbError ecbIntersectDeviceEx(ecbScene* s, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride, uint32_t* d_block_out,
+                              void* stream) {
+  return run_device(s, false, instID, d_rayhit, M, byteStride, d_block_out, stream);
+}
+ecbError ecbIntersectDeviceStats(ecbScene* s, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride, uint64_t* d_counters,
+                                 void* stream) {
+  if (!d_counters) return ECB_ERROR_INVALID_ARGUMENT;
+  return run_device(s, false, instID, d_rayhit, M, byteStride, nullptr, stream, reinterpret_cast<unsigned long long*>(d_counters));
+}
+ecbError ecbOccludedDevice(ecbScene* s, uint32_t instID, void* d_ray, uint64_t M, size_t byteStride, void* stream) {
+  return run_device(s, true, instID, d_ray, M, byteStride, nullptr, stream);
+}
+
+ecbError ecbSceneBlockNormals(const ecbScene* s, float* out, size_t cap) {
+  if (!s || !out) return ECB_ERROR_INVALID_ARGUMENT;
+  if (cap < 3 * (size_t)s->info.n_blocks) return ECB_ERROR_INVALID_ARGUMENT;
+  for (uint32_t b = 0; b < s->info.n_blocks; b++) {
+    const EcbBlockHeader* h = reinterpret_cast<const EcbBlockHeader*>(s->blocks.data() + (size_t)b * s->block_stride);
+    // space = inverse([vx vy vz]) stored by columns; its third ROW is vz (unit, orthogonal to vx and vy; compressed.h:121-126)
+    out[3 * b + 0] = h->space[2];
+    out[3 * b + 1] = h->space[5];
+    out[3 * b + 2] = h->space[8];
+  }
+  return ECB_SUCCESS;
+}
+
+ecbError ecbHostAlloc(void** ptr, size_t bytes) {
+  if (!ptr) return ECB_ERROR_INVALID_ARGUMENT;
+  CU(cudaMallocHost(ptr, bytes));
+  return ECB_SUCCESS;
+}
+void ecbHostFree(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+uint64_t ecbLaunchCount(void) { return g_launches.load(); }
+
+const char* ecbErrorString(ecbError e) {
+  switch (e) {
+    case ECB_SUCCESS: return "success";
+    case ECB_ERROR_UNKNOWN: return "unknown error";
+    case ECB_ERROR_INVALID_ARGUMENT: return "invalid argument";
+    case ECB_ERROR_INVALID_OPERATION: return "invalid operation";
+    case ECB_ERROR_OUT_OF_MEMORY: return "out of memory";
+    case ECB_ERROR_UNSUPPORTED: return "scene uses a feature outside the compressed-BVH hot path";
+    case ECB_ERROR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case ECB_ERROR_CUDA: return "CUDA error";
+  }
+  return "?";
+}
+const char* ecbLastErrorMessage(void) { return g_last_error.c_str(); }
+
+}  // extern "C"

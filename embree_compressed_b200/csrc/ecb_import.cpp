@@ -1,0 +1,175 @@
+// ecb_import.cpp -- converts the reference's committed compressed BVH4 into the device scene format.
+//
+// The importer reads the reference's memory directly through a hard-coded description of its layout (no reference
+// headers are included; the layout is probe-verified by tests/test_layout.py against the compiled reference):
+//   BVH4 NodeRef            kernels/bvh/bvh.h:107-140,150-400   low 4 bits = type, tyLeaf = 8, emptyNode = 8
+//   BVH4::AlignedNode       kernels/bvh/bvh.h:403-430,588-594   children[4] @0 (8 B each), 6 x vfloat4 bounds @32
+//   leaf                    encodeTypedLeaf(cbvh,1): one CompressedBVH per leaf (kernels/bvh/bvh_builder_subdiv.cpp:727-728)
+//   CompressedBVH<node_t>   kernels/geometry/compressed.h:408-433,340-376  184-byte header, then nodes/leaves/grid
+// Host only; runs without a GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+
+#include "ecb_scene.h"
+
+namespace {
+
+// ---- reference layout ----
+constexpr uint64_t kAlignMask = 15, kTyLeaf = 8, kEmpty = 8;
+constexpr size_t kAN_Children = 0, kAN_Bounds = 32, kAN_Size = 128;
+constexpr size_t kB_GeomID = 0, kB_PrimID = 4, kB_UV = 8, kB_Nodes = 32, kB_Leaves = 40, kB_Grid = 48, kB_Extent = 56,
+                 kB_Elems = 60, kB_GridWidth = 64, kB_Space = 68, kB_Proj = 104, kB_Box = 140, kB_Size = 184;
+
+template <typename T>
+T rd(const uint8_t* p) {
+  T v;
+  memcpy(&v, p, sizeof(T));
+  return v;
+}
+
+struct Importer {
+  const ecbImportDesc& d;
+  ecbScene& s;
+  const uint8_t* base;
+  uint32_t max_depth = 0;
+  uint64_t ref_bytes = 0;
+  std::string err;
+
+  Importer(const ecbImportDesc& desc, ecbScene& scene) : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+
+  const uint8_t* at(uint64_t ref) const { return base + (ref & ~kAlignMask); }
+
+  uint32_t import_block(uint64_t ref) {
+    const uint8_t* b = at(ref);
+    const uint32_t elems = rd<uint32_t>(b + kB_Elems);
+    const uint32_t width = rd<uint32_t>(b + kB_GridWidth);
+    if (elems != s.elems || width != s.grid_width) {
+      err = "block with elems=" + std::to_string(elems) + " grid_width=" + std::to_string(width) +
+            " does not match compression level " + std::to_string(d.comp_level);
+      return ECB_REF_EMPTY;
+    }
+    const size_t index = s.blocks.size() / s.block_stride;
+    s.blocks.resize(s.blocks.size() + s.block_stride, 0);
+    uint8_t* out = s.blocks.data() + index * s.block_stride;
+    EcbBlockHeader h;
+    memset(&h, 0, sizeof(h));
+    for (int i = 0; i < 9; i++) h.space[i] = rd<float>(b + kB_Space + 4 * i);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) h.proj[3 * r + c] = rd<float>(b + kB_Proj + 4 * (d.proj_col_major ? 3 * c + r : 3 * r + c));
+    for (int i = 0; i < 10; i++) h.box[i] = rd<float>(b + kB_Box + 4 * i);
+    for (int i = 0; i < 4; i++) h.uv[i] = rd<float>(b + kB_UV + 4 * i);
+    h.extent = rd<float>(b + kB_Extent);
+    h.geomID = rd<uint32_t>(b + kB_GeomID);
+    h.primID = rd<uint32_t>(b + kB_PrimID);
+    const uint8_t* nodes = base + rd<uint64_t>(b + kB_Nodes);
+    h.root_word = rd<uint32_t>(nodes);
+    memcpy(out, &h, sizeof(h));
+    if (elems > 1) memcpy(out + ECB_BLOCK_NODES_OFFSET, nodes + 4, 4 * (size_t)(elems - 1));
+    const size_t cells = 3 * (size_t)elems + 1;
+    if (d.leaf_kind == ECB_LEAF_LEAF) {
+      memcpy(out + s.leaf_offset, base + rd<uint64_t>(b + kB_Leaves), 2 * cells);
+      ref_bytes += 2 * cells;
+    } else if (d.leaf_kind == ECB_LEAF_GRID) {
+      memcpy(out + s.leaf_offset, base + rd<uint64_t>(b + kB_Grid), 12 * (size_t)width * width);
+      ref_bytes += 12 * (size_t)width * width;
+    }
+    ref_bytes += kB_Size + 4 * (size_t)elems;
+    return ECB_REF_LEAF | (uint32_t)index;
+  }
+
+  // pre-order DFS keeps subtrees (and the blocks below them) contiguous in memory
+  uint32_t import_ref(uint64_t ref, uint32_t depth) {
+    if (!err.empty()) return ECB_REF_EMPTY;
+    if (ref == kEmpty) return ECB_REF_EMPTY;
+    if (ref & kTyLeaf) {
+      const uint64_t num = (ref & kAlignMask) - kTyLeaf;
+      if (num != 1) {
+        err = "leaf with " + std::to_string(num) + " blocks (the compressed builder emits exactly 1)";
+        return ECB_REF_EMPTY;
+      }
+      if (depth > max_depth) max_depth = depth;
+      return import_block(ref);
+    }
+    if ((ref & kAlignMask) != 0) {
+      err = "node type " + std::to_string(ref & kAlignMask) + " is not an AlignedNode (outside the compressed path)";
+      return ECB_REF_EMPTY;
+    }
+    if (depth > 512) {
+      err = "top-level BVH deeper than 512";
+      return ECB_REF_EMPTY;
+    }
+    const uint8_t* n = at(ref);
+    const uint32_t index = (uint32_t)s.top.size();
+    s.top.emplace_back();
+    ref_bytes += kAN_Size;
+    EcbTopNode node;
+    memcpy(node.bounds, n + kAN_Bounds, 96);
+    for (int i = 0; i < 4; i++) node.child[i] = import_ref(rd<uint64_t>(n + kAN_Children + 8 * i), depth + 1);
+    s.top[index] = node;
+    return index;
+  }
+};
+
+}  // namespace
+
+ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out) {
+  if (!desc || !out) return ECB_ERROR_INVALID_ARGUMENT;
+  if (desc->leaf_kind > ECB_LEAF_BOX) {
+    ecb_set_error("unknown leaf kind");
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  if (desc->comp_level < 1 || desc->comp_level > ECB_MAX_C) {
+    ecb_set_error("compression level must be in 1.." + std::to_string(ECB_MAX_C));
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  ecbScene* s = new (std::nothrow) ecbScene;
+  if (!s) return ECB_ERROR_OUT_OF_MEMORY;
+  const uint32_t C = desc->comp_level;
+  const uint32_t cells = 1u << (2 * C);
+  s->elems = (cells - 1) / 3;
+  s->grid_width = (1u << C) + 1;
+  s->rcp_edges = 1.0f / (float)(1u << C);
+  size_t off = ECB_BLOCK_NODES_OFFSET + 4 * (size_t)(s->elems - 1);
+  off = (off + 15) & ~size_t(15);
+  s->leaf_offset = (uint32_t)off;
+  if (desc->leaf_kind == ECB_LEAF_LEAF) off += 2 * (size_t)cells;
+  if (desc->leaf_kind == ECB_LEAF_GRID) off += 12 * (size_t)s->grid_width * s->grid_width;
+  s->block_stride = (uint32_t)((off + 15) & ~size_t(15));
+
+  Importer imp(*desc, *s);
+  try {
+    s->root = imp.import_ref(desc->root, 0);
+  } catch (const std::bad_alloc&) {
+    delete s;
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+  if (!imp.err.empty()) {
+    ecb_set_error(imp.err);
+    delete s;
+    return ECB_ERROR_UNSUPPORTED;
+  }
+  if (3 * imp.max_depth + 4 > ECB_MAX_TOP_STACK) {
+    ecb_set_error("top-level BVH depth " + std::to_string(imp.max_depth) + " exceeds the traversal stack");
+    delete s;
+    return ECB_ERROR_UNSUPPORTED;
+  }
+  ecbSceneInfo& in = s->info;
+  in.leaf_kind = desc->leaf_kind;
+  in.subdiv_level = desc->subdiv_level;
+  in.comp_level = C;
+  in.n_top_nodes = (uint32_t)s->top.size();
+  in.n_blocks = (uint32_t)(s->blocks.size() / s->block_stride);
+  in.top_depth = imp.max_depth;
+  in.block_stride = s->block_stride;
+  in.top_node_bytes = sizeof(EcbTopNode);
+  in.device_bytes = s->top.size() * sizeof(EcbTopNode) + s->blocks.size();
+  in.reference_bytes = imp.ref_bytes;
+  in.micro_triangles = 2ull * cells * in.n_blocks;
+  memcpy(in.bounds, desc->bounds, sizeof(in.bounds));
+  in.device = -1;
+  *out = s;
+  return ECB_SUCCESS;
+}

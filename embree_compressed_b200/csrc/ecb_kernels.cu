@@ -1,0 +1,705 @@
+// ecb_kernels.cu -- sm_100a traversal kernels for the compressed subdivision/displacement BVH.
+//
+// Per-ray semantics restate (paths relative to the reference tree):
+//   top level   BVHNIntersector1<4,BVH_AN1,robust>::intersect / occluded   kernels/bvh/bvh_intersector1.cpp:40-209
+//               TravRay / intersectNodeRobust                              kernels/bvh/node_intersector1.h:113-139,334-368
+//               traverseClosestHit / traverseAnyHit + sort networks        kernels/bvh/bvh_traverser1.h:436-537, kernels/common/stack_item.h:39-60
+//   block       CompressedBVHIntersector1::intersect                       kernels/geometry/compressed.h:454-752
+//               Node::getNode + tables                                     kernels/geometry/compressed_node.h:22-39,261-295,488-510
+//               leafStorage<4>::getZ                                       kernels/geometry/compressed_leaf.h:93-111
+//               project / frustum / patch / triangles / Morton             kernels/geometry/compressed_help.h:19-50,86-308
+//
+// Arithmetic contract: fp32, compiled with -fmad=false; the only fused multiply-adds are the explicit __fmaf_rn in
+// xfm() where the reference's AVX2 build has explicit FMAs (common/math/linearspace3.h:168-169).  Division and sqrt
+// are IEEE (the reference uses rcpss/rsqrtss + one Newton step, common/math/math.h:60-97; results agree to ~1 ulp).
+// With this contract the kernels are bit-identical to the scalar oracle (oracle/cbvh_port.c).
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ecb_format.h"
+#include "ecb_kernels.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }  // _mm_max_ps operand semantics
+__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float zero_fix(float a) { return fabsf(a) < 1E-18f ? 1E-18f : a; }
+
+__device__ __forceinline__ uint32_t compact1by1(uint32_t x) {
+  x &= 0x55555555u;
+  x = (x ^ (x >> 1)) & 0x33333333u;
+  x = (x ^ (x >> 2)) & 0x0f0f0f0fu;
+  x = (x ^ (x >> 4)) & 0x00ff00ffu;
+  x = (x ^ (x >> 8)) & 0x0000ffffu;
+  return x;
+}
+
+// quantization tables (compressed_node.h:22-39): [0] border, [1] mid, [2] 1-mid, [3] 1-border
+__device__ __forceinline__ void init_lut(float* lut) {
+  const float border[8] = {0.000f, 0.005f, 0.010f, 0.050f, 0.100f, 0.200f, 0.400f, 0.600f};
+  const float mid[8] = {0.00f, 0.40f, 0.48f, 0.49f, 0.50f, 0.51f, 0.52f, 0.60f};
+  const int t = threadIdx.x;
+  if (t < 8) {
+    lut[t] = border[t];
+    lut[8 + t] = mid[t];
+    lut[16 + t] = 1.f - mid[t];
+    lut[24 + t] = 1.f - border[t];
+  }
+}
+
+struct TravRay {
+  float org[3], rdn[3], rdf[3];
+  float tnear, tfar;
+  int nu[3];  // 1 if the near plane along that axis is the upper bound
+};
+
+__device__ __forceinline__ void travray_init(TravRay& r, const float org[3], const float dir[3], float tnear, float tfar) {
+  const float ulp3 = 1.0f + 3.0f * FLT_EPSILON;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    r.org[k] = org[k];
+    r.rdn[k] = 1.0f / zero_fix(dir[k]);
+    r.rdf[k] = r.rdn[k] * ulp3;
+    r.nu[k] = r.rdn[k] >= 0.0f ? 0 : 1;
+  }
+  r.tnear = tnear;
+  r.tfar = tfar;
+}
+
+// one child of a 4-wide node; lo/hi per axis
+__device__ __forceinline__ bool slab(const TravRay& r, float lx, float ux, float ly, float uy, float lz, float uz,
+                                     float& tn, float& tf) {
+  const float tnx = ((r.nu[0] ? ux : lx) - r.org[0]) * r.rdn[0];
+  const float tny = ((r.nu[1] ? uy : ly) - r.org[1]) * r.rdn[1];
+  const float tnz = ((r.nu[2] ? uz : lz) - r.org[2]) * r.rdn[2];
+  const float tfx = ((r.nu[0] ? lx : ux) - r.org[0]) * r.rdf[0];
+  const float tfy = ((r.nu[1] ? ly : uy) - r.org[1]) * r.rdf[1];
+  const float tfz = ((r.nu[2] ? lz : uz) - r.org[2]) * r.rdf[2];
+  tn = sse_max(sse_max(tnx, tny), sse_max(tnz, r.tnear));
+  tf = sse_min(sse_min(tfx, tfy), sse_min(tfz, r.tfar));
+  return tn <= tf;
+}
+
+__device__ __forceinline__ void project3(const float* m /*row-major 3x3*/, const float a[3], float out[3]) {
+  const float X = m[0] * a[0] + m[1] * a[1] + m[2] * 1.0f;
+  const float Y = m[3] * a[0] + m[4] * a[1] + m[5] * 1.0f;
+  const float W = m[6] * a[0] + m[7] * a[1] + m[8] * 1.0f;
+  out[0] = X / W;
+  out[1] = Y / W;
+  out[2] = a[2];
+}
+
+__device__ __noinline__ void inverse3(const float* a, float* r) {
+  const float c00 = a[4] * a[8] - a[5] * a[7];
+  const float c10 = a[2] * a[7] - a[1] * a[8];
+  const float c20 = a[1] * a[5] - a[2] * a[4];
+  const float det = c00 * a[0] + c10 * a[3] + c20 * a[6];
+  const float id = 1.0f / det;
+  r[0] = c00 * id;
+  r[1] = c10 * id;
+  r[2] = c20 * id;
+  r[3] = (a[5] * a[6] - a[3] * a[8]) * id;
+  r[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+  r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  r[6] = (a[3] * a[7] - a[4] * a[6]) * id;
+  r[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+  r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+__device__ __forceinline__ float intersect_line(float p2x, float p2y, float p3x, float p3y, const float o[3], const float d[3]) {
+  const float vx = p2x - o[0], vy = p2y - o[1];
+  const float lx = p3x - p2x, ly = p3y - p2y;
+  const float t1 = (ly * vx - lx * vy) / (ly * d[0] - lx * d[1]);
+  const float t2 = (d[0] * vy - d[1] * vx) / (lx * d[1] - ly * d[0]);
+  return (t2 >= 0.f && t2 <= 1.f) ? t1 : __int_as_float(0x7fc00000);
+}
+
+__device__ __forceinline__ bool intersect_frustum(const float* box, const float o[3], const float d[3], float& t_near, float& t_far) {
+  const float rdz = 1.0f / zero_fix(d[2]);
+  const float org_rdz = o[2] * rdz;
+  const float t1z = box[0] * rdz - org_rdz;
+  const float t2z = box[1] * rdz - org_rdz;
+  const float t1x = intersect_line(box[2], box[3], box[6], box[7], o, d);
+  const float t2x = intersect_line(box[4], box[5], box[8], box[9], o, d);
+  const float t1y = intersect_line(box[2], box[3], box[4], box[5], o, d);
+  const float t2y = intersect_line(box[6], box[7], box[8], box[9], o, d);
+  const float near1 = fminf(fminf(t1x, t2x), fminf(t1y, t2y));
+  const float far1 = fmaxf(fmaxf(t1x, t2x), fmaxf(t1y, t2y));
+  t_near = fmaxf(fmaxf(fminf(t1z, t2z), near1), t_near);
+  t_far = fminf(fminf(fmaxf(t1z, t2z), far1), t_far);
+  return t_near <= t_far && near1 == near1 && far1 == far1;
+}
+
+__device__ __forceinline__ bool intersect_patch(uint32_t idx, float rcp_edges, float dz, float t1, float t2, float v0, float v1,
+                                                float v2, float v3, const float box[6], const float org[3], const float dir[3],
+                                                float& u, float& v, float& tt) {
+  const float px = t1 * dir[0] + org[0], py = t1 * dir[1] + org[1], pz = t1 * dir[2] + org[2];
+  const float p2x = t2 * dir[0] + org[0], p2y = t2 * dir[1] + org[1], p2z = t2 * dir[2] + org[2];
+  const float lenX = 1.0f / (box[3] - box[0]);
+  const float lenY = 1.0f / (box[4] - box[1]);
+  const float fx1 = (px - box[0]) * lenX;
+  const float fy1 = (py - box[1]) * lenY;
+  const float mx = (float)compact1by1(idx), my = (float)compact1by1(idx >> 1);
+  if (t2 - t1 < 1.0E-6f) {
+    tt = t1;
+    u = (fx1 + mx) * rcp_edges;
+    v = (fy1 + my) * rcp_edges;
+    return true;
+  }
+  const float fx2 = (p2x - box[0]) * lenX;
+  const float fy2 = (p2y - box[1]) * lenY;
+  const float dx1 = 1.f - fx1, dy1 = 1.f - fy1;
+  float z1 = v0 * dx1 * dy1 + v1 * fx1 * dy1 + v2 * dx1 * fy1 + v3 * fx1 * fy1;
+  const float dx2 = 1.f - fx2, dy2 = 1.f - fy2;
+  float z2 = v0 * dx2 * dy2 + v1 * fx2 * dy2 + v2 * dx2 * fy2 + v3 * fx2 * fy2;
+  if (pz >= z1 && pz <= z1 + dz) {
+    tt = t1;
+    u = (fx1 + mx) * rcp_edges;
+    v = (fy1 + my) * rcp_edges;
+    return true;
+  }
+  if (pz > z1 + dz) {
+    z1 += dz;
+    z2 += dz;
+  }
+  const float alpha = p2z - z2;
+  const float beta = z1 - pz;
+  const float t = (t1 * alpha + t2 * beta) / (alpha + beta);
+  const float d = (t - t1) / (t2 - t1);
+  const float fx = fx2 - fx1, fy = fy2 - fy1;
+  if (t < tt && t >= t1 && t <= t2) {
+    u = (fx * d + fx1 + mx) * rcp_edges;
+    v = (fy * d + fy1 + my) * rcp_edges;
+    tt = t;
+    return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool intersect_triangle(const float* v0, const float* v1, const float* v2, const float rorg[3],
+                                                   const float rdir[3], float tnear, float& tfar, float& ou, float& ov) {
+  const float a = v0[0] - v1[0], b = v0[1] - v1[1], c = v0[2] - v1[2];
+  const float d = v0[0] - v2[0], e = v0[1] - v2[1], f = v0[2] - v2[2];
+  const float g = rdir[0], h = rdir[1], i = rdir[2];
+  const float j = v0[0] - rorg[0], k = v0[1] - rorg[1], l = v0[2] - rorg[2];
+  float common1 = e * i - h * f;
+  float common2 = g * f - d * i;
+  float common3 = d * h - e * g;
+  const float M = 1.0f / (a * common1 + b * common2 + c * common3);
+  float beta = j * common1 + k * common2 + l * common3;
+  common1 = a * k - j * b;
+  common2 = j * c - a * l;
+  common3 = b * l - k * c;
+  float gamma = i * common1 + h * common2 + g * common3;
+  float tt = -(f * common1 + e * common2 + d * common3);
+  beta *= M;
+  gamma *= M;
+  tt *= M;
+  if (tt > 0 && tt < tfar && tt >= tnear)
+    if (beta > 0 && gamma > 0 && beta + gamma <= 1) {
+      tfar = tt;
+      ou = beta;
+      ov = gamma;
+      return true;
+    }
+  return false;
+}
+
+struct Hit {
+  float tfar, u, v;
+  uint32_t primID, geomID, block;
+};
+
+// per-thread work counters of the instrumented (STATS) kernel variant: SURVEY 8d's N_top, N_blk, N_cnode, N_cell
+struct Work {
+  uint32_t top_nodes, blocks, cnodes, cells;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// block traversal (CompressedBVHIntersector1::intersect)
+// ---------------------------------------------------------------------------------------------------------------
+template <int LEAF, bool STATS>
+__device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const float* __restrict__ lut, uint32_t block_index,
+                                                const float rorg[3], const float rdir[3], float ray_tnear, Hit& hit, Work& work) {
+  if (STATS) work.blocks++;
+  const uint8_t* blk = sc.blocks + (size_t)block_index * sc.block_stride;
+  const float4* h4 = reinterpret_cast<const float4*>(blk);
+  // 144-byte header = 9 x 16-byte read-only loads
+  float hdr[36];
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    const float4 q = __ldg(h4 + i);
+    hdr[4 * i + 0] = q.x; hdr[4 * i + 1] = q.y; hdr[4 * i + 2] = q.z; hdr[4 * i + 3] = q.w;
+  }
+  const float* space = hdr;       // [3*c+k]
+  const float* proj = hdr + 9;    // row-major
+  const float* box = hdr + 18;
+  const float uv0x = hdr[28], uv0y = hdr[29], uvEx = hdr[30], uvEy = hdr[31];
+  const float extent = hdr[32];
+  const uint32_t geomID = __float_as_uint(hdr[33]), primID = __float_as_uint(hdr[34]), root_word = __float_as_uint(hdr[35]);
+
+  float lOrg[3], lDir[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    lOrg[k] = __fmaf_rn(rorg[0], space[k], __fmaf_rn(rorg[1], space[3 + k], rorg[2] * space[6 + k]));
+    lDir[k] = __fmaf_rn(rdir[0], space[k], __fmaf_rn(rdir[1], space[3 + k], rdir[2] * space[6 + k]));
+  }
+  float near = ray_tnear;
+  float far = hit.tfar;
+  if (!intersect_frustum(box, lOrg, lDir, near, far)) return;
+
+  float pin[3], pout[3], org[3], tar[3], dir[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) pin[k] = lOrg[k] + lDir[k] * near;
+#pragma unroll
+  for (int k = 0; k < 3; k++) pout[k] = lOrg[k] + lDir[k] * far;
+  project3(proj, pin, org);
+  project3(proj, pout, tar);
+#pragma unroll
+  for (int k = 0; k < 3; k++) dir[k] = tar[k] - org[k];
+  float zFactor = 0.f;
+  bool special = false;
+  float tfar = 0.f;
+  const float g_epsilon = 1.0E-4f;
+  const float ax = fabsf(dir[0]), ay = fabsf(dir[1]), az = fabsf(dir[2]);
+  if (ax < g_epsilon && ay < g_epsilon && az < g_epsilon) {
+    dir[2] = copysignf(1.f, lDir[2]);
+    org[2] -= dir[2];
+    zFactor = FLT_MAX;
+    tfar = FLT_MAX;
+  } else if (az < g_epsilon) {
+    special = true;
+    const float d2 = (dir[0] * dir[0] + dir[1] * dir[1]) + (dir[2] * dir[2] + 0.f);
+    tfar = sqrtf(d2);
+    const float rl = 1.0f / sqrtf(d2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) dir[k] = dir[k] * rl;
+  } else {
+    const float d2 = (dir[0] * dir[0] + dir[1] * dir[1]) + (dir[2] * dir[2] + 0.f);
+    const float rl = 1.0f / sqrtf(d2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) dir[k] = dir[k] * rl;
+    zFactor = lDir[2] / dir[2];
+    tfar = (hit.tfar - near) * zFactor;
+  }
+
+  TravRay tr;
+  travray_init(tr, org, dir, 0.f, tfar);
+
+  unsigned stack[16];
+  float boxStack[16][6];
+  int sp = 0;
+  stack[0] = 0;
+  boxStack[0][0] = -1.f; boxStack[0][1] = -1.f; boxStack[0][2] = box[0];
+  boxStack[0][3] = 1.f;  boxStack[0][4] = 1.f;  boxStack[0][5] = box[1];
+  float tNear[4] = {0.f, 0.f, 0.f, 0.f}, tFar[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t elems = sc.elems;
+  const uint32_t* node_words = reinterpret_cast<const uint32_t*>(blk + ECB_BLOCK_NODES_OFFSET);
+
+  while (sp >= 0) {
+    const unsigned curr = stack[sp];
+    float pBox[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pBox[k] = boxStack[sp][k];
+    sp--;
+
+    if (curr >= elems) {
+      const unsigned idx = curr - elems;
+      if (STATS) work.cells++;
+      if (LEAF == 1) {
+        const float box_near = (idx & 2) ? ((idx & 1) ? tNear[3] : tNear[2]) : ((idx & 1) ? tNear[1] : tNear[0]);
+        if (box_near >= tfar) continue;
+        const float box_far = (idx & 2) ? ((idx & 1) ? tFar[3] : tFar[2]) : ((idx & 1) ? tFar[1] : tFar[0]);
+        const float dimZ = pBox[5] - pBox[2];
+        const float range = (1.f + 2.f * extent) * dimZ;
+        const float dz = 0.0625f * range;
+        const float offset = pBox[2] - dimZ * extent;
+        const float rcpF = 0.0625f * range;
+        const uint32_t zz = __ldg(reinterpret_cast<const unsigned short*>(blk + sc.leaf_offset) + idx);
+        const unsigned z12 = zz & 0xff, z34 = zz >> 8;
+        const float z1 = offset + rcpF * (float)((z12 & 0xf0) >> 4);
+        const float z2 = offset + rcpF * (float)(z12 & 0x0f);
+        const float z3 = offset + rcpF * (float)((z34 & 0xf0) >> 4);
+        const float z4 = offset + rcpF * (float)(z34 & 0x0f);
+        float u, v, t = tfar;
+        if (intersect_patch(idx, sc.rcp_edges, dz, box_near, box_far, z1, z2, z3, z4, pBox, org, dir, u, v, t)) {
+          float tw;
+          if (special) {
+            float ip[9], q[3], p[3];
+            inverse3(proj, ip);
+#pragma unroll
+            for (int k = 0; k < 3; k++) q[k] = org[k] + dir[k] * t;
+            project3(ip, q, p);
+            const float ex = p[0] - lOrg[0], ey = p[1] - lOrg[1], ez = p[2] - lOrg[2];
+            tw = sqrtf((ex * ex + ey * ey) + (ez * ez + 0.f));
+          } else {
+            tw = t / zFactor + near;
+          }
+          hit.u = uv0x + u * uvEx;
+          hit.v = uv0y + v * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+          tfar = t;
+          hit.tfar = tw;
+        }
+      } else if (LEAF == 0) {
+        const unsigned x = compact1by1(idx), y = compact1by1(idx >> 1);
+        const float* grid = reinterpret_cast<const float*>(blk + sc.leaf_offset);
+        const unsigned g0 = y * sc.grid_width + x, g2 = g0 + sc.grid_width;
+        float V[4][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          V[0][k] = __ldg(grid + 3 * g0 + k);
+          V[1][k] = __ldg(grid + 3 * g0 + 3 + k);
+          V[2][k] = __ldg(grid + 3 * g2 + k);
+          V[3][k] = __ldg(grid + 3 * g2 + 3 + k);
+        }
+        float tf = hit.tfar, uu = 0.f, vv = 0.f;
+        const bool hit1 = intersect_triangle(V[0], V[1], V[2], rorg, rdir, ray_tnear, tf, uu, vv);
+        const bool hit2 = intersect_triangle(V[3], V[2], V[1], rorg, rdir, ray_tnear, tf, uu, vv);
+        if (hit1 || hit2) {
+          float lu, lv;
+          if (hit2) {
+            lu = ((float)x + (1.f - uu)) * sc.rcp_edges;
+            lv = ((float)y + (1.f - vv)) * sc.rcp_edges;
+          } else {
+            lu = ((float)x + uu) * sc.rcp_edges;
+            lv = ((float)y + vv) * sc.rcp_edges;
+          }
+          hit.tfar = tf;
+          hit.u = uv0x + lu * uvEx;
+          hit.v = uv0y + lv * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+        }
+      } else {
+        const float is = (idx & 2) ? ((idx & 1) ? tNear[3] : tNear[2]) : ((idx & 1) ? tNear[1] : tNear[0]);
+        if (is <= tfar) {
+          const float mx = (float)compact1by1(idx), my = (float)compact1by1(idx >> 1);
+          const float x = (((org[0] + dir[0] * is) - pBox[0]) / (pBox[3] - pBox[0]) + mx) * sc.rcp_edges;
+          const float y = (((org[1] + dir[1] * is) - pBox[1]) / (pBox[4] - pBox[1]) + my) * sc.rcp_edges;
+          float tw;
+          if (special) {
+            float ip[9], q[3], p[3];
+            inverse3(proj, ip);
+#pragma unroll
+            for (int k = 0; k < 3; k++) q[k] = org[k] + dir[k] * is;
+            project3(ip, q, p);
+            const float ex = p[0] - lOrg[0], ey = p[1] - lOrg[1], ez = p[2] - lOrg[2];
+            tw = sqrtf((ex * ex + ey * ey) + (ez * ez + 0.f));
+          } else {
+            tw = is / zFactor + near;
+          }
+          hit.u = uv0x + x * uvEx;
+          hit.v = uv0y + y * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+          tfar = is;
+          hit.tfar = tw;
+        }
+      }
+      continue;
+    }
+
+    // inner node: decode (Node::getNode), test 4 children, push the hit ones nearest-on-top
+    const unsigned next = curr * 4 + 1;
+    if (STATS) work.cnodes++;
+    const uint32_t w = curr == 0 ? root_word : __ldg(node_words + (curr - 1));
+    const unsigned xz = w & 0xff, xb = (w >> 8) & 0xff, yz = (w >> 16) & 0xff, yb = w >> 24;
+    const float dimX = pBox[3] - pBox[0], dimY = pBox[4] - pBox[1], dimZ = pBox[5] - pBox[2];
+    const float lx02 = lut[(xz & 0xe0) >> 5] * dimX + pBox[0];
+    const float lx13 = lut[8 + ((xz & 0x1c) >> 2)] * dimX + pBox[0];
+    const float ux02 = lut[16 + ((xb & 0xe0) >> 5)] * dimX + pBox[0];
+    const float ux13 = lut[24 + ((xb & 0x1c) >> 2)] * dimX + pBox[0];
+    const float ly01 = lut[(yz & 0xe0) >> 5] * dimY + pBox[1];
+    const float ly23 = lut[8 + ((yz & 0x1c) >> 2)] * dimY + pBox[1];
+    const float uy01 = lut[16 + ((yb & 0xe0) >> 5)] * dimY + pBox[1];
+    const float uy23 = lut[24 + ((yb & 0x1c) >> 2)] * dimY + pBox[1];
+    const float lz = (0.25f * (float)(xz & 3)) * dimZ + pBox[2];
+    const float uz = (1.f - 0.25f * (float)(yz & 3)) * dimZ + pBox[2];
+
+    unsigned mask = 0;
+    if (slab(tr, lx02, ux02, ly01, uy01, lz, uz, tNear[0], tFar[0])) mask |= 1;
+    if (slab(tr, lx13, ux13, ly01, uy01, lz, uz, tNear[1], tFar[1])) mask |= 2;
+    if (slab(tr, lx02, ux02, ly23, uy23, lz, uz, tNear[2], tFar[2])) mask |= 4;
+    if (slab(tr, lx13, ux13, ly23, uy23, lz, uz, tNear[3], tFar[3])) mask |= 8;
+    if (mask == 0) continue;
+
+    // stack position of child r = sp+1 + #(hit children that must be popped after it)   (compressed.h:668-749)
+    const int n = __popc(mask);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (!(mask & (1u << r))) continue;
+      int below = 0;  // number of other hit children popped AFTER r  (farther, or equal and higher index)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (q == r || !(mask & (1u << q))) continue;
+        const bool r_first = (q > r) ? (tNear[r] <= tNear[q]) : (tNear[r] < tNear[q]);
+        below += r_first ? 1 : 0;
+      }
+      const int pos = sp + 1 + below;
+      stack[pos] = next + r;
+      boxStack[pos][0] = (r & 1) ? lx13 : lx02;
+      boxStack[pos][1] = (r & 2) ? ly23 : ly01;
+      boxStack[pos][2] = lz;
+      boxStack[pos][3] = (r & 1) ? ux13 : ux02;
+      boxStack[pos][4] = (r & 2) ? uy23 : uy01;
+      boxStack[pos][5] = uz;
+    }
+    sp += n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// top-level traversal
+// ---------------------------------------------------------------------------------------------------------------
+struct TopNodeRegs {
+  float b[6][4];
+  uint32_t child[4];
+};
+
+__device__ __forceinline__ void load_top(const EcbDeviceScene& sc, uint32_t index, TopNodeRegs& n) {
+  const float4* p = reinterpret_cast<const float4*>(sc.top + index);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float4 q = __ldg(p + i);
+    n.b[i][0] = q.x; n.b[i][1] = q.y; n.b[i][2] = q.z; n.b[i][3] = q.w;
+  }
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(p + 6));
+  n.child[0] = c.x; n.child[1] = c.y; n.child[2] = c.z; n.child[3] = c.w;
+}
+
+__device__ __forceinline__ unsigned top_test(const TopNodeRegs& n, const TravRay& tr, float tNear[4]) {
+  unsigned mask = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float tf;
+    if (slab(tr, n.b[0][i], n.b[1][i], n.b[2][i], n.b[3][i], n.b[4][i], n.b[5][i], tNear[i], tf)) mask |= 1u << i;
+  }
+  return mask;
+}
+
+__device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, uint32_t& db) {
+  // if (b.dist < a.dist) xchg(b,a)   (stack_item.h:40-60)
+  if (db < da) {
+    const uint32_t tr = ra, td = da;
+    ra = rb; da = db;
+    rb = tr; db = td;
+  }
+}
+
+template <int LEAF, bool STATS>
+__device__ __forceinline__ void trace_closest(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
+                                              float ray_tnear, Hit& hit, Work& work) {
+  uint32_t stack_ref[ECB_MAX_TOP_STACK];
+  uint32_t stack_dist[ECB_MAX_TOP_STACK];
+  int sp = 1;
+  stack_ref[0] = sc.root;
+  stack_dist[0] = 0xff800000u;
+  TravRay tr;
+  travray_init(tr, org, dir, sse_max(ray_tnear, 0.0f), sse_max(hit.tfar, 0.0f));
+
+  while (sp > 0) {
+    sp--;
+    uint32_t cur = stack_ref[sp];
+    if (__uint_as_float(stack_dist[sp]) > hit.tfar) continue;
+    bool popped = false;
+    while (!(cur & ECB_REF_LEAF)) {
+      TopNodeRegs n;
+      load_top(sc, cur, n);
+      if (STATS) work.top_nodes++;
+      float tNear[4];
+      const unsigned mask = top_test(n, tr, tNear);
+      if (mask == 0) { popped = true; break; }
+      // traverseClosestHit (bvh_traverser1.h:436-506)
+      uint32_t c[4], d[4];
+      int nh = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (mask & (1u << r)) { c[nh] = n.child[r]; d[nh] = __float_as_uint(tNear[r]); nh++; }
+      if (nh == 1) { cur = c[0]; continue; }
+      if (nh == 2) {
+        if (d[0] < d[1]) { stack_ref[sp] = c[1]; stack_dist[sp] = d[1]; sp++; cur = c[0]; }
+        else             { stack_ref[sp] = c[0]; stack_dist[sp] = d[0]; sp++; cur = c[1]; }
+        continue;
+      }
+      if (nh == 3) {
+        // items pushed in order c0,c1,c2 ; sort(s1=top(c2), s2=c1, s3=c0)
+        uint32_t r1 = c[2], d1 = d[2], r2 = c[1], d2 = d[1], r3 = c[0], d3 = d[0];
+        cswap(r1, d1, r2, d2);
+        cswap(r2, d2, r3, d3);
+        cswap(r1, d1, r2, d2);
+        stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
+        stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
+        cur = r1;
+        continue;
+      }
+      {
+        uint32_t r1 = c[3], d1 = d[3], r2 = c[2], d2 = d[2], r3 = c[1], d3 = d[1], r4 = c[0], d4 = d[0];
+        cswap(r1, d1, r2, d2);
+        cswap(r3, d3, r4, d4);
+        cswap(r1, d1, r3, d3);
+        cswap(r2, d2, r4, d4);
+        cswap(r2, d2, r3, d3);
+        stack_ref[sp] = r4; stack_dist[sp] = d4; sp++;
+        stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
+        stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
+        cur = r1;
+      }
+    }
+    if (popped || cur == ECB_REF_EMPTY) continue;
+    block_intersect<LEAF, STATS>(sc, lut, cur & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+    tr.tfar = hit.tfar;
+  }
+}
+
+// any-hit: the first block whose world box the ray segment overlaps occludes (compressed.h:754-756 returns true)
+__device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float org[3], const float dir[3], float ray_tnear,
+                                          float ray_tfar) {
+  uint32_t stack_ref[ECB_MAX_TOP_STACK];
+  int sp = 1;
+  stack_ref[0] = sc.root;
+  TravRay tr;
+  travray_init(tr, org, dir, sse_max(ray_tnear, 0.0f), sse_max(ray_tfar, 0.0f));
+  while (sp > 0) {
+    sp--;
+    uint32_t cur = stack_ref[sp];
+    bool popped = false;
+    while (!(cur & ECB_REF_LEAF)) {
+      TopNodeRegs n;
+      load_top(sc, cur, n);
+      float tNear[4];
+      const unsigned mask = top_test(n, tr, tNear);
+      if (mask == 0) { popped = true; break; }
+      int last = -1;
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (mask & (1u << r)) {
+          if (last >= 0) stack_ref[sp++] = n.child[last];
+          last = r;
+        }
+      cur = n.child[last];
+    }
+    if (popped || cur == ECB_REF_EMPTY) continue;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels: one thread per ray, grid-stride persistent loop, AoS RTCRayHit / RTCRay in place
+// ---------------------------------------------------------------------------------------------------------------
+template <int LEAF, bool STATS>
+__global__ void __launch_bounds__(ECB_THREADS) ecb_intersect_kernel(EcbDeviceScene sc, uint8_t* __restrict__ rays, uint64_t M,
+                                                                    size_t stride, uint32_t instID,
+                                                                    uint32_t* __restrict__ block_out,
+                                                                    unsigned long long* __restrict__ counters) {
+  __shared__ float lut[32];
+  init_lut(lut);
+  __syncthreads();
+  Work work = {0u, 0u, 0u, 0u};
+  uint32_t n_rays = 0, n_hits = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint8_t* rp = rays + i * stride;
+    const float4 r0 = *reinterpret_cast<const float4*>(rp);       // org.xyz, tnear
+    const float4 r1 = *reinterpret_cast<const float4*>(rp + 16);  // dir.xyz, time
+    const float tfar_in = *reinterpret_cast<const float*>(rp + 32);
+    if (block_out) block_out[i] = 0xFFFFFFFFu;
+    if (r0.w > tfar_in) continue;  // inactive stream ray
+    const float org[3] = {r0.x, r0.y, r0.z};
+    const float dir[3] = {r1.x, r1.y, r1.z};
+    Hit hit;
+    hit.tfar = tfar_in;
+    hit.block = 0xFFFFFFFFu;
+    hit.u = hit.v = 0.f;
+    hit.primID = hit.geomID = 0xFFFFFFFFu;
+    if (sc.root != ECB_REF_EMPTY) trace_closest<LEAF, STATS>(sc, lut, org, dir, r0.w, hit, work);
+    if (STATS) n_rays++;
+    if (hit.block != 0xFFFFFFFFu) {
+      if (STATS) n_hits++;
+      *reinterpret_cast<float*>(rp + 32) = hit.tfar;
+      *reinterpret_cast<float4*>(rp + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
+      *reinterpret_cast<float4*>(rp + 64) =
+          make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(instID));
+      if (block_out) block_out[i] = hit.block;
+    }
+  }
+  if (STATS) {
+    atomicAdd(counters + 0, (unsigned long long)n_rays);
+    atomicAdd(counters + 1, (unsigned long long)work.top_nodes);
+    atomicAdd(counters + 2, (unsigned long long)work.blocks);
+    atomicAdd(counters + 3, (unsigned long long)work.cnodes);
+    atomicAdd(counters + 4, (unsigned long long)work.cells);
+    atomicAdd(counters + 5, (unsigned long long)n_hits);
+  }
+}
+
+__global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, uint8_t* __restrict__ rays, uint64_t M,
+                                                                   size_t stride) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint8_t* rp = rays + i * stride;
+    const float4 r0 = *reinterpret_cast<const float4*>(rp);
+    const float4 r1 = *reinterpret_cast<const float4*>(rp + 16);
+    const float tfar_in = *reinterpret_cast<const float*>(rp + 32);
+    if (r0.w > tfar_in) continue;
+    if (tfar_in < 0.0f) continue;  // bvh_intersector1.cpp:133
+    const float org[3] = {r0.x, r0.y, r0.z};
+    const float dir[3] = {r1.x, r1.y, r1.z};
+    if (sc.root != ECB_REF_EMPTY && trace_any(sc, org, dir, r0.w, tfar_in))
+      *reinterpret_cast<float*>(rp + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+static int g_grid_cache[16] = {0};
+
+static int grid_for(uint64_t M, int device) {
+  if (device < 0 || device >= 16) device = 0;
+  if (!g_grid_cache[device]) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    g_grid_cache[device] = sms;
+  }
+  const uint64_t need = (M + ECB_THREADS - 1) / ECB_THREADS;
+  const uint64_t cap = (uint64_t)g_grid_cache[device] * ECB_BLOCKS_PER_SM;
+  return (int)(need < cap ? (need ? need : 1) : cap);
+}
+
+cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, void* d_rayhit, uint64_t M, size_t stride, uint32_t instID,
+                                 uint32_t* d_block_out, unsigned long long* d_counters, cudaStream_t stream) {
+  if (M == 0) return cudaSuccess;
+  const int grid = grid_for(M, device);
+  uint8_t* rays = static_cast<uint8_t*>(d_rayhit);
+#define ECB_LAUNCH(LEAF)                                                                                                  \
+  if (d_counters)                                                                                                         \
+    ecb_intersect_kernel<LEAF, true><<<grid, ECB_THREADS, 0, stream>>>(sc, rays, M, stride, instID, d_block_out, d_counters); \
+  else                                                                                                                    \
+    ecb_intersect_kernel<LEAF, false><<<grid, ECB_THREADS, 0, stream>>>(sc, rays, M, stride, instID, d_block_out, nullptr)
+  switch (sc.leaf_kind) {
+    case 0: ECB_LAUNCH(0); break;
+    case 1: ECB_LAUNCH(1); break;
+    default: ECB_LAUNCH(2); break;
+  }
+#undef ECB_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, void* d_ray, uint64_t M, size_t stride, cudaStream_t stream) {
+  if (M == 0) return cudaSuccess;
+  const int grid = grid_for(M, device);
+  ecb_occluded_kernel<<<grid, ECB_THREADS, 0, stream>>>(sc, static_cast<uint8_t*>(d_ray), M, stride);
+  return cudaGetLastError();
+}
+

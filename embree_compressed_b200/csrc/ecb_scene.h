@@ -1,0 +1,32 @@
+// ecb_scene.h -- host-side scene object behind the opaque ecbScene handle.
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ecb200.h"
+#include "ecb_format.h"
+
+struct ecbScene {
+  // converted scene (host copy, pointer-free)
+  std::vector<EcbTopNode> top;
+  std::vector<uint8_t> blocks;
+  ecbSceneInfo info{};
+  uint32_t root = ECB_REF_EMPTY;
+  uint32_t block_stride = 0, leaf_offset = 0, elems = 0, grid_width = 0;
+  float rcp_edges = 0.f;
+
+  // device residency
+  std::mutex mutex;
+  int device = -1;
+  void* d_top = nullptr;
+  void* d_blocks = nullptr;
+  EcbDeviceScene dev{};
+
+  // staging for the host-buffer entry points (lazily created, per scene)
+  struct Staging* staging = nullptr;
+};
+
+void ecb_set_error(const std::string& msg);
+ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out);

@@ -1,0 +1,137 @@
+/* ecb200.h -- C ABI of the B200-native compressed-BVH traversal plugin (libecb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of lispbub/embree-compressed: ray traversal and
+ * intersection over the compressed subdivision/displacement BVH ("cBVH").  The scene is still
+ * built by the reference's CPU builder; the host application (the reference's rtcCommitScene, or
+ * the embree3-compatible shim in embree_compressed_b200/csrc/rtcore_shim.cpp) hands the committed
+ * BVH4 to ecbSceneImportBVH4() once and then routes its ray queries to the ecbIntersect* /
+ * ecbOccluded* entry points below.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * All traversal runs in hand-written sm_100a CUDA kernels.  There is no CPU fallback: every
+ * traversal entry point returns ECB_ERROR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   ecbSceneImportBVH4   <- hand-off after Scene::commit_task, kernels/common/scene.cpp:632-697;
+ *                           input = BVH4::root of the accel created by BVH4Factory::BVH4SubdivPatch1c{Grid,Leaf,Box}
+ *                           (kernels/bvh/bvh4_factory.cpp:1653-1675), blocks = CompressedBVH (kernels/geometry/compressed.h:408-433)
+ *   ecbIntersect1        <- rtcIntersect1   kernels/common/rtcore.cpp:287-304
+ *   ecbIntersect16       <- rtcIntersect16  kernels/common/rtcore.cpp:370-401   (segfaults in the reference on this accel)
+ *   ecbIntersect1M       <- rtcIntersect1M  kernels/common/rtcore.cpp:403-432   (same)
+ *   ecbOccluded1         <- rtcOccluded1    kernels/common/rtcore.cpp:541-555
+ *   ecbOccluded1M        <- rtcOccluded1M   kernels/common/rtcore.cpp:656-683
+ *   per-ray semantics    <- BVHNIntersector1<4,BVH_AN1,true,SubdivPatch1c*Intersector1>::intersect/occluded
+ *                           kernels/bvh/bvh_intersector1.cpp:40-209 + CompressedBVHIntersector1 kernels/geometry/compressed.h:454-756
+ */
+#ifndef ECB200_H
+#define ECB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECB_API __attribute__((visibility("default")))
+
+/* error codes: values follow enum RTCError (include/embree3/rtcore_device.h) where one exists */
+typedef enum ecbError {
+  ECB_SUCCESS = 0,
+  ECB_ERROR_UNKNOWN = 1,
+  ECB_ERROR_INVALID_ARGUMENT = 2,
+  ECB_ERROR_INVALID_OPERATION = 3,
+  ECB_ERROR_OUT_OF_MEMORY = 4,
+  ECB_ERROR_UNSUPPORTED = 5, /* RTC_ERROR_UNSUPPORTED_CPU slot: scene uses a feature outside the hot path */
+  ECB_ERROR_NO_DEVICE = 100, /* no usable CUDA device / kernel image: the path fails loudly, it never falls back */
+  ECB_ERROR_CUDA = 101
+} ecbError;
+
+/* leaf flavour of the committed accel: which reference factory built it */
+typedef enum ecbLeafKind {
+  ECB_LEAF_GRID = 0, /* bvh4.compressed.grid : full-precision vertex grid, exact micro-triangles */
+  ECB_LEAF_LEAF = 1, /* bvh4.compressed.leaf : 2-byte "pizza box" bilinear slabs             */
+  ECB_LEAF_BOX = 2   /* bvh4.compressed.box  : voxel leaves                                   */
+} ecbLeafKind;
+
+typedef struct ecbScene ecbScene; /* opaque */
+
+/* What the host hands over at commit time. */
+typedef struct ecbImportDesc {
+  const void* base;        /* added to every reference pointer: NULL for live reference memory in this process,
+                              start of the buffer for a relocated image (oracle/rimg.h) */
+  uint64_t root;           /* BVH4::root NodeRef (tagged pointer, kernels/bvh/bvh.h:150-400,1492) */
+  uint32_t leaf_kind;      /* ecbLeafKind */
+  uint32_t proj_col_major; /* storage order of Eigen::Matrix3f CompressedBVH::proj in the host build (1 = Eigen default) */
+  uint32_t subdiv_level;   /* S of rtcSetSceneLevels (informational: bytes per micro-triangle) */
+  uint32_t comp_level;     /* C of rtcSetSceneLevels; verified against every block's `elems` */
+  float bounds[6];         /* scene bounds (rtcGetSceneBounds), lower xyz then upper xyz; informational */
+} ecbImportDesc;
+
+typedef struct ecbSceneInfo {
+  uint32_t leaf_kind, subdiv_level, comp_level;
+  uint32_t n_top_nodes, n_blocks, top_depth;
+  uint32_t block_stride;       /* bytes per block in the device format */
+  uint32_t top_node_bytes;     /* bytes per top-level node in the device format */
+  uint64_t device_bytes;       /* total bytes of the device scene */
+  uint64_t reference_bytes;    /* bytes the same accel occupies in the reference layout (nodes+blocks, no allocator slack) */
+  uint64_t micro_triangles;    /* 2 * 4^C * n_blocks */
+  float bounds[6];
+  int32_t device;              /* CUDA device ordinal the scene is resident on, -1 if host only */
+} ecbSceneInfo;
+
+/* ---- scene ---------------------------------------------------------------------------------------- */
+/* Converts the reference's committed compressed BVH4 into the device scene format (host work only). */
+ECB_API ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out);
+/* Convenience: import from an RIMG file / buffer (header carries root, leaf kind, S, C, bounds). */
+ECB_API ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out);
+ECB_API ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out);
+/* Native serialisation of the converted scene (the reference has none). */
+ECB_API ecbError ecbSceneSave(const ecbScene* scene, const char* path);
+ECB_API ecbError ecbSceneLoad(const char* path, ecbScene** scene_out);
+/* Makes the scene resident on CUDA device `device` (cudaMalloc + copy).  Traversal calls do this lazily on device 0. */
+ECB_API ecbError ecbSceneUpload(ecbScene* scene, int device);
+ECB_API ecbError ecbSceneGetInfo(const ecbScene* scene, ecbSceneInfo* info);
+ECB_API void ecbSceneRelease(ecbScene* scene);
+
+/* ---- traversal, host buffers (drop-in semantics of the rtc* calls named above) ---------------------
+ * rayhit / ray point to RTCRayHit (80 B) / RTCRay (48 B) structs, include/embree3/rtcore_ray.h:26-64, mutated in
+ * place exactly like the reference does: on a hit tfar,Ng,u,v,primID,geomID,instID are overwritten, on a miss
+ * nothing is written; occluded sets tfar=-inf.  Stream rays with tnear > tfar are inactive.  instID is what
+ * RTCIntersectContext::instID[0] holds (RTC_INVALID_GEOMETRY_ID at top level). */
+ECB_API ecbError ecbIntersect1(ecbScene* scene, uint32_t instID, void* rayhit);
+ECB_API ecbError ecbIntersect1M(ecbScene* scene, uint32_t instID, void* rayhit, uint32_t M, size_t byteStride);
+ECB_API ecbError ecbIntersect16(const int* valid, ecbScene* scene, uint32_t instID, void* rayhit16);
+ECB_API ecbError ecbOccluded1(ecbScene* scene, uint32_t instID, void* ray);
+ECB_API ecbError ecbOccluded1M(ecbScene* scene, uint32_t instID, void* ray, uint32_t M, size_t byteStride);
+
+/* ---- traversal, device-resident buffers (extension; what the benchmark's `value` times) ------------
+ * d_rayhit / d_ray are device pointers on the scene's device; stream is a cudaStream_t (NULL = default stream).
+ * Asynchronous: returns after the launch. */
+ECB_API ecbError ecbIntersectDevice(ecbScene* scene, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride, void* stream);
+ECB_API ecbError ecbOccludedDevice(ecbScene* scene, uint32_t instID, void* d_ray, uint64_t M, size_t byteStride, void* stream);
+/* Like ecbIntersectDevice, and additionally writes, per ray, the index of the block that produced the final hit
+ * (0xFFFFFFFF for a miss / unchanged) to d_block_out[M] when it is not NULL.  Used by the benchmark's bounce-ray
+ * generator (the reference returns a dummy Ng, compressed.h:574, so normals must come from the block frame). */
+ECB_API ecbError ecbIntersectDeviceEx(ecbScene* scene, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride,
+                                      uint32_t* d_block_out, void* stream);
+/* Instrumented variant (same results, slower): adds this launch's work to d_counters[6] = {rays traced, top-level
+ * nodes tested, blocks entered, quantized nodes decoded, leaf cells tested, hits} -- the per-ray counts the roofline's
+ * algorithmic-bytes figure is built from.  d_counters is a device pointer the caller zeroes. */
+ECB_API ecbError ecbIntersectDeviceStats(ecbScene* scene, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride,
+                                         uint64_t* d_counters, void* stream);
+/* World-space unit normal of a block's local frame (third row of CompressedBVH::space), 3 floats per block, host copy. */
+ECB_API ecbError ecbSceneBlockNormals(const ecbScene* scene, float* normals_out, size_t capacity_floats);
+
+/* Pinned host staging memory for callers that want the fast DMA path on the host-buffer entry points. */
+ECB_API ecbError ecbHostAlloc(void** ptr, size_t bytes);
+ECB_API void ecbHostFree(void* ptr);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+ECB_API uint64_t ecbLaunchCount(void);
+ECB_API const char* ecbErrorString(ecbError e);
+ECB_API const char* ecbLastErrorMessage(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECB200_H */

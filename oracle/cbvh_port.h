@@ -1,0 +1,75 @@
+/* oracle/cbvh_port.h -- CPU restatement ("port") of the reference's compressed-BVH traversal.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this.  The product (embree_compressed_b200/) never does.
+ *
+ * The port is plain scalar C over the REFERENCE's own committed memory layout (128-byte BVH4
+ * AlignedNodes with tagged 64-bit child refs, 184-byte CompressedBVH block headers followed by
+ * 4-byte quantized nodes and 2-byte leaf heights / 12-byte grid vertices).  Every address is
+ * `base + (ref & ~15)`: base = 0 walks a live reference scene in this process, base = buffer
+ * walks a relocated image (oracle "RIMG", see rimg.h).
+ *
+ * Pinned against: the compiled reference itself (oracle/_ref, rtcIntersect1 / rtcOccluded1 on the
+ * same rays) and the golden fixtures under tests/golden/ that were generated from it.  The
+ * reference's own tests hold no vectors for this path.
+ *
+ * Arithmetic: fp32, no contraction (-ffp-contract=off), IEEE division / sqrt where the
+ * reference uses rcpss/rsqrtss + one Newton step (common/math/math.h:60-97), fmaf() only where
+ * the reference's AVX2 build has an explicit FMA (xfmPoint/xfmVector: common/math/linearspace3.h:168-169).
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { CBVH_LEAF_GRID = 0, CBVH_LEAF_LEAF = 1, CBVH_LEAF_BOX = 2 };
+
+typedef struct cbvh_scene {
+  const uint8_t* base;      /* 0 for live reference memory, image payload otherwise */
+  uint64_t root;            /* BVH4 NodeRef (kernels/bvh/bvh.h:150-400) */
+  int32_t leaf_kind;        /* CBVH_LEAF_* : which CompressedBVHIntersector1 variant (compressed.h:777-779) */
+  int32_t proj_col_major;   /* storage order of Eigen::Matrix3f proj in the block header */
+} cbvh_scene;
+
+/* include/embree3/rtcore_ray.h:26-64 */
+typedef struct cbvh_ray {
+  float org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, time, tfar;
+  uint32_t mask, id, flags;
+} cbvh_ray;
+typedef struct cbvh_hit {
+  float Ng_x, Ng_y, Ng_z, u, v;
+  uint32_t primID, geomID, instID;
+} cbvh_hit;
+typedef struct cbvh_rayhit {
+  cbvh_ray ray;
+  cbvh_hit hit;
+} cbvh_rayhit;
+
+/* per-ray work counters (N_top, N_blk, N_cnode, N_cell) */
+typedef struct cbvh_stats {
+  uint64_t rays, top_nodes, blocks, cnodes, cells, hits;
+} cbvh_stats;
+
+/* optional second-nearest-candidate record used by the tests to compute the near-tie set */
+typedef struct cbvh_candidates {
+  float t_best, t_second;        /* nearest and second nearest accepted leaf candidates (world t), +inf if none */
+  uint32_t prim_best, prim_second;
+} cbvh_candidates;
+
+void cbvh_intersect1(const cbvh_scene* scene, cbvh_rayhit* rh, uint32_t instID, cbvh_stats* stats);
+void cbvh_occluded1(const cbvh_scene* scene, cbvh_ray* ray, cbvh_stats* stats);
+
+/* all rays of a strided array (inactive rays tnear>tfar skipped), nthreads pthreads; returns wall seconds */
+double cbvh_intersectN(const cbvh_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
+double cbvh_occludedN(const cbvh_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
+
+/* Like cbvh_intersect1 but never shrinks the search interval: records the two nearest leaf candidates. */
+void cbvh_candidates1(const cbvh_scene* scene, const cbvh_rayhit* rh, cbvh_candidates* out);
+void cbvh_candidatesN(const cbvh_scene* scene, const void* rayhits, size_t n, size_t stride, int nthreads, cbvh_candidates* out);
+
+#ifdef __cplusplus
+}
+#endif

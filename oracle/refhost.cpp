@@ -8,6 +8,7 @@
 //       prove the hard-coded layout (include/ecb200.h) matches the compiled reference.
 // Everything else goes through the public rtc* API.
 #include "refhost.h"
+#include "rimg.h"
 
 #include <embree3/rtcore.h>
 
@@ -49,7 +50,7 @@ std::map<std::string, RTCDevice> g_devices;
 
 RTCDevice get_device(const std::string& leaf, int threads) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  std::string accel = leaf == "eager" ? "bvh4.grid.eager" : "bvh4.compressed." + leaf;
+  std::string accel = leaf.compare(0, 5, "eager") == 0 ? "bvh4.grid." + leaf : "bvh4.compressed." + leaf;
   // set_affinity=0: with the internal tasking system the default pins the calling thread (kernels/common/state.cpp:123-128)
   std::string cfg = "subdiv_accel=" + accel + ",set_affinity=0,start_threads=0";
   if (threads > 0) cfg += ",threads=" + std::to_string(threads);
@@ -88,6 +89,8 @@ struct RefScene {
   RTCDevice device = nullptr;
   RTCScene scene = nullptr;
   std::vector<std::unique_ptr<Mesh>> meshes;  // shared buffers must outlive the scene
+  int leaf_kind = -1;                          // 0 grid, 1 leaf, 2 box (-1: stock accel)
+  unsigned S = 0, C = 0;
 };
 
 REF_API void ref_layout(RefLayout* o) {
@@ -131,6 +134,12 @@ REF_API RefScene* ref_scene_new(const char* leaf, unsigned S, unsigned C, int bu
   // instantiated robust-only anyway (kernels/bvh/bvh_intersector1_bvh4.cpp:63-78)
   rtcSetSceneFlags(s->scene, RTC_SCENE_FLAG_ROBUST);
   rtcSetSceneLevels(s->scene, S, C);
+  // `leaf` may carry extra device options after a comma, e.g. "leaf,max_isa=sse4.2" (used to measure how far the
+  // reference's own ISA code paths drift from each other on the same rays)
+  const std::string kind = std::string(leaf).substr(0, std::string(leaf).find(','));
+  s->leaf_kind = kind == "grid" ? 0 : kind == "leaf" ? 1 : kind == "box" ? 2 : -1;
+  s->S = S;
+  s->C = C;
   return s;
 }
 
@@ -344,4 +353,93 @@ REF_API void ref_hit_normals(RefScene* s, const void* rayhits, size_t n, size_t 
 REF_API int ref_hardware_threads(void) {
   unsigned n = std::thread::hardware_concurrency();
   return n ? (int)n : 1;
+}
+
+// ---- relocatable image of the committed compressed accel (rimg.h) ----
+namespace {
+struct Dumper {
+  RefScene* s;
+  char* buf;
+  size_t cap, pos;
+  uint32_t n_nodes = 0, n_blocks = 0;
+  std::map<uint64_t, uint64_t> seen;
+
+  size_t alloc(size_t bytes) {
+    const size_t at = (pos + 15) & ~size_t(15);
+    pos = at + bytes;
+    return at;
+  }
+  void put(size_t at, const void* src, size_t bytes) {
+    if (buf && at + bytes <= cap) memcpy(buf + at, src, bytes);
+  }
+  uint64_t visit(uint64_t ref) {
+    using namespace embree;
+    if (ref == BVH4::emptyNode) return ref;
+    const uint64_t tag = ref & 15, ptr = ref & ~uint64_t(15);
+    auto it = seen.find(ptr);
+    if (it != seen.end()) return it->second | tag;
+    if (ref & BVH4::tyLeaf) {
+      typedef isa::compressed::CompressedBVH<isa::compressed::compressedNonUniform> Block;
+      const Block* b = (const Block*)ptr;
+      const size_t cells = 3 * (size_t)b->elems + 1;
+      const size_t nodes_b = 4 * (size_t)b->elems;
+      const size_t leaves_b = s->leaf_kind == 1 ? 2 * cells : 0;
+      const size_t grid_b = s->leaf_kind == 0 ? 12 * (size_t)b->grid_width * b->grid_width : 0;
+      const size_t at = alloc(sizeof(Block) + nodes_b + leaves_b + grid_b);
+      seen[ptr] = at;
+      n_blocks++;
+      std::vector<char> tmp(sizeof(Block) + nodes_b + leaves_b + grid_b);
+      memcpy(tmp.data(), b, sizeof(Block));
+      memcpy(tmp.data() + sizeof(Block), b->nodes, nodes_b);
+      if (leaves_b) memcpy(tmp.data() + sizeof(Block) + nodes_b, b->leaves, leaves_b);
+      if (grid_b) memcpy(tmp.data() + sizeof(Block) + nodes_b + leaves_b, b->grid, grid_b);
+      Block* nb = (Block*)tmp.data();
+      nb->nodes = (decltype(nb->nodes))(at + sizeof(Block));
+      nb->leaves = (decltype(nb->leaves))(at + sizeof(Block) + nodes_b);
+      nb->grid = (decltype(nb->grid))(at + sizeof(Block) + nodes_b + leaves_b);
+      put(at, tmp.data(), tmp.size());
+      return at | tag;
+    }
+    const BVH4::AlignedNode* n = (const BVH4::AlignedNode*)ptr;
+    const size_t at = alloc(sizeof(BVH4::AlignedNode));
+    seen[ptr] = at;
+    n_nodes++;
+    char tmp[sizeof(BVH4::AlignedNode)];
+    memcpy(tmp, n, sizeof(tmp));
+    for (int i = 0; i < 4; i++) {
+      const uint64_t c = visit((uint64_t)(size_t)n->child(i));
+      memcpy(tmp + 8 * i, &c, 8);
+    }
+    put(at, tmp, sizeof(tmp));
+    return at | tag;
+  }
+};
+}  // namespace
+
+REF_API size_t ref_scene_dump_image(RefScene* s, void* buf, size_t cap) {
+  int n_accels = 0;
+  const uint64_t root = ref_scene_compressed_root(s, &n_accels);
+  if (!root || s->leaf_kind < 0) return 0;
+  Dumper d;
+  d.s = s;
+  d.buf = (char*)buf;
+  d.cap = cap;
+  d.pos = sizeof(rimg_header);
+  rimg_header h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, RIMG_MAGIC, 8);
+  h.version = 1;
+  h.leaf_kind = (uint32_t)s->leaf_kind;
+  h.subdiv_level = s->S;
+  h.comp_level = s->C;
+  RefLayout lay;
+  ref_layout(&lay);
+  h.proj_col_major = lay.proj_col_major;
+  h.root = d.visit(root);
+  h.n_nodes = d.n_nodes;
+  h.n_blocks = d.n_blocks;
+  h.total_bytes = (d.pos + 15) & ~size_t(15);
+  ref_scene_bounds(s, h.bounds);
+  d.put(0, &h, sizeof(h));
+  return (size_t)h.total_bytes;
 }

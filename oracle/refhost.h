@@ -64,6 +64,11 @@ double ref_occluded(RefScene*, void* rays, size_t n, size_t stride, int nthreads
  * writes 3 floats per ray (zeros for misses). */
 void ref_hit_normals(RefScene*, const void* rayhits, size_t n, size_t stride, float* normals3);
 
+/* Relocatable image ("RIMG") of the committed compressed accel: every AlignedNode and CompressedBVH block copied
+ * verbatim (reference layout) into one buffer, pointers replaced by byte offsets from the start of the buffer with
+ * their tag bits kept.  Layout of the 96-byte header: see rimg.h.  Returns the image size (call with cap=0 to size). */
+size_t ref_scene_dump_image(RefScene*, void* buf, size_t cap);
+
 int ref_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,219 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (include/ecb200.h), against the oracle.
+
+Every comparison is made twice: bit-exact against the scalar C port (oracle/cbvh_port.c) and, within the
+north_star tolerance with the near-tie set computed by the oracle, against the compiled reference itself
+(rtcIntersect1 / rtcOccluded1 applied per ray -- the only call form that works on this accel).
+"""
+import numpy as np
+import pytest
+
+import parity
+from embree_compressed_b200 import raygen as rg
+
+pytestmark = pytest.mark.gpu
+
+LEAVES = ["leaf", "grid", "box"]
+CASES = [  # (scene kind, S, C, camera, width, height)
+    ("cube", 6, 4, rg.CUBE_CAMERA, 512, 512),            # BASELINE config 1 geometry (1024^2 in the slow test)
+    ("bomberman", 6, 3, rg.BOMBERMAN_CAMERA, 640, 360),  # BASELINE config 2 geometry (1920x1080 in the slow test)
+    ("cube", 4, 2, rg.CUBE_CAMERA, 256, 256),
+    ("cube", 5, 1, rg.CUBE_CAMERA, 128, 128),
+]
+
+
+def _scene_pair(ecb, oracle, ref):
+    """product scene imported from LIVE reference memory + the port bound to the same memory."""
+    root, n_accels = ref.root()
+    assert root and n_accels == 1
+    scene = ecb.Scene.import_bvh4(root, ref.leaf, ref.C, ref.S, oracle.ref_layout()["proj_col_major"], 0, ref.bounds())
+    return scene, oracle.PortScene.from_ref(ref)
+
+
+def _check_intersect(scene, port, ref, rays, what):
+    got = rays.copy()
+    scene.intersect1M(got)
+    want = rays.copy()
+    port.intersect(want)
+    bad = parity.bit_exact_mismatches(got, want)
+    assert len(bad) == 0, "%s: CUDA differs from the oracle port on %d of %d rays (first rows %s)" % (
+        what, len(bad), len(rays), bad[:8])
+    truth = rays.copy()
+    ref.intersect(truth)
+    c = parity.assert_reference_parity(got, truth, port.candidates(rays), what)
+    return got, truth, c
+
+
+@pytest.mark.parametrize("leaf", LEAVES)
+@pytest.mark.parametrize("kind,S,C,cam,W,H", CASES)
+def test_primary_and_diffuse(ecb, reference, ref_scene, leaf, kind, S, C, cam, W, H):
+    ref = ref_scene(kind, leaf, S, C)
+    scene, port = _scene_pair(ecb, reference, ref)
+    rays = rg.primary_rays(W, H, **cam)
+    got, truth, c = _check_intersect(scene, port, ref, rays, "%s S%d C%d %s primary" % (kind, S, C, leaf))
+    assert c["hits_ref"] > 0
+    # cosine-diffuse bounce from the REFERENCE's hits with the viewer's smooth normals (same array to all three)
+    b = ref.bounds()
+    diag = float(np.linalg.norm(b[3:] - b[:3]))
+    bounce = rg.diffuse_rays(truth, ref.hit_normals(truth), diag)
+    _check_intersect(scene, port, ref, bounce, "%s S%d C%d %s diffuse" % (kind, S, C, leaf))
+    # shadow-style any-hit query on the same rays: rtcOccluded1 semantics (top-level boxes only)
+    occ = rg.rays_only(bounce)
+    got_o, want_o, truth_o = occ.copy(), occ.copy(), occ.copy()
+    scene.occluded1M(got_o)
+    port.occluded(want_o)
+    ref.occluded(truth_o)
+    assert (got_o.view(np.uint32) == want_o.view(np.uint32)).all()
+    assert (got_o.view(np.uint32) == truth_o.view(np.uint32)).all(), "occluded differs from the reference"
+    scene.release()
+
+
+@pytest.mark.parametrize("leaf", LEAVES)
+def test_incoherent_rays(ecb, reference, ref_scene, leaf):
+    ref = ref_scene("bomberman", leaf, 6, 3)
+    scene, port = _scene_pair(ecb, reference, ref)
+    b = ref.bounds()
+    lo, hi = b[:3].copy(), b[3:].copy()
+    # shrink the AABB to the character (the ground quad dominates the scene bounds, SURVEY 8d caveat)
+    lo[0], lo[2], hi[0], hi[2] = -25, -25, 25, 25
+    rays = rg.incoherent_rays(200_000, np.concatenate([lo, hi]), seed=7)
+    _check_intersect(scene, port, ref, rays, "bomberman %s incoherent" % leaf)
+    scene.release()
+
+
+def test_entry_points_and_edge_cases(ecb, reference, ref_scene):
+    ref = ref_scene("cube", "leaf", 4, 2)
+    scene, port = _scene_pair(ecb, reference, ref)
+    rays = rg.primary_rays(64, 64, **rg.CUBE_CAMERA)
+    want = rays.copy()
+    port.intersect(want)
+
+    # M = 0 and M = 1
+    scene.intersect1M(rays[:0].copy())
+    one = rays[2080:2081].copy()
+    scene.intersect1(one[0])
+    assert (one.view(np.uint32) == want[2080:2081].view(np.uint32)).all()
+
+    # byteStride > sizeof(RTCRayHit): 96-byte records, padding must stay untouched
+    wide = np.full((len(rays), 24), 7.0, np.float32)
+    wide[:, :20] = rays
+    scene.intersect1M(wide)
+    assert (wide[:, :20].view(np.uint32) == want.view(np.uint32)).all()
+    assert (wide[:, 20:] == 7.0).all()
+
+    # inactive stream rays (tnear > tfar) are skipped; a miss writes nothing at all
+    mixed = rays.copy()
+    mixed[::3, 3] = 2.0
+    mixed[::3, 8] = 1.0
+    ref_mixed = mixed.copy()
+    port.intersect(ref_mixed)
+    scene.intersect1M(mixed)
+    assert (mixed.view(np.uint32) == ref_mixed.view(np.uint32)).all()
+    assert (mixed[::3].view(np.uint32) == ref_mixed[::3].view(np.uint32)).all()
+
+    # rays that already carry a finite tfar / a previous hit keep it when nothing nearer is found
+    near = rays.copy()
+    near[:, 8] = 0.5
+    near.view(np.uint32)[:, 18] = 5
+    near_want = near.copy()
+    port.intersect(near_want)
+    scene.intersect1M(near)
+    assert (near.view(np.uint32) == near_want.view(np.uint32)).all()
+
+    # instID is taken from the context argument
+    inst = rays.copy()
+    scene.intersect1M(inst, inst_id=3)
+    hit = inst.view(np.uint32)[:, 18] != 0xFFFFFFFF
+    assert hit.any() and (inst.view(np.uint32)[hit, 19] == 3).all()
+
+    # rtcIntersect16: SoA packet with a valid mask
+    packet_rows = np.arange(2072, 2088)
+    soa = np.ascontiguousarray(rays[packet_rows].T)
+    valid = np.full(16, -1, np.int32)
+    valid[[1, 5, 6]] = 0
+    scene.intersect16(valid, soa)
+    back = soa.T
+    act = valid == -1
+    assert (back[act].view(np.uint32) == want[packet_rows][act].view(np.uint32)).all()
+    assert (np.ascontiguousarray(back[~act]).view(np.uint32) == rays[packet_rows][~act].view(np.uint32)).all()
+
+    # occluded: tfar < 0 is "already occluded" and stays untouched
+    occ = rg.rays_only(rays)
+    occ[::2, 8] = -1.0
+    occ_want = occ.copy()
+    port.occluded(occ_want)
+    scene.occluded1M(occ)
+    assert (occ.view(np.uint32) == occ_want.view(np.uint32)).all()
+    one_o = rg.rays_only(rays)[2081:2082].copy()
+    one_want = one_o.copy()
+    port.occluded(one_want)
+    scene.occluded1(one_o[0])
+    assert (one_o.view(np.uint32) == one_want.view(np.uint32)).all()
+    scene.release()
+
+
+def test_device_resident_path_and_block_output(ecb, reference, ref_scene):
+    import torch
+    ref = ref_scene("bomberman", "leaf", 6, 3)
+    scene, port = _scene_pair(ecb, reference, ref)
+    rays = rg.primary_rays(480, 270, **rg.BOMBERMAN_CAMERA)
+    want = rays.copy()
+    port.intersect(want)
+    d = torch.from_numpy(rays).cuda()
+    blocks = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    scene.intersect_device(d.data_ptr(), len(rays), 80, stream, blocks.data_ptr())
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    blk = blocks.cpu().numpy().view(np.uint32)
+    hit = got.view(np.uint32)[:, 18] != 0xFFFFFFFF
+    assert (blk[~hit] == 0xFFFFFFFF).all() and (blk[hit] < scene.info()["n_blocks"]).all()
+    # the block frame normal is a unit vector roughly aligned with the reference's smooth normal
+    n_blk = scene.block_normals()[blk[hit]]
+    assert np.allclose(np.linalg.norm(n_blk, axis=1), 1.0, atol=1e-3)
+    n_ref = ref.hit_normals(want)[hit]
+    n_ref /= np.maximum(np.linalg.norm(n_ref, axis=1, keepdims=True), 1e-20)
+    assert np.median(np.abs(np.sum(n_blk * n_ref, axis=1))) > 0.95
+    scene.release()
+
+
+def test_image_and_blob_round_trip(ecb, reference, ref_scene, tmp_path):
+    ref = ref_scene("cube", "grid", 4, 2)
+    live, port = _scene_pair(ecb, reference, ref)
+    rays = rg.primary_rays(128, 128, **rg.CUBE_CAMERA)
+    want = rays.copy()
+    port.intersect(want)
+    image = ref.dump_image()
+    from_img = ecb.Scene.from_image(image)
+    p = str(tmp_path / "scene.ecbs")
+    from_img.save(p)
+    from_blob = ecb.Scene.load(p)
+    for s in (live, from_img, from_blob):
+        got = rays.copy()
+        s.intersect1M(got)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all()
+        s.release()
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("leaf", LEAVES)
+def test_full_size_configs(ecb, reference, ref_scene, leaf):
+    """BASELINE.json configs 1 and 2 at their full ray counts (1024^2 and 1920x1080 primary + one diffuse bounce)."""
+    for kind, S, C, cam, W, H in (("cube", 6, 4, rg.CUBE_CAMERA, 1024, 1024),
+                                  ("bomberman", 6, 3, rg.BOMBERMAN_CAMERA, 1920, 1080)):
+        ref = ref_scene(kind, leaf, S, C)
+        scene, port = _scene_pair(ecb, reference, ref)
+        rays = rg.primary_rays(W, H, **cam)
+        got, truth, _ = _check_intersect(scene, port, ref, rays, "%s %s full primary" % (kind, leaf))
+        b = ref.bounds()
+        bounce = rg.diffuse_rays(truth, ref.hit_normals(truth), float(np.linalg.norm(b[3:] - b[:3])))
+        _check_intersect(scene, port, ref, bounce, "%s %s full diffuse" % (kind, leaf))
+        # size-independent property: re-tracing the result never finds anything farther, never turns a hit into a
+        # miss, and moves t by at most the tolerance (a hit at t == tfar may be re-found within rounding)
+        again = got.copy()
+        scene.intersect1M(again)
+        assert (again[:, 8] <= got[:, 8]).all()
+        assert (again.view(np.uint32)[:, 18] == got.view(np.uint32)[:, 18]).all()
+        hit = got.view(np.uint32)[:, 18] != 0xFFFFFFFF
+        assert (np.abs(again[hit, 8] - got[hit, 8]) <= 1e-5 * np.abs(got[hit, 8])).all()
+        scene.release()
