@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py -- Mrays/s of the compressed-BVH traversal hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--leaf leaf|grid|box]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): build/bomberman.obj as one subdivision mesh, S=6 C=3 compressed leaves,
+camera of build/bomberman.ecs, 1920x1080 primary rays + one cosine-diffuse bounce ray per primary hit.
+A step = one pass of the hot path over that batch: trace the primary rays, trace the bounce rays.
+
+  value      device-timed: rays resident in HBM, CUDA events around the K steps on the launching stream.
+  e2e        the same step through the reference-facing call (ecbIntersect1M == rtcIntersect1M) with pinned HOST
+             ray buffers; host<->device copies inside the timed region.
+  roofline   algorithmic bytes of one launch (measured by the instrumented kernel variant, SURVEY 8d formula with
+             this repo's node/header sizes) / average launch duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the compiled reference (oracle/_ref, rtcIntersect1 per ray on all host threads) on the same rays.
+
+Scenes are images of the REFERENCE's committed BVH (built by its CPU builder at build() time, scenes/_built/*.rimg)
+converted by the product's importer; nothing under oracle/ is touched outside the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+METRIC = "Mrays/s primary+diffuse (device-timed)"
+UNIT = "Mrays/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def scene_path(leaf):
+    return os.path.join(ROOT, "scenes", "_built", "bomberman_s6c3_%s.rimg" % leaf)
+
+
+def workload_config(leaf, n_primary, n_bounce):
+    return {"workload": "bomberman.obj subdiv S=6 C=3 compress.%s, %dx%d primary + 1 cosine-diffuse bounce" % (leaf, WIDTH, HEIGHT),
+            "rays_primary": int(n_primary), "rays_bounce_active": int(n_bounce),
+            "l2": "ray buffers (2 x 166 MB per step, a fresh copy every step) exceed the 126 MB L2; the 18.8 MB scene is "
+                  "L2-resident by construction of the workload"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(leaf):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if one exists."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(leaf)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def make_rays(scene, ecb, rg, torch, dev):
+    """Primary rays of the ecs camera and their bounce rays (block-frame normals; generated once, untimed)."""
+    prim = rg.primary_rays(WIDTH, HEIGHT, **rg.BOMBERMAN_CAMERA)
+    d = torch.from_numpy(prim).to(dev)
+    blocks = torch.empty(len(prim), dtype=torch.int32, device=dev)
+    scene.intersect_device(d.data_ptr(), len(prim), 80, torch.cuda.current_stream().cuda_stream, blocks.data_ptr())
+    torch.cuda.synchronize()
+    first = d.cpu().numpy()
+    blk = blocks.cpu().numpy().view(np.uint32)
+    hit = first.view(np.uint32)[:, 18] != 0xFFFFFFFF
+    normals = np.zeros((len(prim), 3), np.float32)
+    normals[hit] = scene.block_normals()[blk[hit]]
+    b = scene.info()["bounds"]
+    diag = float(np.linalg.norm(np.array(b[3:]) - np.array(b[:3])))
+    xs, ys = np.meshgrid(np.arange(WIDTH, dtype=np.uint32), np.arange(HEIGHT, dtype=np.uint32))
+    bounce = rg.diffuse_rays(first, normals, diag, sample=0, pixel_xy=(xs.ravel(), ys.ravel()))
+    return prim, bounce, int(hit.sum())
+
+
+def run_ours(args, rank, world):
+    import torch
+    import embree_compressed_b200 as ecb
+    from embree_compressed_b200 import raygen as rg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the traversal path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    path = scene_path(args.leaf)
+    if not os.path.exists(path):
+        raise SystemExit("bench.py: %s missing -- run __graft_entry__.build() where /root/reference is mounted" % path)
+    scene = ecb.Scene.from_image_file(path).upload(local)
+    info = scene.info()
+    prim, bounce, n_hits = make_rays(scene, ecb, rg, torch, dev)
+    n_prim = len(prim)
+    n_bounce = int((bounce[:, 3] <= bounce[:, 8]).sum())
+    rays_per_step = n_prim + n_bounce
+    K, W = args.steps, args.warmup
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- device-timed value: a fresh copy of the ray buffers for every step (nothing is cached between steps) ----
+    d_prim0 = torch.from_numpy(prim).to(dev)
+    d_bounce0 = torch.from_numpy(bounce).to(dev)
+    bufs = [(d_prim0.clone(), d_bounce0.clone()) for _ in range(K + W)]
+
+    def step(i):
+        p, b = bufs[i]
+        scene.intersect_device(p.data_ptr(), n_prim, 80, stream)
+        scene.intersect_device(b.data_ptr(), len(bounce), 80, stream)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ecb.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(W, W + K):
+        step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = ecb.launch_count() - launches0
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * rays_per_step * K / (ms_max * 1e-3) / 1e6
+
+    # ---- per-kernel timing of the dominant launch (primary pass) + algorithmic bytes from the instrumented variant ----
+    cnt = torch.zeros(6, dtype=torch.int64, device=dev)
+    tmp = d_prim0.clone()
+    scene.intersect_device_stats(tmp.data_ptr(), n_prim, cnt.data_ptr(), 80, stream)
+    torch.cuda.synchronize()
+    c_prim = cnt.cpu().numpy().astype(np.float64)
+    cnt.zero_()
+    tmp = d_bounce0.clone()
+    scene.intersect_device_stats(tmp.data_ptr(), len(bounce), cnt.data_ptr(), 80, stream)
+    torch.cuda.synchronize()
+    c_bounce = cnt.cpu().numpy().astype(np.float64)
+    leaf_bytes = {"leaf": 2.0, "grid": 48.0, "box": 0.0}[args.leaf]
+
+    def algorithmic_bytes(c, n_records):
+        # ray in + hit out + 112 B per top-level node + 144 B per block header + 4 B per quantized node
+        # + leaf payload per cell (2 B heights / 4 x 12 B vertices / none); every record is read, hits are written
+        return 80.0 * n_records + 48.0 * c[5] + 112.0 * c[1] + 144.0 * c[2] + 4.0 * c[3] + leaf_bytes * c[4]
+
+    kernel_ms = {}
+    for name, src, n in (("primary", d_prim0, n_prim), ("bounce", d_bounce0, len(bounce))):
+        reps = []
+        for _ in range(5):
+            tmp = src.clone()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            scene.intersect_device(tmp.data_ptr(), n, 80, stream)
+            b.record()
+            torch.cuda.synchronize()
+            reps.append(a.elapsed_time(b))
+        kernel_ms[name] = float(np.mean(reps[1:]))
+    bytes_prim = algorithmic_bytes(c_prim, n_prim)
+    bytes_bounce = algorithmic_bytes(c_bounce, len(bounce))
+    dom = "primary" if kernel_ms["primary"] >= kernel_ms["bounce"] else "bounce"
+    dom_bytes = bytes_prim if dom == "primary" else bytes_bounce
+    peak, peak_src = measured_peak()
+    achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": recorded_traffic(args.leaf), "peak_source": peak_src, "kernel": "ecb_intersect_kernel<%s> (%s pass)" % (args.leaf, dom),
+                "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
+                "algorithmic_bytes_per_ray": {"primary": round(bytes_prim / n_prim, 1), "bounce": round(bytes_bounce / max(1, n_bounce), 1)},
+                "work_per_ray": {"primary": {"top_nodes": round(c_prim[1] / c_prim[0], 3), "blocks": round(c_prim[2] / c_prim[0], 3),
+                                             "cnodes": round(c_prim[3] / c_prim[0], 3), "cells": round(c_prim[4] / c_prim[0], 3)},
+                                 "bounce": {"top_nodes": round(c_bounce[1] / max(1, c_bounce[0]), 3), "blocks": round(c_bounce[2] / max(1, c_bounce[0]), 3),
+                                            "cnodes": round(c_bounce[3] / max(1, c_bounce[0]), 3), "cells": round(c_bounce[4] / max(1, c_bounce[0]), 3)}},
+                "mrays_per_s": {"primary": round(n_prim / kernel_ms["primary"] / 1e3, 1), "bounce": round(n_bounce / kernel_ms["bounce"] / 1e3, 1)}}
+
+    # ---- e2e: the reference-facing call with pinned host buffers, copies inside the timed region ----
+    hp, hp_ptr = ecb.host_alloc(prim.nbytes)
+    hb, hb_ptr = ecb.host_alloc(bounce.nbytes)
+    hp = hp.view(np.float32).reshape(prim.shape)
+    hb = hb.view(np.float32).reshape(bounce.shape)
+    e2e_steps = max(3, min(K, 10))
+    e2e_t = []
+    for i in range(2 + e2e_steps):
+        hp[:] = prim
+        hb[:] = bounce
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        scene.intersect1M(hp)
+        scene.intersect1M(hb)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t[2:]))
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * rays_per_step / float(t.item()) / 1e6
+    e2e_hits = int((hp.view(np.uint32)[:, 18] != 0xFFFFFFFF).sum())
+    assert e2e_hits == n_hits, "e2e path found %d hits, device path %d" % (e2e_hits, n_hits)
+    e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(prim.nbytes + bounce.nbytes),
+           "d2h_bytes_per_step": int(prim.nbytes + bounce.nbytes), "steps": e2e_steps,
+           "call": "ecbIntersect1M (rtcIntersect1M drop-in), pinned host RTCRayHit arrays"}
+    ecb.host_free(hp_ptr)
+    ecb.host_free(hb_ptr)
+
+    # ---- multi-GPU: the one exchange step of the path, hit records gathered to rank 0 over NCCL (timed apart) ----
+    gather = None
+    if dist:
+        p, b = bufs[W]
+        compact = torch.cat([p[:, 8:9], p[:, 15:20]], 1).contiguous()  # tfar,u,v,primID,geomID,instID = 24 B per ray
+        outs = [torch.empty_like(compact) for _ in range(world)] if rank == 0 else None
+        for _ in range(2):
+            dist.gather(compact, outs, dst=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            dist.gather(compact, outs, dst=0)
+        bb.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([a.elapsed_time(bb) / 5], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_pass": round(float(tg.item()), 3), "bytes_per_rank": int(compact.numel() * 4),
+                  "what": "NCCL gather of 24-byte hit records of the primary pass to rank 0 (not inside `value`)"}
+
+    out = None
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args.leaf, n_prim, n_bounce),
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+               "bytes_per_micro_triangle": {"device_format": round(info["bytes_per_micro_triangle"], 3),
+                                            "reference_layout": round(info["reference_bytes_per_micro_triangle"], 3)},
+               "parallelism": "rays sharded per rank (each rank traces its own full frame), scene replicated, no data-path collective"}
+        if gather:
+            out["gather"] = gather
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, prim, bounce, n_prim, n_bounce)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def reference_pass(ref, prim, bounce, threads):
+    a, b = prim.copy(), bounce.copy()  # fresh rays (the trace mutates them); the copy is not timed
+    t0 = time.perf_counter()
+    ref.intersect(a, threads)
+    ref.intersect(b, threads)
+    return time.perf_counter() - t0
+
+
+def build_reference_scene(leaf):
+    from oracle import pyoracle as po
+    if not po.have_reference():
+        return None, po
+    ref = po.RefScene(leaf, 6, 3)
+    ref.add_obj()
+    ref.commit()
+    return ref, po
+
+
+def cpu_baseline(args, prim, bounce, n_prim, n_bounce):
+    """The compiled reference (rtcIntersect1 per ray, all host threads) on the same rays: bounded sample."""
+    ref, po = build_reference_scene(args.leaf)
+    threads = po.hardware_threads()
+    if ref is None:
+        port = po.PortScene.from_image(np.fromfile(scene_path(args.leaf), np.uint8))
+        ts = []
+        for _ in range(3):
+            a, b = prim.copy(), bounce.copy()
+            t0 = time.perf_counter()
+            port.intersect(a, threads)
+            port.intersect(b, threads)
+            ts.append(time.perf_counter() - t0)
+        kind = "port"
+    else:
+        ts = [reference_pass(ref, prim, bounce, threads) for _ in range(4)][1:]
+        kind = "reference"
+    best = min(ts)
+    return {"value": round((n_prim + n_bounce) / best / 1e6, 2), "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "the full step (%d primary + %d active bounce rays), best of %d passes, rtcIntersect1 per ray on %d std::threads, AVX2 build"
+                      % (n_prim, n_bounce, len(ts), threads)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return None
+    from embree_compressed_b200 import raygen as rg
+    ref, po = build_reference_scene(args.leaf)
+    threads = po.hardware_threads()
+    prim = rg.primary_rays(WIDTH, HEIGHT, **rg.BOMBERMAN_CAMERA)
+    xs, ys = np.meshgrid(np.arange(WIDTH, dtype=np.uint32), np.arange(HEIGHT, dtype=np.uint32))
+    if ref is None:
+        # oracle/_ref did not travel: time the scalar C restatement instead (bounce normals = reversed incoming ray)
+        image = np.fromfile(scene_path(args.leaf), np.uint8)
+        tracer = po.PortScene.from_image(image)
+        kind = "port"
+        first = prim.copy()
+        tracer.intersect(first, threads)
+        h = po.rimg_header(image)
+        diag = float(np.linalg.norm(h["bounds"][3:] - h["bounds"][:3]))
+        normals = -first[:, 4:7]
+
+        class _Port:
+            def intersect(self, r, t):
+                return tracer.intersect(r, t)
+        ref = _Port()
+    else:
+        kind = "reference"
+        first = prim.copy()
+        ref.intersect(first, threads)
+        b = ref.bounds()
+        diag = float(np.linalg.norm(b[3:] - b[:3]))
+        normals = ref.hit_normals(first)
+    bounce = rg.diffuse_rays(first, normals, diag, sample=0, pixel_xy=(xs.ravel(), ys.ravel()))
+    n_prim, n_bounce = len(prim), int((bounce[:, 3] <= bounce[:, 8]).sum())
+    for _ in range(args.warmup):
+        reference_pass(ref, prim, bounce, threads)
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += reference_pass(ref, prim, bounce, threads)
+    value = (n_prim + n_bounce) * args.steps / dt / 1e6
+    return {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.leaf, n_prim, n_bounce),
+            "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "every step traces the full workload (%d + %d rays) with rtcIntersect1 per ray on %d std::threads (AVX2 build, internal tasking)"
+                                       % (n_prim, n_bounce, threads)},
+            "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--leaf", default="leaf", choices=["leaf", "grid", "box"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+    else:
+        out = run_ours(args, rank, world)
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

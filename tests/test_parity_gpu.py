@@ -13,11 +13,15 @@ from embree_compressed_b200 import raygen as rg
 pytestmark = pytest.mark.gpu
 
 LEAVES = ["leaf", "grid", "box"]
+# The tutorial camera looks down the cube's diagonal: pixel rays then hit shared micro-triangle edges EXACTLY, where
+# the reference's strict beta>0 / gamma>0 test (compressed_help.h:266) lets a ray fall through or not depending on the
+# last ulp (its SSE4.2 and AVX2 paths disagree on those rays too).  The small cases use a camera off the symmetry axis.
+OFF_AXIS = dict(vp=(1.6, 1.45, -1.35), vi=(0.05, -0.02, 0.03), vu=(0.0, 1.0, 0.0), fov=90.0)
 CASES = [  # (scene kind, S, C, camera, width, height)
     ("cube", 6, 4, rg.CUBE_CAMERA, 512, 512),            # BASELINE config 1 geometry (1024^2 in the slow test)
     ("bomberman", 6, 3, rg.BOMBERMAN_CAMERA, 640, 360),  # BASELINE config 2 geometry (1920x1080 in the slow test)
-    ("cube", 4, 2, rg.CUBE_CAMERA, 256, 256),
-    ("cube", 5, 1, rg.CUBE_CAMERA, 128, 128),
+    ("cube", 4, 2, OFF_AXIS, 256, 256),
+    ("cube", 5, 1, OFF_AXIS, 128, 128),
 ]
 
 
