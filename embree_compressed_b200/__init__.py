@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libecb200.so")
+# ECB200_LIB: developer override used to A/B kernel variants (tools/kbench.py); the shipped library is in-tree
+LIB_PATH = os.environ.get("ECB200_LIB") or os.path.join(HERE, "libecb200.so")
 
 INVALID_GEOMETRY_ID = 0xFFFFFFFF
 LEAF_GRID, LEAF_LEAF, LEAF_BOX = 0, 1, 2
@@ -189,9 +190,12 @@ class Scene:
     # -- traversal, host buffers (rtcIntersect1M / rtcOccluded1M / rtcIntersect16 semantics) -----------------------
     @staticmethod
     def _host_args(a, width):
-        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 2 and a.shape[1] >= width
-                and a.strides[1] == 4):
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 2 and a.shape[1] >= width):
             raise ValueError("rays must be a float32 array of shape (N, >=%d)" % width)
+        if a.shape[0] == 0:
+            return None, 0, 4 * a.shape[1]
+        if a.strides[1] != 4:
+            raise ValueError("ray fields must be contiguous")
         return a.ctypes.data, a.shape[0], a.strides[0]
 
     def intersect1M(self, rayhits, inst_id=INVALID_GEOMETRY_ID):

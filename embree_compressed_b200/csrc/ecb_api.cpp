@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
@@ -21,7 +22,8 @@ std::atomic<uint64_t> g_launches{0};
 
 constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
 constexpr int kStages = 3;
-constexpr size_t kChunkRays = 1u << 19;  // 512 Ki rays (40 MiB of RTCRayHit) per pipeline stage
+constexpr size_t kChunkRays = 1u << 18;  // 256 Ki rays per pipeline stage
+constexpr uint32_t kQueueRing = 256;
 
 ecbError cuda_fail(cudaError_t e, const char* what) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -99,10 +101,14 @@ ecbError ensure_resident(ecbScene* s, int device) {
   d.elems = s->elems;
   d.grid_width = s->grid_width;
   d.rcp_edges = s->rcp_edges;
+  CU(cudaMalloc(reinterpret_cast<void**>(&s->d_queues), kQueueRing * sizeof(unsigned long long)));
+  CU(cudaMemset(s->d_queues, 0, kQueueRing * sizeof(unsigned long long)));
   s->device = device;
   s->info.device = device;
   return ECB_SUCCESS;
 }
+
+unsigned long long* next_queue(ecbScene* s) { return s->d_queues + (s->next_queue.fetch_add(1) % kQueueRing); }
 
 ecbError ensure_staging(ecbScene* s) {
   if (s->staging) return ECB_SUCCESS;
@@ -130,6 +136,23 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Transfer strategy of the host-buffer entry points when the caller's rays are in pinned memory
+// (ECB200_HOST_PATH = "copy" | "zerocopy" | "zerocopy2d"; measured on B200 / PCIe Gen5 x16, 55 GB/s one way, 35+35 both):
+//   copy (default): contiguous DMA of the full records both ways, 3-stage pipeline      -> 456 Mrays/s on the bench step
+//   zerocopy      : contiguous H2D DMA, kernel writes tfar + hit of the rays that hit straight into the caller's array
+//                   through its mapped device address (no D2H copy)                     -> 363 Mrays/s (small PCIe writes)
+//   zerocopy2d    : as above with a 2-D H2D copy of the 48-byte RTCRay part only        ->  35 Mrays/s (row-sized DMAs)
+int host_path_mode() {  // 0 copy, 1 zero-copy results + contiguous H2D, 2 zero-copy results + 48-byte 2-D H2D
+  static const int mode = [] {
+    const char* e = getenv("ECB200_HOST_PATH");
+    if (e && strcmp(e, "zerocopy") == 0) return 1;
+    if (e && strcmp(e, "zerocopy2d") == 0) return 2;
+    return 0;
+  }();
+  return mode;
+}
+bool use_zero_copy() { return host_path_mode() != 0; }
+
 // Shared by intersect (elem = 80) and occluded (elem = 48).
 ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride) {
   if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
@@ -146,15 +169,66 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   err = ensure_staging(s);
   if (err != ECB_SUCCESS) return err;
   Staging* st = s->staging;
-  const bool pinned = is_pinned(rays);
-  // device-side layout is always densely packed (stride = elem, 16-byte aligned)
-  const size_t chunk = kChunkRays;
   uint8_t* base = static_cast<uint8_t*>(rays);
+  const size_t chunk = kChunkRays;
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
+
+  void* mapped = nullptr;
+  const bool pinned = is_pinned(rays);
+  const bool zero_copy = pinned && use_zero_copy() && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(rays) & 15) == 0) &&
+                         (stride % 16 == 0) && cudaHostGetDevicePointer(&mapped, rays, 0) == cudaSuccess && mapped;
+  if (!zero_copy) cudaGetLastError();
+
+  auto launch = [&](int k, size_t n, size_t in_stride, uint8_t* out, size_t out_stride) -> cudaError_t {
+    EcbLaunch L;
+    L.in = static_cast<const uint8_t*>(st->d_buf[k]);
+    L.in_stride = in_stride;
+    L.out = out;
+    L.out_stride = out_stride;
+    L.M = n;
+    L.instID = instID;
+    L.block_out = nullptr;
+    L.counters = nullptr;
+    L.queue = next_queue(s);
+    g_launches.fetch_add(1);
+    return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
+  };
+
+  if (zero_copy) {
+    // H2D: only the RTCRay part (48 B) of every record; results go back through the mapped pointer
+    for (uint64_t c = 0; c < n_chunks; c++) {
+      const int k = (int)(c % kStages);
+      const uint64_t first = c * chunk;
+      const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
+      cudaStream_t q = st->stream[k];
+      size_t in_stride = elem;
+      if (host_path_mode() == 2) {
+        in_stride = kRayBytes;
+        CU(cudaMemcpy2DAsync(st->d_buf[k], kRayBytes, base + first * stride, stride, kRayBytes, n, cudaMemcpyHostToDevice, q));
+      } else if (stride == elem) {
+        CU(cudaMemcpyAsync(st->d_buf[k], base + first * stride, n * elem, cudaMemcpyHostToDevice, q));
+      } else {
+        CU(cudaMemcpy2DAsync(st->d_buf[k], elem, base + first * stride, stride, elem, n, cudaMemcpyHostToDevice, q));
+      }
+      cudaError_t le = launch(k, n, in_stride, static_cast<uint8_t*>(mapped) + first * stride, stride);
+      if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+    }
+    for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
+    return ECB_SUCCESS;
+  }
+
   if (!pinned) {
     for (int i = 0; i < kStages; i++)
       if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRays * kRayHitBytes));
   }
+  auto unpack = [&](uint64_t c, int k) {  // bounce buffer -> caller's array
+    const uint64_t first = c * chunk;
+    const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
+    uint8_t* dst = base + first * stride;
+    const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
+    if (stride == elem) memcpy(dst, hb, n * elem);
+    else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, hb + i * elem, elem);
+  };
   for (uint64_t c = 0; c < n_chunks; c++) {
     const int k = (int)(c % kStages);
     const uint64_t first = c * chunk;
@@ -165,26 +239,16 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
       if (stride == elem) CU(cudaMemcpyAsync(st->d_buf[k], src, n * elem, cudaMemcpyHostToDevice, q));
       else CU(cudaMemcpy2DAsync(st->d_buf[k], elem, src, stride, elem, n, cudaMemcpyHostToDevice, q));
     } else {
-      // bounce through pinned memory: wait until this stage's previous round trip has drained
+      // pageable caller memory: bounce through pinned buffers; first drain this stage's previous round trip
       CU(cudaStreamSynchronize(q));
-      if (c >= (uint64_t)kStages) {
-        // write back the results of chunk c-kStages that used this bounce buffer
-        const uint64_t pfirst = (c - kStages) * chunk;
-        const size_t pn = (size_t)((M - pfirst) < chunk ? (M - pfirst) : chunk);
-        uint8_t* dst = base + pfirst * stride;
-        const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
-        if (stride == elem) memcpy(dst, hb, pn * elem);
-        else for (size_t i = 0; i < pn; i++) memcpy(dst + i * stride, hb + i * elem, elem);
-      }
+      if (c >= (uint64_t)kStages) unpack(c - kStages, k);
       uint8_t* hb = static_cast<uint8_t*>(st->h_pin[k]);
       if (stride == elem) memcpy(hb, src, n * elem);
       else for (size_t i = 0; i < n; i++) memcpy(hb + i * elem, src + i * stride, elem);
       CU(cudaMemcpyAsync(st->d_buf[k], hb, n * elem, cudaMemcpyHostToDevice, q));
     }
-    cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, st->d_buf[k], n, elem, q)
-                              : ecb_launch_intersect(s->dev, s->device, st->d_buf[k], n, elem, instID, nullptr, nullptr, q);
+    cudaError_t le = launch(k, n, elem, static_cast<uint8_t*>(st->d_buf[k]), elem);
     if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
-    g_launches.fetch_add(1);
     if (pinned) {
       if (stride == elem) CU(cudaMemcpyAsync(src, st->d_buf[k], n * elem, cudaMemcpyDeviceToHost, q));
       else CU(cudaMemcpy2DAsync(src, stride, st->d_buf[k], elem, elem, n, cudaMemcpyDeviceToHost, q));
@@ -195,15 +259,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
   if (!pinned) {
     const uint64_t tail0 = n_chunks > (uint64_t)kStages ? n_chunks - kStages : 0;
-    for (uint64_t c = tail0; c < n_chunks; c++) {
-      const int k = (int)(c % kStages);
-      const uint64_t first = c * chunk;
-      const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
-      uint8_t* dst = base + first * stride;
-      const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
-      if (stride == elem) memcpy(dst, hb, n * elem);
-      else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, hb + i * elem, elem);
-    }
+    for (uint64_t c = tail0; c < n_chunks; c++) unpack(c, (int)(c % kStages));
   }
   return ECB_SUCCESS;
 }
@@ -218,11 +274,21 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
   }
   ecbError err = ensure_resident(s, -1);
   if (err != ECB_SUCCESS) return err;
+  if (M == 0) return ECB_SUCCESS;
   cudaStream_t q = static_cast<cudaStream_t>(stream);
-  cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, d_rays, M, stride, q)
-                            : ecb_launch_intersect(s->dev, s->device, d_rays, M, stride, instID, d_block_out, d_counters, q);
+  EcbLaunch L;
+  L.in = static_cast<const uint8_t*>(d_rays);
+  L.in_stride = stride;
+  L.out = static_cast<uint8_t*>(d_rays);
+  L.out_stride = stride;
+  L.M = M;
+  L.instID = instID;
+  L.block_out = d_block_out;
+  L.counters = d_counters;
+  L.queue = next_queue(s);
+  cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, L, q) : ecb_launch_intersect(s->dev, s->device, L, q);
   if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
-  if (M) g_launches.fetch_add(1);
+  g_launches.fetch_add(1);
   return ECB_SUCCESS;
 }
 
@@ -384,6 +450,7 @@ void ecbSceneRelease(ecbScene* s) {
     delete s->staging;
     if (s->d_top) cudaFree(s->d_top);
     if (s->d_blocks) cudaFree(s->d_blocks);
+    if (s->d_queues) cudaFree(s->d_queues);
   }
   delete s;
 }

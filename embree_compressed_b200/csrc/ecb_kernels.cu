@@ -26,8 +26,13 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }  // _mm_max_ps operand semantics
-__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }
+// _mm_max_ps(a,b) = a > b ? a : b (second operand on NaN / equal zeros).  In the slab tests no operand can be NaN for a
+// finite ray ((plane - org) * rdir with |rdir| <= 1e18 and planes finite or +-inf) and the sign of a zero result never
+// reaches a bit-compare (tNear >= +0 always, see trace_closest), so the single-instruction IEEE min/max is identical.
+__device__ __forceinline__ float sse_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float sse_min(float a, float b) { return fminf(a, b); }
+// exact operand-order form, used where a NaN or a signed zero could make a difference (ray set-up)
+__device__ __forceinline__ float sse_max_exact(float a, float b) { return a > b ? a : b; }
 __device__ __forceinline__ float zero_fix(float a) { return fabsf(a) < 1E-18f ? 1E-18f : a; }
 
 __device__ __forceinline__ uint32_t compact1by1(uint32_t x) {
@@ -69,20 +74,6 @@ __device__ __forceinline__ void travray_init(TravRay& r, const float org[3], con
   }
   r.tnear = tnear;
   r.tfar = tfar;
-}
-
-// one child of a 4-wide node; lo/hi per axis
-__device__ __forceinline__ bool slab(const TravRay& r, float lx, float ux, float ly, float uy, float lz, float uz,
-                                     float& tn, float& tf) {
-  const float tnx = ((r.nu[0] ? ux : lx) - r.org[0]) * r.rdn[0];
-  const float tny = ((r.nu[1] ? uy : ly) - r.org[1]) * r.rdn[1];
-  const float tnz = ((r.nu[2] ? uz : lz) - r.org[2]) * r.rdn[2];
-  const float tfx = ((r.nu[0] ? lx : ux) - r.org[0]) * r.rdf[0];
-  const float tfy = ((r.nu[1] ? ly : uy) - r.org[1]) * r.rdf[1];
-  const float tfz = ((r.nu[2] ? lz : uz) - r.org[2]) * r.rdf[2];
-  tn = sse_max(sse_max(tnx, tny), sse_max(tnz, r.tnear));
-  tf = sse_min(sse_min(tfx, tfy), sse_min(tfz, r.tfar));
-  return tn <= tf;
 }
 
 __device__ __forceinline__ void project3(const float* m /*row-major 3x3*/, const float a[3], float out[3]) {
@@ -426,11 +417,20 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
     const float lz = (0.25f * (float)(xz & 3)) * dimZ + pBox[2];
     const float uz = (1.f - 0.25f * (float)(yz & 3)) * dimZ + pBox[2];
 
-    unsigned mask = 0;
-    if (slab(tr, lx02, ux02, ly01, uy01, lz, uz, tNear[0], tFar[0])) mask |= 1;
-    if (slab(tr, lx13, ux13, ly01, uy01, lz, uz, tNear[1], tFar[1])) mask |= 2;
-    if (slab(tr, lx02, ux02, ly23, uy23, lz, uz, tNear[2], tFar[2])) mask |= 4;
-    if (slab(tr, lx13, ux13, ly23, uy23, lz, uz, tNear[3], tFar[3])) mask |= 8;
+    // the four children share their planes: x ranges A (children 0,2) / B (1,3), y ranges A (0,1) / B (2,3), one z range
+    // (compressed_node.h:488-510) -> 5 near + 5 far plane distances instead of 24; same operands, same floats
+    const float tnxA = ((tr.nu[0] ? ux02 : lx02) - tr.org[0]) * tr.rdn[0], tfxA = ((tr.nu[0] ? lx02 : ux02) - tr.org[0]) * tr.rdf[0];
+    const float tnxB = ((tr.nu[0] ? ux13 : lx13) - tr.org[0]) * tr.rdn[0], tfxB = ((tr.nu[0] ? lx13 : ux13) - tr.org[0]) * tr.rdf[0];
+    const float tnyA = ((tr.nu[1] ? uy01 : ly01) - tr.org[1]) * tr.rdn[1], tfyA = ((tr.nu[1] ? ly01 : uy01) - tr.org[1]) * tr.rdf[1];
+    const float tnyB = ((tr.nu[1] ? uy23 : ly23) - tr.org[1]) * tr.rdn[1], tfyB = ((tr.nu[1] ? ly23 : uy23) - tr.org[1]) * tr.rdf[1];
+    const float tnz = ((tr.nu[2] ? uz : lz) - tr.org[2]) * tr.rdn[2], tfz = ((tr.nu[2] ? lz : uz) - tr.org[2]) * tr.rdf[2];
+    const float tnzn = sse_max(tnz, tr.tnear), tfzf = sse_min(tfz, tr.tfar);
+    tNear[0] = sse_max(sse_max(tnxA, tnyA), tnzn); tFar[0] = sse_min(sse_min(tfxA, tfyA), tfzf);
+    tNear[1] = sse_max(sse_max(tnxB, tnyA), tnzn); tFar[1] = sse_min(sse_min(tfxB, tfyA), tfzf);
+    tNear[2] = sse_max(sse_max(tnxA, tnyB), tnzn); tFar[2] = sse_min(sse_min(tfxA, tfyB), tfzf);
+    tNear[3] = sse_max(sse_max(tnxB, tnyB), tnzn); tFar[3] = sse_min(sse_min(tfxB, tfyB), tfzf);
+    const unsigned mask = (tNear[0] <= tFar[0] ? 1u : 0u) | (tNear[1] <= tFar[1] ? 2u : 0u) | (tNear[2] <= tFar[2] ? 4u : 0u) |
+                          (tNear[3] <= tFar[3] ? 8u : 0u);
     if (mask == 0) continue;
 
     // stack position of child r = sp+1 + #(hit children that must be popped after it)   (compressed.h:668-749)
@@ -461,29 +461,31 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
 // ---------------------------------------------------------------------------------------------------------------
 // top-level traversal
 // ---------------------------------------------------------------------------------------------------------------
-struct TopNodeRegs {
-  float b[6][4];
-  uint32_t child[4];
-};
-
-__device__ __forceinline__ void load_top(const EcbDeviceScene& sc, uint32_t index, TopNodeRegs& n) {
+// The near / far plane of each axis is picked by ADDRESS (like the reference's nearX/farX byte offsets,
+// node_intersector1.h:126-131): six 16-byte read-only loads deliver near and far planes of all four children.
+__device__ __forceinline__ unsigned top_node(const EcbDeviceScene& sc, uint32_t index, const TravRay& tr, float tNear[4],
+                                             uint32_t child[4]) {
   const float4* p = reinterpret_cast<const float4*>(sc.top + index);
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const float4 q = __ldg(p + i);
-    n.b[i][0] = q.x; n.b[i][1] = q.y; n.b[i][2] = q.z; n.b[i][3] = q.w;
-  }
+  const float4 nx = __ldg(p + tr.nu[0]), fx = __ldg(p + (1 - tr.nu[0]));
+  const float4 ny = __ldg(p + 2 + tr.nu[1]), fy = __ldg(p + (3 - tr.nu[1]));
+  const float4 nz = __ldg(p + 4 + tr.nu[2]), fz = __ldg(p + (5 - tr.nu[2]));
   const uint4 c = __ldg(reinterpret_cast<const uint4*>(p + 6));
-  n.child[0] = c.x; n.child[1] = c.y; n.child[2] = c.z; n.child[3] = c.w;
-}
-
-__device__ __forceinline__ unsigned top_test(const TopNodeRegs& n, const TravRay& tr, float tNear[4]) {
+  child[0] = c.x; child[1] = c.y; child[2] = c.z; child[3] = c.w;
   unsigned mask = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    float tf;
-    if (slab(tr, n.b[0][i], n.b[1][i], n.b[2][i], n.b[3][i], n.b[4][i], n.b[5][i], tNear[i], tf)) mask |= 1u << i;
+#define ECB_TOP_CHILD(i, m)                                                                                  \
+  {                                                                                                          \
+    const float tnx = (nx.m - tr.org[0]) * tr.rdn[0], tny = (ny.m - tr.org[1]) * tr.rdn[1], tnz = (nz.m - tr.org[2]) * tr.rdn[2]; \
+    const float tfx = (fx.m - tr.org[0]) * tr.rdf[0], tfy = (fy.m - tr.org[1]) * tr.rdf[1], tfz = (fz.m - tr.org[2]) * tr.rdf[2]; \
+    const float tn = sse_max(sse_max(tnx, tny), sse_max(tnz, tr.tnear));                                     \
+    const float tf = sse_min(sse_min(tfx, tfy), sse_min(tfz, tr.tfar));                                      \
+    tNear[i] = tn;                                                                                           \
+    if (tn <= tf) mask |= 1u << i;                                                                           \
   }
+  ECB_TOP_CHILD(0, x)
+  ECB_TOP_CHILD(1, y)
+  ECB_TOP_CHILD(2, z)
+  ECB_TOP_CHILD(3, w)
+#undef ECB_TOP_CHILD
   return mask;
 }
 
@@ -496,35 +498,28 @@ __device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, 
   }
 }
 
-template <int LEAF, bool STATS>
-__device__ __forceinline__ void trace_closest(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
-                                              float ray_tnear, Hit& hit, Work& work) {
-  uint32_t stack_ref[ECB_MAX_TOP_STACK];
-  uint32_t stack_dist[ECB_MAX_TOP_STACK];
-  int sp = 1;
-  stack_ref[0] = sc.root;
-  stack_dist[0] = 0xff800000u;
-  TravRay tr;
-  travray_init(tr, org, dir, sse_max(ray_tnear, 0.0f), sse_max(hit.tfar, 0.0f));
-
+// Pops / descends the top-level BVH4 until the ray reaches a block (returns its leaf ref) or the stack runs empty
+// (returns ECB_REF_EMPTY).  Resumable: the caller keeps stack and sp between calls (one call per block entered).
+// Restates the pop loop + down loop of bvh_intersector1.cpp:73-105 with traverseClosestHit (bvh_traverser1.h:436-506).
+template <bool STATS>
+__device__ __forceinline__ uint32_t next_block(const EcbDeviceScene& sc, const TravRay& tr, uint32_t* stack_ref, uint32_t* stack_dist,
+                                               int& sp, float ray_tfar, Work& work) {
   while (sp > 0) {
     sp--;
     uint32_t cur = stack_ref[sp];
-    if (__uint_as_float(stack_dist[sp]) > hit.tfar) continue;
+    if (__uint_as_float(stack_dist[sp]) > ray_tfar) continue;
     bool popped = false;
     while (!(cur & ECB_REF_LEAF)) {
-      TopNodeRegs n;
-      load_top(sc, cur, n);
       if (STATS) work.top_nodes++;
       float tNear[4];
-      const unsigned mask = top_test(n, tr, tNear);
+      uint32_t child[4];
+      const unsigned mask = top_node(sc, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
-      // traverseClosestHit (bvh_traverser1.h:436-506)
       uint32_t c[4], d[4];
       int nh = 0;
 #pragma unroll
       for (int r = 0; r < 4; r++)
-        if (mask & (1u << r)) { c[nh] = n.child[r]; d[nh] = __float_as_uint(tNear[r]); nh++; }
+        if (mask & (1u << r)) { c[nh] = child[r]; d[nh] = __float_as_uint(tNear[r]); nh++; }
       if (nh == 1) { cur = c[0]; continue; }
       if (nh == 2) {
         if (d[0] < d[1]) { stack_ref[sp] = c[1]; stack_dist[sp] = d[1]; sp++; cur = c[0]; }
@@ -532,7 +527,7 @@ __device__ __forceinline__ void trace_closest(const EcbDeviceScene& sc, const fl
         continue;
       }
       if (nh == 3) {
-        // items pushed in order c0,c1,c2 ; sort(s1=top(c2), s2=c1, s3=c0)
+        // items pushed in order c0,c1,c2 ; sort(s1=top(c2), s2=c1, s3=c0)  (stack_item.h:45-50)
         uint32_t r1 = c[2], d1 = d[2], r2 = c[1], d2 = d[1], r3 = c[0], d3 = d[0];
         cswap(r1, d1, r2, d2);
         cswap(r2, d2, r3, d3);
@@ -556,9 +551,9 @@ __device__ __forceinline__ void trace_closest(const EcbDeviceScene& sc, const fl
       }
     }
     if (popped || cur == ECB_REF_EMPTY) continue;
-    block_intersect<LEAF, STATS>(sc, lut, cur & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
-    tr.tfar = hit.tfar;
+    return cur;
   }
+  return ECB_REF_EMPTY;
 }
 
 // any-hit: the first block whose world box the ray segment overlaps occludes (compressed.h:754-756 returns true)
@@ -568,25 +563,24 @@ __device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float 
   int sp = 1;
   stack_ref[0] = sc.root;
   TravRay tr;
-  travray_init(tr, org, dir, sse_max(ray_tnear, 0.0f), sse_max(ray_tfar, 0.0f));
+  travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(ray_tfar, 0.0f));
   while (sp > 0) {
     sp--;
     uint32_t cur = stack_ref[sp];
     bool popped = false;
     while (!(cur & ECB_REF_LEAF)) {
-      TopNodeRegs n;
-      load_top(sc, cur, n);
       float tNear[4];
-      const unsigned mask = top_test(n, tr, tNear);
+      uint32_t child[4];
+      const unsigned mask = top_node(sc, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
       int last = -1;
 #pragma unroll
       for (int r = 0; r < 4; r++)
         if (mask & (1u << r)) {
-          if (last >= 0) stack_ref[sp++] = n.child[last];
+          if (last >= 0) stack_ref[sp++] = child[last];
           last = r;
         }
-      cur = n.child[last];
+      cur = child[last];
     }
     if (popped || cur == ECB_REF_EMPTY) continue;
     return true;
@@ -595,66 +589,140 @@ __device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// kernels: one thread per ray, grid-stride persistent loop, AoS RTCRayHit / RTCRay in place
+// closest-hit kernel: persistent warps, dynamic ray fetch with lane refill, while-while traversal
+//
+//   * The grid is sized to the machine (SMs x ECB_BLOCKS_PER_SM CTAs); warps pull chunks of ECB_CHUNK consecutive ray
+//     indices from a global queue (one atomicAdd per chunk) and hand them to their idle lanes.
+//   * Every lane keeps its own ray, top-level stack and hit.  One outer iteration lets each busy lane run to its next
+//     block (or to termination) and then traverse that block; when fewer than ECB_REFILL_MIN lanes are still busy the
+//     warp goes back to refill the idle ones, so short rays (sky pixels, bounce rays that leave the scene at once)
+//     do not leave lanes idle for the duration of the longest ray.
+//   * Rays are read from `in` (stride in_stride: RTCRayHit = 80, or a packed RTCRay copy = 48) and hits are written
+//     to `out` (the caller's RTCRayHit array; may be mapped pinned host memory -> no device-to-host copy at all).
 // ---------------------------------------------------------------------------------------------------------------
 template <int LEAF, bool STATS>
-__global__ void __launch_bounds__(ECB_THREADS) ecb_intersect_kernel(EcbDeviceScene sc, uint8_t* __restrict__ rays, uint64_t M,
-                                                                    size_t stride, uint32_t instID,
-                                                                    uint32_t* __restrict__ block_out,
-                                                                    unsigned long long* __restrict__ counters) {
+__global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_kernel(EcbDeviceScene sc, EcbLaunch L) {
   __shared__ float lut[32];
   init_lut(lut);
   __syncthreads();
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   Work work = {0u, 0u, 0u, 0u};
   uint32_t n_rays = 0, n_hits = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-    uint8_t* rp = rays + i * stride;
-    const float4 r0 = *reinterpret_cast<const float4*>(rp);       // org.xyz, tnear
-    const float4 r1 = *reinterpret_cast<const float4*>(rp + 16);  // dir.xyz, time
-    const float tfar_in = *reinterpret_cast<const float*>(rp + 32);
-    if (block_out) block_out[i] = 0xFFFFFFFFu;
-    if (r0.w > tfar_in) continue;  // inactive stream ray
-    const float org[3] = {r0.x, r0.y, r0.z};
-    const float dir[3] = {r1.x, r1.y, r1.z};
-    Hit hit;
-    hit.tfar = tfar_in;
-    hit.block = 0xFFFFFFFFu;
-    hit.u = hit.v = 0.f;
-    hit.primID = hit.geomID = 0xFFFFFFFFu;
-    if (sc.root != ECB_REF_EMPTY) trace_closest<LEAF, STATS>(sc, lut, org, dir, r0.w, hit, work);
-    if (STATS) n_rays++;
-    if (hit.block != 0xFFFFFFFFu) {
-      if (STATS) n_hits++;
-      *reinterpret_cast<float*>(rp + 32) = hit.tfar;
-      *reinterpret_cast<float4*>(rp + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
-      *reinterpret_cast<float4*>(rp + 64) =
-          make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(instID));
-      if (block_out) block_out[i] = hit.block;
+
+  // warp-private chunk of ray indices (uniform across the warp)
+  uint64_t chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+
+  // per-lane ray state
+  bool busy = false;
+  uint64_t index = 0;
+  float org[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
+  float ray_tnear = 0.f;
+  TravRay tr;
+  Hit hit;
+  hit.tfar = 0.f; hit.u = hit.v = 0.f; hit.primID = hit.geomID = hit.block = 0xFFFFFFFFu;
+  uint32_t stack_ref[ECB_MAX_TOP_STACK];
+  uint32_t stack_dist[ECB_MAX_TOP_STACK];
+  int sp = 0;
+  travray_init(tr, org, dir, 0.f, 0.f);
+
+  for (;;) {
+    // ---- refill idle lanes ----
+    unsigned need = __ballot_sync(0xffffffffu, !busy);
+    while (need && !exhausted) {
+      if (chunk_next == chunk_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(L.queue, (unsigned long long)ECB_CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= L.M) { exhausted = true; break; }
+        chunk_next = base;
+        chunk_end = base + ECB_CHUNK < L.M ? base + ECB_CHUNK : L.M;
+      }
+      const unsigned avail = (unsigned)(chunk_end - chunk_next);
+      const unsigned n_need = __popc(need);
+      const unsigned take = avail < n_need ? avail : n_need;
+      const unsigned rank = __popc(need & lt_mask);
+      const bool mine = ((need >> lane) & 1u) && rank < take;
+      if (mine) {
+        index = chunk_next + rank;
+        const uint8_t* rp = L.in + index * L.in_stride;
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));       // org.xyz, tnear
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
+        const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+        if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
+        if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY) {  // tnear > tfar: inactive stream ray
+          org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
+          dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
+          ray_tnear = r0.w;
+          hit.tfar = tfar_in;
+          hit.block = 0xFFFFFFFFu;
+          travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(tfar_in, 0.0f));
+          stack_ref[0] = sc.root;
+          stack_dist[0] = 0xff800000u;  // -inf
+          sp = 1;
+          busy = true;
+          if (STATS) n_rays++;
+        }
+      }
+      chunk_next += take;
+      // lanes served in this round (busy or consumed an inactive ray) leave the need mask
+      need &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (!__any_sync(0xffffffffu, busy)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- traverse until too few lanes are busy ----
+    for (;;) {
+      uint32_t leaf = ECB_REF_EMPTY;
+      if (busy) {
+        leaf = next_block<STATS>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+        if (leaf == ECB_REF_EMPTY) {
+          // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
+          busy = false;
+          if (hit.block != 0xFFFFFFFFu) {
+            uint8_t* op = L.out + index * L.out_stride;
+            *reinterpret_cast<float*>(op + 32) = hit.tfar;
+            *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
+            *reinterpret_cast<float4*>(op + 64) =
+                make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(L.instID));
+            if (L.block_out) L.block_out[index] = hit.block;
+            if (STATS) n_hits++;
+          }
+        }
+      }
+      if (leaf != ECB_REF_EMPTY) {
+        block_intersect<LEAF, STATS>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+        tr.tfar = hit.tfar;  // bvh_intersector1.cpp:117
+      }
+      const unsigned alive = __popc(__ballot_sync(0xffffffffu, busy));
+      if (alive == 0 || (alive < ECB_REFILL_MIN && !exhausted)) break;
     }
   }
   if (STATS) {
-    atomicAdd(counters + 0, (unsigned long long)n_rays);
-    atomicAdd(counters + 1, (unsigned long long)work.top_nodes);
-    atomicAdd(counters + 2, (unsigned long long)work.blocks);
-    atomicAdd(counters + 3, (unsigned long long)work.cnodes);
-    atomicAdd(counters + 4, (unsigned long long)work.cells);
-    atomicAdd(counters + 5, (unsigned long long)n_hits);
+    atomicAdd(L.counters + 0, (unsigned long long)n_rays);
+    atomicAdd(L.counters + 1, (unsigned long long)work.top_nodes);
+    atomicAdd(L.counters + 2, (unsigned long long)work.blocks);
+    atomicAdd(L.counters + 3, (unsigned long long)work.cnodes);
+    atomicAdd(L.counters + 4, (unsigned long long)work.cells);
+    atomicAdd(L.counters + 5, (unsigned long long)n_hits);
   }
 }
 
-__global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, uint8_t* __restrict__ rays, uint64_t M,
-                                                                   size_t stride) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-    uint8_t* rp = rays + i * stride;
-    const float4 r0 = *reinterpret_cast<const float4*>(rp);
-    const float4 r1 = *reinterpret_cast<const float4*>(rp + 16);
-    const float tfar_in = *reinterpret_cast<const float*>(rp + 32);
+__global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, EcbLaunch L) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* rp = L.in + i * L.in_stride;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
     if (r0.w > tfar_in) continue;
     if (tfar_in < 0.0f) continue;  // bvh_intersector1.cpp:133
     const float org[3] = {r0.x, r0.y, r0.z};
     const float dir[3] = {r1.x, r1.y, r1.z};
     if (sc.root != ECB_REF_EMPTY && trace_any(sc, org, dir, r0.w, tfar_in))
-      *reinterpret_cast<float*>(rp + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
+      *reinterpret_cast<float*>(L.out + i * L.out_stride + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
   }
 }
 
@@ -677,16 +745,16 @@ static int grid_for(uint64_t M, int device) {
   return (int)(need < cap ? (need ? need : 1) : cap);
 }
 
-cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, void* d_rayhit, uint64_t M, size_t stride, uint32_t instID,
-                                 uint32_t* d_block_out, unsigned long long* d_counters, cudaStream_t stream) {
-  if (M == 0) return cudaSuccess;
-  const int grid = grid_for(M, device);
-  uint8_t* rays = static_cast<uint8_t*>(d_rayhit);
-#define ECB_LAUNCH(LEAF)                                                                                                  \
-  if (d_counters)                                                                                                         \
-    ecb_intersect_kernel<LEAF, true><<<grid, ECB_THREADS, 0, stream>>>(sc, rays, M, stride, instID, d_block_out, d_counters); \
-  else                                                                                                                    \
-    ecb_intersect_kernel<LEAF, false><<<grid, ECB_THREADS, 0, stream>>>(sc, rays, M, stride, instID, d_block_out, nullptr)
+cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream) {
+  if (L.M == 0) return cudaSuccess;
+  const int grid = grid_for(L.M, device);
+  cudaError_t e = cudaMemsetAsync(L.queue, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+#define ECB_LAUNCH(LEAF)                                                                  \
+  if (L.counters)                                                                         \
+    ecb_intersect_kernel<LEAF, true><<<grid, ECB_THREADS, 0, stream>>>(sc, L);            \
+  else                                                                                    \
+    ecb_intersect_kernel<LEAF, false><<<grid, ECB_THREADS, 0, stream>>>(sc, L)
   switch (sc.leaf_kind) {
     case 0: ECB_LAUNCH(0); break;
     case 1: ECB_LAUNCH(1); break;
@@ -696,10 +764,9 @@ cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, void* d_r
   return cudaGetLastError();
 }
 
-cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, void* d_ray, uint64_t M, size_t stride, cudaStream_t stream) {
-  if (M == 0) return cudaSuccess;
-  const int grid = grid_for(M, device);
-  ecb_occluded_kernel<<<grid, ECB_THREADS, 0, stream>>>(sc, static_cast<uint8_t*>(d_ray), M, stride);
+cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream) {
+  if (L.M == 0) return cudaSuccess;
+  const int grid = grid_for(L.M, device);
+  ecb_occluded_kernel<<<grid, ECB_THREADS, 0, stream>>>(sc, L);
   return cudaGetLastError();
 }
-

@@ -5,9 +5,35 @@
 
 #include "ecb_format.h"
 
+#ifndef ECB_THREADS
 #define ECB_THREADS 128        // threads per CTA
+#endif
+#ifndef ECB_BLOCKS_PER_SM
 #define ECB_BLOCKS_PER_SM 8    // persistent grid = SMs x this
+#endif
+#ifndef ECB_MIN_BLOCKS
+#define ECB_MIN_BLOCKS 4       // __launch_bounds__ occupancy target (caps registers per thread)
+#endif
 
-cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, void* d_rayhit, uint64_t M, size_t stride, uint32_t instID,
-                                 uint32_t* d_block_out, unsigned long long* d_counters, cudaStream_t stream);
-cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, void* d_ray, uint64_t M, size_t stride, cudaStream_t stream);
+#ifndef ECB_CHUNK
+#define ECB_CHUNK 128          // ray indices a warp takes from the global queue per atomic
+#endif
+#ifndef ECB_REFILL_MIN
+#define ECB_REFILL_MIN 20      // a warp goes back to fetch rays when fewer lanes than this are still traversing
+#endif
+
+// One launch: where rays are read, where hits are written (may be the same array, may be mapped host memory).
+struct EcbLaunch {
+  const uint8_t* in;              // RTCRayHit / RTCRay records (org,tnear,dir,time,tfar in the first 36 bytes)
+  size_t in_stride;
+  uint8_t* out;                   // RTCRayHit / RTCRay records that receive tfar + hit
+  size_t out_stride;
+  uint64_t M;
+  uint32_t instID;
+  uint32_t* block_out;            // optional: index of the block of the final hit per ray
+  unsigned long long* counters;   // optional: instrumented variant (6 counters)
+  unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)
+};
+
+cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
+cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);

@@ -1,5 +1,6 @@
 // ecb_scene.h -- host-side scene object behind the opaque ecbScene handle.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <mutex>
 #include <string>
@@ -23,6 +24,10 @@ struct ecbScene {
   void* d_top = nullptr;
   void* d_blocks = nullptr;
   EcbDeviceScene dev{};
+
+  // ring of device words used as dynamic ray-fetch cursors, one per launch in flight
+  unsigned long long* d_queues = nullptr;
+  std::atomic<uint32_t> next_queue{0};
 
   // staging for the host-buffer entry points (lazily created, per scene)
   struct Staging* staging = nullptr;

@@ -216,7 +216,9 @@ def test_full_size_configs(ecb, reference, ref_scene, leaf):
         # miss, and moves t by at most the tolerance (a hit at t == tfar may be re-found within rounding)
         again = got.copy()
         scene.intersect1M(again)
-        assert (again[:, 8] <= got[:, 8]).all()
+        # (the pizza-box path maps t through the local frame and back, t/zFactor + near, so a re-found hit may land one
+        # rounding step beyond the old tfar -- the reference does the same)
+        assert (again[:, 8] <= got[:, 8] * (1 + 1e-6)).all()
         assert (again.view(np.uint32)[:, 18] == got.view(np.uint32)[:, 18]).all()
         hit = got.view(np.uint32)[:, 18] != 0xFFFFFFFF
         assert (np.abs(again[hit, 8] - got[hit, 8]) <= 1e-5 * np.abs(got[hit, 8])).all()
