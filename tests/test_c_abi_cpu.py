@@ -1,0 +1,108 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads, exports what include/ecb200.h declares, and its host-side logic
+(importer, serialisation, argument checks) works without a GPU.  No compute call is made here."""
+import os
+import re
+
+import ctypes as C
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ecb200.h")).read()
+    return sorted(set(re.findall(r"ECB_API\s+[\w\s\*]+?\b(ecb\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(ecb):
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    lib = C.CDLL(ecb.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libecb200.so does not export %s" % name
+    assert sorted(ecb.SYMBOLS) == declared, "python binding and header disagree"
+
+
+def test_kernel_image_is_sm_100a(ecb):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", ecb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+@pytest.mark.parametrize("name", ["cube_s4c2_leaf", "cube_s4c2_grid", "cube_s4c2_box", "cube_s4c1_grid"])
+def test_import_image_and_blob_round_trip(ecb, name, tmp_path):
+    image = np.fromfile(os.path.join(GOLDEN, name + ".rimg"), np.uint8)
+    scene = ecb.Scene.from_image(image)
+    info = scene.info()
+    C_ = info["comp_level"]
+    assert info["n_blocks"] > 0 and info["micro_triangles"] == 2 * 4 ** C_ * info["n_blocks"]
+    assert info["block_stride"] % 16 == 0 and info["top_node_bytes"] == 112
+    assert info["device_bytes"] == info["n_top_nodes"] * 112 + info["n_blocks"] * info["block_stride"]
+    assert info["device_bytes"] < info["reference_bytes"], "device format should be smaller than the reference layout"
+    assert info["device"] == -1
+    p = str(tmp_path / "s.ecbs")
+    scene.save(p)
+    again = ecb.Scene.load(p)
+    i2 = again.info()
+    for k in ("leaf_kind", "comp_level", "n_top_nodes", "n_blocks", "top_depth", "block_stride", "device_bytes", "reference_bytes"):
+        assert info[k] == i2[k]
+    n = scene.block_normals()
+    assert n.shape == (info["n_blocks"], 3) and np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-3)
+    assert (again.block_normals() == n).all()
+    # a blob with a corrupted child reference is rejected, not trusted
+    raw = bytearray(open(p, "rb").read())
+    hdr = 8 + 4 * 13 + 4 * 6 + 4 + 8 * 3
+    raw[hdr + 96:hdr + 100] = (0x7FFFFFF0).to_bytes(4, "little")
+    bad = str(tmp_path / "bad.ecbs")
+    open(bad, "wb").write(raw)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(bad)
+
+
+def test_importer_rejects_bad_input(ecb):
+    image = np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.from_image(image[:64])
+    junk = image.copy()
+    junk[:8] = 0
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.from_image(junk)
+    from oracle import pyoracle as po
+    h = po.rimg_header(image)
+    with pytest.raises(ecb.EcbError):   # compression level that does not match the blocks
+        ecb.Scene.import_bvh4(int(h["root"]), "leaf", 3, 4, int(h["proj_col_major"]), image.ctypes.data)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.import_bvh4(int(h["root"]), "leaf", 9, 4, 1, image.ctypes.data)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load("/nonexistent/scene.ecbs")
+
+
+def test_no_cpu_fallback(ecb):
+    """Without a CUDA device every traversal entry point must fail loudly with ECB_ERROR_NO_DEVICE."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from embree_compressed_b200 import raygen as rg
+    scene = ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8))
+    rays = rg.primary_rays(8, 8, **rg.CUBE_CAMERA)
+    before = rays.copy()
+    for call in (lambda: scene.intersect1M(rays), lambda: scene.occluded1M(rg.rays_only(rays)),
+                 lambda: scene.intersect1(rays[0]), lambda: scene.upload(0)):
+        with pytest.raises(ecb.EcbError) as e:
+            call()
+        assert e.value.code == ecb.ERROR_NO_DEVICE
+    assert (rays.view(np.uint32) == before.view(np.uint32)).all()
+
+
+def test_argument_checks(ecb):
+    scene = ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8))
+    with pytest.raises(ValueError):
+        scene.intersect1M(np.zeros((4, 12), np.float32))
+    with pytest.raises(ValueError):
+        scene.intersect1M(np.zeros((4, 20), np.float64))
+    scene.intersect1M(np.zeros((0, 20), np.float32))  # M == 0 is a no-op on any machine
