@@ -65,6 +65,15 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("g++ failed building libembree3_b200.so")
+    demo_src = os.path.join(HERE, "..", "tests", "cpp", "shim_demo.cpp")
+    demo = os.path.join(HERE, "..", "tests", "cpp", "shim_demo")
+    if os.path.exists(demo_src) and os.path.exists(SHIM) and (force or _stale(demo, [demo_src, SHIM])):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", demo, demo_src, "-L" + HERE, "-lembree3_b200", "-lecb200",
+               "-Wl,-rpath," + HERE]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building tests/cpp/shim_demo")
     return LIB
 
 

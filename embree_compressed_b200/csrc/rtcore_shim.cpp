@@ -1,0 +1,413 @@
+// rtcore_shim.cpp -- libembree3_b200.so: the embree3 API surface of the compressed-BVH path with the traversal on B200.
+//
+// A caller of the reference's API (rtcNewDevice ... rtcCommitScene, rtcIntersect1/4/8/16/1M, rtcOccluded1/4/8/16/1M,
+// same struct layouts; include/embree3/rtcore_scene.h:43-133) links against this library instead of libembree3.so:
+//   * scene CONSTRUCTION is forwarded to a host Embree (the reference: its CPU builder stays the builder), which is
+//     dlopen'ed from the path given by the device config key `host_embree=` or by $ECB200_HOST_EMBREE;
+//   * rtcCommitScene commits on the host, asks the host for the committed compressed BVH4
+//     (rtcGetCompressedBVH_b200, the accessor INTEGRATION.md adds to kernels/common/rtcore.cpp) and converts it with
+//     ecbSceneImportBVH4 into the device scene;
+//   * every ray query runs in the CUDA kernels through the C ABI of include/ecb200.h.  There is NO fallback to the
+//     host's intersectors: if the device path cannot serve a scene or there is no GPU, the call raises an RTCError
+//     through the reference's sticky-error convention (rtcGetDeviceError / error callback, kernels/common/rtcore.h:40-69)
+//     and leaves the rays untouched.
+// rtcIntersect4/8/16/1M crash in the reference on this accel (null intersector pointers); here they
+// are defined as "rtcIntersect1 applied to every active ray", which is Embree's contract for packets and streams.
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/ecb200.h"
+#include "../../include/embree3_b200/rtcore_subset.h"
+
+namespace {
+
+struct HostApi {
+  void* lib = nullptr;
+#define HOST_FN(ret, name, args) ret(*name) args = nullptr;
+  HOST_FN(RTCDevice, rtcNewDevice, (const char*))
+  HOST_FN(void, rtcReleaseDevice, (RTCDevice))
+  HOST_FN(RTCError, rtcGetDeviceError, (RTCDevice))
+  HOST_FN(RTCGeometry, rtcNewGeometry, (RTCDevice, RTCGeometryType))
+  HOST_FN(void, rtcRetainGeometry, (RTCGeometry))
+  HOST_FN(void, rtcReleaseGeometry, (RTCGeometry))
+  HOST_FN(void, rtcCommitGeometry, (RTCGeometry))
+  HOST_FN(void, rtcEnableGeometry, (RTCGeometry))
+  HOST_FN(void, rtcDisableGeometry, (RTCGeometry))
+  HOST_FN(void, rtcSetGeometryTimeStepCount, (RTCGeometry, unsigned))
+  HOST_FN(void, rtcSetGeometryVertexAttributeCount, (RTCGeometry, unsigned))
+  HOST_FN(void, rtcSetGeometryBuildQuality, (RTCGeometry, RTCBuildQuality))
+  HOST_FN(void, rtcSetSharedGeometryBuffer, (RTCGeometry, RTCBufferType, unsigned, RTCFormat, const void*, size_t, size_t, size_t))
+  HOST_FN(void*, rtcSetNewGeometryBuffer, (RTCGeometry, RTCBufferType, unsigned, RTCFormat, size_t, size_t))
+  HOST_FN(void*, rtcGetGeometryBufferData, (RTCGeometry, RTCBufferType, unsigned))
+  HOST_FN(void, rtcUpdateGeometryBuffer, (RTCGeometry, RTCBufferType, unsigned))
+  HOST_FN(void, rtcSetGeometryUserData, (RTCGeometry, void*))
+  HOST_FN(void*, rtcGetGeometryUserData, (RTCGeometry))
+  HOST_FN(void, rtcSetGeometryTessellationRate, (RTCGeometry, float))
+  HOST_FN(void, rtcSetGeometryTopologyCount, (RTCGeometry, unsigned))
+  HOST_FN(void, rtcSetGeometrySubdivisionMode, (RTCGeometry, unsigned, RTCSubdivisionMode))
+  HOST_FN(void, rtcSetGeometryVertexAttributeTopology, (RTCGeometry, unsigned, unsigned))
+  HOST_FN(void, rtcSetGeometryDisplacementFunction, (RTCGeometry, RTCDisplacementFunctionN))
+  HOST_FN(void, rtcInterpolate, (const RTCInterpolateArguments*))
+  HOST_FN(RTCScene, rtcNewScene, (RTCDevice))
+  HOST_FN(void, rtcReleaseScene, (RTCScene))
+  HOST_FN(unsigned, rtcAttachGeometry, (RTCScene, RTCGeometry))
+  HOST_FN(void, rtcAttachGeometryByID, (RTCScene, RTCGeometry, unsigned))
+  HOST_FN(void, rtcDetachGeometry, (RTCScene, unsigned))
+  HOST_FN(RTCGeometry, rtcGetGeometry, (RTCScene, unsigned))
+  HOST_FN(void, rtcSetSceneLevels, (RTCScene, unsigned, unsigned))
+  HOST_FN(void, rtcCommitScene, (RTCScene))
+  HOST_FN(void, rtcSetSceneBuildQuality, (RTCScene, RTCBuildQuality))
+  HOST_FN(void, rtcSetSceneFlags, (RTCScene, RTCSceneFlags))
+  HOST_FN(RTCSceneFlags, rtcGetSceneFlags, (RTCScene))
+  HOST_FN(void, rtcGetSceneBounds, (RTCScene, RTCBounds*))
+  HOST_FN(int, rtcGetCompressedBVH_b200, (RTCScene, RTCCompressedBVHInfo_b200*))
+#undef HOST_FN
+};
+
+struct ShimDevice {
+  std::atomic<int> refs{1};
+  HostApi host;
+  RTCDevice hdev = nullptr;
+  std::mutex mutex;
+  RTCError error = RTC_ERROR_NONE;
+  RTCErrorFunction callback = nullptr;
+  void* callback_ptr = nullptr;
+  int verbose = 0;
+
+  void raise(RTCError code, const std::string& msg) {
+    RTCErrorFunction cb;
+    void* p;
+    {
+      std::lock_guard<std::mutex> lock(mutex);
+      if (error == RTC_ERROR_NONE) error = code;  // first error sticks (kernels/common/device.cpp process_error)
+      cb = callback;
+      p = callback_ptr;
+    }
+    if (cb) cb(p, code, msg.c_str());
+    if (verbose) fprintf(stderr, "embree3_b200: error %d: %s\n", (int)code, msg.c_str());
+  }
+};
+
+struct ShimScene {
+  std::atomic<int> refs{1};
+  ShimDevice* dev = nullptr;
+  RTCScene hscene = nullptr;
+  ecbScene* gpu = nullptr;
+  std::mutex mutex;
+};
+
+// handles of one geometry are the host's own handles; scenes and devices are wrapped
+inline ShimDevice* D(RTCDevice d) { return reinterpret_cast<ShimDevice*>(d); }
+inline ShimScene* S(RTCScene s) { return reinterpret_cast<ShimScene*>(s); }
+
+// the device of a geometry is not recoverable from the host handle, so pass-through geometry calls use the last
+// device that created a geometry on this thread's process (one host library per process in practice)
+std::atomic<ShimDevice*> g_any_device{nullptr};
+thread_local RTCError g_thread_error = RTC_ERROR_NONE;  // errors without a device (rtcore.cpp:79-98)
+
+RTCError map_error(ecbError e) {
+  switch (e) {
+    case ECB_SUCCESS: return RTC_ERROR_NONE;
+    case ECB_ERROR_INVALID_ARGUMENT: return RTC_ERROR_INVALID_ARGUMENT;
+    case ECB_ERROR_INVALID_OPERATION: return RTC_ERROR_INVALID_OPERATION;
+    case ECB_ERROR_OUT_OF_MEMORY: return RTC_ERROR_OUT_OF_MEMORY;
+    case ECB_ERROR_UNSUPPORTED: return RTC_ERROR_INVALID_OPERATION;
+    default: return RTC_ERROR_UNKNOWN;  // CUDA errors and "no device": SURVEY 5 (RTC_ERROR_UNKNOWN, sticky)
+  }
+}
+
+bool load_host(HostApi& h, const std::string& path, std::string& err) {
+  h.lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!h.lib) {
+    err = std::string("cannot load host embree '") + path + "': " + dlerror();
+    return false;
+  }
+#define RESOLVE(name)                                                   \
+  h.name = reinterpret_cast<decltype(h.name)>(dlsym(h.lib, #name));     \
+  if (!h.name) { err = std::string("host embree lacks ") + #name; return false; }
+  RESOLVE(rtcNewDevice) RESOLVE(rtcReleaseDevice) RESOLVE(rtcGetDeviceError) RESOLVE(rtcNewGeometry) RESOLVE(rtcRetainGeometry)
+  RESOLVE(rtcReleaseGeometry) RESOLVE(rtcCommitGeometry) RESOLVE(rtcEnableGeometry) RESOLVE(rtcDisableGeometry)
+  RESOLVE(rtcSetGeometryTimeStepCount) RESOLVE(rtcSetGeometryVertexAttributeCount) RESOLVE(rtcSetGeometryBuildQuality)
+  RESOLVE(rtcSetSharedGeometryBuffer) RESOLVE(rtcSetNewGeometryBuffer) RESOLVE(rtcGetGeometryBufferData) RESOLVE(rtcUpdateGeometryBuffer)
+  RESOLVE(rtcSetGeometryUserData) RESOLVE(rtcGetGeometryUserData) RESOLVE(rtcSetGeometryTessellationRate)
+  RESOLVE(rtcSetGeometryTopologyCount) RESOLVE(rtcSetGeometrySubdivisionMode) RESOLVE(rtcSetGeometryVertexAttributeTopology)
+  RESOLVE(rtcSetGeometryDisplacementFunction) RESOLVE(rtcInterpolate) RESOLVE(rtcNewScene) RESOLVE(rtcReleaseScene)
+  RESOLVE(rtcAttachGeometry) RESOLVE(rtcAttachGeometryByID) RESOLVE(rtcDetachGeometry) RESOLVE(rtcGetGeometry) RESOLVE(rtcSetSceneLevels)
+  RESOLVE(rtcCommitScene) RESOLVE(rtcSetSceneBuildQuality) RESOLVE(rtcSetSceneFlags) RESOLVE(rtcGetSceneFlags) RESOLVE(rtcGetSceneBounds)
+#undef RESOLVE
+  h.rtcGetCompressedBVH_b200 = reinterpret_cast<decltype(h.rtcGetCompressedBVH_b200)>(dlsym(h.lib, "rtcGetCompressedBVH_b200"));
+  if (!h.rtcGetCompressedBVH_b200) {
+    err = "host embree does not export rtcGetCompressedBVH_b200 (apply the accessor of INTEGRATION.md)";
+    return false;
+  }
+  return true;
+}
+
+// splits "key=value,key=value" ; returns the config for the host with our keys removed
+std::string parse_config(const char* cfg, std::string& host_path, int& verbose) {
+  std::string rest;
+  std::string s = cfg ? cfg : "";
+  size_t i = 0;
+  while (i <= s.size()) {
+    size_t j = s.find(',', i);
+    if (j == std::string::npos) j = s.size();
+    std::string item = s.substr(i, j - i);
+    i = j + 1;
+    if (item.empty()) continue;
+    if (item.compare(0, 12, "host_embree=") == 0) { host_path = item.substr(12); continue; }
+    if (item.compare(0, 8, "verbose=") == 0) verbose = atoi(item.c_str() + 8);
+    if (!rest.empty()) rest += ",";
+    rest += item;
+  }
+  return rest;
+}
+
+uint32_t ctx_inst(const RTCIntersectContext* c) { return c ? c->instID[0] : RTC_INVALID_GEOMETRY_ID; }
+
+bool ready(ShimScene* s, const char* what) {
+  if (!s) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return false; }
+  if (!s->gpu) {
+    s->dev->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": scene not committed to the B200 path");
+    return false;
+  }
+  return true;
+}
+
+void check(ShimScene* s, ecbError e, const char* what) {
+  if (e != ECB_SUCCESS) s->dev->raise(map_error(e), std::string(what) + ": " + ecbErrorString(e) + " " + ecbLastErrorMessage());
+}
+
+// SoA packets of N rays <-> N AoS RTCRayHit records.  The SoA structs are 20 (12 for RTCRayN) arrays of N words.
+template <int N>
+void packet_intersect(const int* valid, ShimScene* s, RTCIntersectContext* ctx, void* packet, bool occluded) {
+  const int fields = occluded ? 12 : 20;
+  alignas(16) uint32_t aos[N][20];
+  uint32_t* soa = static_cast<uint32_t*>(packet);
+  const float one = 1.f, zero = 0.f;
+  for (int l = 0; l < N; l++) {
+    for (int f = 0; f < fields; f++) aos[l][f] = soa[f * N + l];
+    if (valid[l] != -1) {  // inactive lane -> inactive stream ray
+      memcpy(&aos[l][3], &one, 4);
+      memcpy(&aos[l][8], &zero, 4);
+    }
+  }
+  ecbError e;
+  if (occluded) {
+    alignas(16) uint32_t rays[N][12];
+    for (int l = 0; l < N; l++) memcpy(rays[l], aos[l], 48);
+    e = ecbOccluded1M(s->gpu, ctx_inst(ctx), rays, N, 48);
+    for (int l = 0; l < N; l++) aos[l][8] = rays[l][8];
+  } else {
+    e = ecbIntersect1M(s->gpu, ctx_inst(ctx), aos, N, 80);
+  }
+  check(s, e, "packet query");
+  if (e != ECB_SUCCESS) return;
+  for (int l = 0; l < N; l++) {
+    if (valid[l] != -1) continue;
+    soa[8 * N + l] = aos[l][8];
+    if (!occluded)
+      for (int f = 12; f < 20; f++) soa[f * N + l] = aos[l][f];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- device ----------------------------------------------------------------------------------------------------------
+RTC_API RTCDevice rtcNewDevice(const char* config) {
+  ShimDevice* d = new ShimDevice;
+  std::string host_path = getenv("ECB200_HOST_EMBREE") ? getenv("ECB200_HOST_EMBREE") : "";
+  const std::string host_cfg = parse_config(config, host_path, d->verbose);
+  std::string err;
+  if (host_path.empty()) err = "no host embree given (device config host_embree=<libembree3.so> or $ECB200_HOST_EMBREE)";
+  if (!err.empty() || !load_host(d->host, host_path, err)) {
+    g_thread_error = RTC_ERROR_INVALID_OPERATION;
+    fprintf(stderr, "embree3_b200: %s\n", err.c_str());
+    delete d;
+    return nullptr;
+  }
+  d->hdev = d->host.rtcNewDevice(host_cfg.c_str());
+  if (!d->hdev) {
+    g_thread_error = RTC_ERROR_UNKNOWN;
+    delete d;
+    return nullptr;
+  }
+  g_any_device = d;
+  if (d->verbose) fprintf(stderr, "embree3_b200: host embree %s, traversal on CUDA (libecb200)\n", host_path.c_str());
+  return reinterpret_cast<RTCDevice>(d);
+}
+RTC_API void rtcRetainDevice(RTCDevice device) { if (device) D(device)->refs++; }
+RTC_API void rtcReleaseDevice(RTCDevice device) {
+  if (!device) return;
+  ShimDevice* d = D(device);
+  if (--d->refs == 0) {
+    d->host.rtcReleaseDevice(d->hdev);
+    ShimDevice* expect = d;
+    g_any_device.compare_exchange_strong(expect, nullptr);
+    delete d;  // the host library stays loaded: geometry handles may outlive the device object
+  }
+}
+RTC_API RTCError rtcGetDeviceError(RTCDevice device) {
+  if (!device) { RTCError e = g_thread_error; g_thread_error = RTC_ERROR_NONE; return e; }
+  ShimDevice* d = D(device);
+  RTCError host = d->host.rtcGetDeviceError(d->hdev);
+  std::lock_guard<std::mutex> lock(d->mutex);
+  RTCError e = d->error != RTC_ERROR_NONE ? d->error : host;
+  d->error = RTC_ERROR_NONE;
+  return e;
+}
+RTC_API void rtcSetDeviceErrorFunction(RTCDevice device, RTCErrorFunction error, void* userPtr) {
+  if (!device) return;
+  std::lock_guard<std::mutex> lock(D(device)->mutex);
+  D(device)->callback = error;
+  D(device)->callback_ptr = userPtr;
+}
+
+// ---- geometry: forwarded to the host builder --------------------------------------------------------------------------
+#define HOST() (g_any_device.load()->host)
+RTC_API RTCGeometry rtcNewGeometry(RTCDevice device, RTCGeometryType type) {
+  if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
+  return D(device)->host.rtcNewGeometry(D(device)->hdev, type);
+}
+RTC_API void rtcRetainGeometry(RTCGeometry g) { HOST().rtcRetainGeometry(g); }
+RTC_API void rtcReleaseGeometry(RTCGeometry g) { HOST().rtcReleaseGeometry(g); }
+RTC_API void rtcCommitGeometry(RTCGeometry g) { HOST().rtcCommitGeometry(g); }
+RTC_API void rtcEnableGeometry(RTCGeometry g) { HOST().rtcEnableGeometry(g); }
+RTC_API void rtcDisableGeometry(RTCGeometry g) { HOST().rtcDisableGeometry(g); }
+RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryTimeStepCount(g, n); }
+RTC_API void rtcSetGeometryVertexAttributeCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryVertexAttributeCount(g, n); }
+RTC_API void rtcSetGeometryBuildQuality(RTCGeometry g, RTCBuildQuality q) { HOST().rtcSetGeometryBuildQuality(g, q); }
+RTC_API void rtcSetSharedGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot, RTCFormat f, const void* p, size_t off, size_t stride,
+                                        size_t n) {
+  HOST().rtcSetSharedGeometryBuffer(g, t, slot, f, p, off, stride, n);
+}
+RTC_API void* rtcSetNewGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot, RTCFormat f, size_t stride, size_t n) {
+  return HOST().rtcSetNewGeometryBuffer(g, t, slot, f, stride, n);
+}
+RTC_API void* rtcGetGeometryBufferData(RTCGeometry g, RTCBufferType t, unsigned slot) { return HOST().rtcGetGeometryBufferData(g, t, slot); }
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot) { HOST().rtcUpdateGeometryBuffer(g, t, slot); }
+RTC_API void rtcSetGeometryUserData(RTCGeometry g, void* p) { HOST().rtcSetGeometryUserData(g, p); }
+RTC_API void* rtcGetGeometryUserData(RTCGeometry g) { return HOST().rtcGetGeometryUserData(g); }
+RTC_API void rtcSetGeometryTessellationRate(RTCGeometry g, float r) { HOST().rtcSetGeometryTessellationRate(g, r); }
+RTC_API void rtcSetGeometryTopologyCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryTopologyCount(g, n); }
+RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry g, unsigned t, RTCSubdivisionMode m) { HOST().rtcSetGeometrySubdivisionMode(g, t, m); }
+RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry g, unsigned a, unsigned t) { HOST().rtcSetGeometryVertexAttributeTopology(g, a, t); }
+RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry g, RTCDisplacementFunctionN f) { HOST().rtcSetGeometryDisplacementFunction(g, f); }
+RTC_API void rtcInterpolate(const RTCInterpolateArguments* args) { HOST().rtcInterpolate(args); }
+
+// ---- scene ------------------------------------------------------------------------------------------------------------
+RTC_API RTCScene rtcNewScene(RTCDevice device) {
+  if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
+  ShimScene* s = new ShimScene;
+  s->dev = D(device);
+  s->dev->refs++;
+  s->hscene = s->dev->host.rtcNewScene(s->dev->hdev);
+  return reinterpret_cast<RTCScene>(s);
+}
+RTC_API void rtcRetainScene(RTCScene scene) { if (scene) S(scene)->refs++; }
+RTC_API void rtcReleaseScene(RTCScene scene) {
+  if (!scene) return;
+  ShimScene* s = S(scene);
+  if (--s->refs == 0) {
+    if (s->gpu) ecbSceneRelease(s->gpu);
+    s->dev->host.rtcReleaseScene(s->hscene);
+    rtcReleaseDevice(reinterpret_cast<RTCDevice>(s->dev));
+    delete s;
+  }
+}
+RTC_API unsigned rtcAttachGeometry(RTCScene scene, RTCGeometry g) { return S(scene)->dev->host.rtcAttachGeometry(S(scene)->hscene, g); }
+RTC_API void rtcAttachGeometryByID(RTCScene scene, RTCGeometry g, unsigned id) { S(scene)->dev->host.rtcAttachGeometryByID(S(scene)->hscene, g, id); }
+RTC_API void rtcDetachGeometry(RTCScene scene, unsigned id) { S(scene)->dev->host.rtcDetachGeometry(S(scene)->hscene, id); }
+RTC_API RTCGeometry rtcGetGeometry(RTCScene scene, unsigned id) { return S(scene)->dev->host.rtcGetGeometry(S(scene)->hscene, id); }
+RTC_API void rtcSetSceneLevels(RTCScene scene, unsigned S_, unsigned C_) { S(scene)->dev->host.rtcSetSceneLevels(S(scene)->hscene, S_, C_); }
+RTC_API void rtcSetSceneBuildQuality(RTCScene scene, RTCBuildQuality q) { S(scene)->dev->host.rtcSetSceneBuildQuality(S(scene)->hscene, q); }
+RTC_API void rtcSetSceneFlags(RTCScene scene, RTCSceneFlags f) { S(scene)->dev->host.rtcSetSceneFlags(S(scene)->hscene, f); }
+RTC_API RTCSceneFlags rtcGetSceneFlags(RTCScene scene) { return S(scene)->dev->host.rtcGetSceneFlags(S(scene)->hscene); }
+RTC_API void rtcGetSceneBounds(RTCScene scene, RTCBounds* b) { S(scene)->dev->host.rtcGetSceneBounds(S(scene)->hscene, b); }
+
+// Commit: host build (kernels/common/scene.cpp:632-697), then hand-off of the committed compressed BVH4 to the device path.
+RTC_API void rtcCommitScene(RTCScene scene) {
+  if (!scene) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return; }
+  ShimScene* s = S(scene);
+  std::lock_guard<std::mutex> lock(s->mutex);
+  s->dev->host.rtcCommitScene(s->hscene);
+  if (s->gpu) { ecbSceneRelease(s->gpu); s->gpu = nullptr; }
+  RTCCompressedBVHInfo_b200 info;
+  const int rc = s->dev->host.rtcGetCompressedBVH_b200(s->hscene, &info);
+  if (rc != 0 || info.n_accels != 1) {
+    s->dev->raise(RTC_ERROR_INVALID_OPERATION,
+                  rc == -1 ? "device config must select subdiv_accel=bvh4.compressed.{grid,leaf,box}"
+                           : "scene is not a single compressed subdivision accel (other geometry types are outside the B200 hot path)");
+    return;
+  }
+  ecbImportDesc d;
+  memset(&d, 0, sizeof(d));
+  d.base = nullptr;  // live host memory of this process
+  d.root = info.root;
+  d.leaf_kind = info.leaf_kind;
+  d.proj_col_major = info.proj_col_major;
+  d.subdiv_level = info.subdiv_level;
+  d.comp_level = info.comp_level;
+  memcpy(d.bounds, info.bounds, sizeof(d.bounds));
+  ecbScene* g = nullptr;
+  ecbError e = ecbSceneImportBVH4(&d, &g);
+  if (e == ECB_SUCCESS) e = ecbSceneUpload(g, -1);
+  if (e != ECB_SUCCESS) {
+    if (g) ecbSceneRelease(g);
+    s->dev->raise(map_error(e), std::string("rtcCommitScene: ") + ecbErrorString(e) + " " + ecbLastErrorMessage());
+    return;
+  }
+  s->gpu = g;
+}
+RTC_API void rtcJoinCommitScene(RTCScene scene) { rtcCommitScene(scene); }
+
+// ---- ray queries: all on the device -----------------------------------------------------------------------------------
+RTC_API void rtcIntersect1(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit* rayhit) {
+  ShimScene* s = S(scene);
+  if (ready(s, "rtcIntersect1")) check(s, ecbIntersect1(s->gpu, ctx_inst(ctx), rayhit), "rtcIntersect1");
+}
+RTC_API void rtcIntersect1M(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit* rayhit, unsigned M, size_t byteStride) {
+  ShimScene* s = S(scene);
+  if (ready(s, "rtcIntersect1M")) check(s, ecbIntersect1M(s->gpu, ctx_inst(ctx), rayhit, M, byteStride), "rtcIntersect1M");
+}
+RTC_API void rtcIntersect4(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit4* rh) {
+  if (ready(S(scene), "rtcIntersect4")) packet_intersect<4>(valid, S(scene), ctx, rh, false);
+}
+RTC_API void rtcIntersect8(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit8* rh) {
+  if (ready(S(scene), "rtcIntersect8")) packet_intersect<8>(valid, S(scene), ctx, rh, false);
+}
+RTC_API void rtcIntersect16(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit16* rh) {
+  if (ready(S(scene), "rtcIntersect16")) packet_intersect<16>(valid, S(scene), ctx, rh, false);
+}
+RTC_API void rtcOccluded1(RTCScene scene, RTCIntersectContext* ctx, RTCRay* ray) {
+  ShimScene* s = S(scene);
+  if (ready(s, "rtcOccluded1")) check(s, ecbOccluded1(s->gpu, ctx_inst(ctx), ray), "rtcOccluded1");
+}
+RTC_API void rtcOccluded1M(RTCScene scene, RTCIntersectContext* ctx, RTCRay* ray, unsigned M, size_t byteStride) {
+  ShimScene* s = S(scene);
+  if (ready(s, "rtcOccluded1M")) check(s, ecbOccluded1M(s->gpu, ctx_inst(ctx), ray, M, byteStride), "rtcOccluded1M");
+}
+RTC_API void rtcOccluded4(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay4* r) {
+  if (ready(S(scene), "rtcOccluded4")) packet_intersect<4>(valid, S(scene), ctx, r, true);
+}
+RTC_API void rtcOccluded8(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay8* r) {
+  if (ready(S(scene), "rtcOccluded8")) packet_intersect<8>(valid, S(scene), ctx, r, true);
+}
+RTC_API void rtcOccluded16(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay16* r) {
+  if (ready(S(scene), "rtcOccluded16")) packet_intersect<16>(valid, S(scene), ctx, r, true);
+}
+
+RTC_API void* rtcAllocRays_b200(size_t bytes) {
+  void* p = nullptr;
+  return ecbHostAlloc(&p, bytes) == ECB_SUCCESS ? p : nullptr;
+}
+RTC_API void rtcFreeRays_b200(void* ptr) { ecbHostFree(ptr); }
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+/* rtcore_subset.h -- the part of the embree3 C API (Embree 3.0.0) that the compressed-BVH hot path sits behind,
+ * restated for callers that build without the reference's include/embree3/ tree (tests, demos, the shim itself).
+ *
+ * An application written against the reference's own headers links against libembree3_b200.so unchanged: every
+ * name, enum value and struct layout below is an ABI fact of the reference
+ * (include/embree3/rtcore_{common,device,buffer,ray,geometry,scene}.h) and is verified against the compiled
+ * reference by tests/test_shim_gpu.py.  Nothing here adds API except the two *_b200 entries at the bottom.
+ */
+#ifndef EMBREE3_B200_RTCORE_SUBSET_H
+#define EMBREE3_B200_RTCORE_SUBSET_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/types.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if !defined(RTC_API)
+#define RTC_API __attribute__((visibility("default")))
+#endif
+#define RTC_INVALID_GEOMETRY_ID ((unsigned int)-1)
+#define RTC_MAX_INSTANCE_LEVEL_COUNT 1
+
+typedef struct RTCDeviceTy* RTCDevice;
+typedef struct RTCSceneTy* RTCScene;
+typedef struct RTCGeometryTy* RTCGeometry;
+
+enum RTCError { RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,
+                RTC_ERROR_OUT_OF_MEMORY = 4, RTC_ERROR_UNSUPPORTED_CPU = 5, RTC_ERROR_CANCELLED = 6 };
+enum RTCGeometryType { RTC_GEOMETRY_TYPE_TRIANGLE = 0, RTC_GEOMETRY_TYPE_QUAD = 1, RTC_GEOMETRY_TYPE_SUBDIVISION = 8,
+                       RTC_GEOMETRY_TYPE_USER = 120, RTC_GEOMETRY_TYPE_INSTANCE = 121 };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2,
+                     RTC_BUFFER_TYPE_FACE = 16, RTC_BUFFER_TYPE_LEVEL = 17, RTC_BUFFER_TYPE_EDGE_CREASE_INDEX = 18,
+                     RTC_BUFFER_TYPE_EDGE_CREASE_WEIGHT = 19, RTC_BUFFER_TYPE_VERTEX_CREASE_INDEX = 20,
+                     RTC_BUFFER_TYPE_VERTEX_CREASE_WEIGHT = 21, RTC_BUFFER_TYPE_HOLE = 22 };
+enum RTCFormat { RTC_FORMAT_UINT = 0x5001, RTC_FORMAT_UINT2 = 0x5002, RTC_FORMAT_UINT3 = 0x5003, RTC_FORMAT_UINT4 = 0x5004,
+                 RTC_FORMAT_FLOAT = 0x9001, RTC_FORMAT_FLOAT2 = 0x9002, RTC_FORMAT_FLOAT3 = 0x9003, RTC_FORMAT_FLOAT4 = 0x9004,
+                 RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234 };
+enum RTCBuildQuality { RTC_BUILD_QUALITY_LOW = 0, RTC_BUILD_QUALITY_MEDIUM = 1, RTC_BUILD_QUALITY_HIGH = 2, RTC_BUILD_QUALITY_REFIT = 3 };
+enum RTCSceneFlags { RTC_SCENE_FLAG_NONE = 0, RTC_SCENE_FLAG_DYNAMIC = 1, RTC_SCENE_FLAG_COMPACT = 2, RTC_SCENE_FLAG_ROBUST = 4,
+                     RTC_SCENE_FLAG_CONTEXT_FILTER_FUNCTION = 8 };
+enum RTCIntersectContextFlags { RTC_INTERSECT_CONTEXT_FLAG_NONE = 0, RTC_INTERSECT_CONTEXT_FLAG_INCOHERENT = 0,
+                                RTC_INTERSECT_CONTEXT_FLAG_COHERENT = 1 };
+enum RTCSubdivisionMode { RTC_SUBDIVISION_MODE_NO_BOUNDARY = 0, RTC_SUBDIVISION_MODE_SMOOTH_BOUNDARY = 1,
+                          RTC_SUBDIVISION_MODE_PIN_CORNERS = 2, RTC_SUBDIVISION_MODE_PIN_BOUNDARY = 3, RTC_SUBDIVISION_MODE_PIN_ALL = 4 };
+
+/* rtcore_ray.h:26-64 */
+struct __attribute__((aligned(16))) RTCRay { float org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, time, tfar; unsigned int mask, id, flags; };
+struct __attribute__((aligned(16))) RTCHit { float Ng_x, Ng_y, Ng_z, u, v; unsigned int primID, geomID, instID[RTC_MAX_INSTANCE_LEVEL_COUNT]; };
+struct RTCRayHit { struct RTCRay ray; struct RTCHit hit; };
+#define RTC_B200_PACKET(N)                                                                                                     \
+  struct __attribute__((aligned(4 * N))) RTCRay##N { float org_x[N], org_y[N], org_z[N], tnear[N], dir_x[N], dir_y[N], dir_z[N], time[N], tfar[N]; \
+                                                     unsigned int mask[N], id[N], flags[N]; };                                 \
+  struct __attribute__((aligned(4 * N))) RTCHit##N { float Ng_x[N], Ng_y[N], Ng_z[N], u[N], v[N]; unsigned int primID[N], geomID[N],   \
+                                                     instID[RTC_MAX_INSTANCE_LEVEL_COUNT][N]; };                              \
+  struct RTCRayHit##N { struct RTCRay##N ray; struct RTCHit##N hit; };
+RTC_B200_PACKET(4)
+RTC_B200_PACKET(8)
+RTC_B200_PACKET(16)
+
+struct __attribute__((aligned(16))) RTCBounds { float lower_x, lower_y, lower_z, align0, upper_x, upper_y, upper_z, align1; };
+struct RTCFilterFunctionNArguments;
+typedef void (*RTCFilterFunctionN)(const struct RTCFilterFunctionNArguments* args);
+struct RTCIntersectContext { enum RTCIntersectContextFlags flags; RTCFilterFunctionN filter; unsigned int instID[RTC_MAX_INSTANCE_LEVEL_COUNT]; };
+static inline void rtcInitIntersectContext(struct RTCIntersectContext* c) {
+  c->flags = RTC_INTERSECT_CONTEXT_FLAG_INCOHERENT; c->filter = NULL; c->instID[0] = (unsigned int)-1;
+}
+struct RTCDisplacementFunctionNArguments { void* geometryUserPtr; RTCGeometry geometry; unsigned int primID; unsigned int timeStep;
+                                           const float *u, *v, *Ng_x, *Ng_y, *Ng_z; float *P_x, *P_y, *P_z; unsigned int N; };
+typedef void (*RTCDisplacementFunctionN)(const struct RTCDisplacementFunctionNArguments* args);
+struct RTCInterpolateArguments { RTCGeometry geometry; unsigned int primID; float u, v; enum RTCBufferType bufferType; unsigned int bufferSlot;
+                                 float *P, *dPdu, *dPdv, *ddPdudu, *ddPdvdv, *ddPdudv; unsigned int valueCount; };
+typedef void (*RTCErrorFunction)(void* userPtr, enum RTCError code, const char* str);
+
+/* device (rtcore_device.h) */
+RTC_API RTCDevice rtcNewDevice(const char* config);
+RTC_API void rtcRetainDevice(RTCDevice device);
+RTC_API void rtcReleaseDevice(RTCDevice device);
+RTC_API enum RTCError rtcGetDeviceError(RTCDevice device);
+RTC_API void rtcSetDeviceErrorFunction(RTCDevice device, RTCErrorFunction error, void* userPtr);
+/* geometry (rtcore_geometry.h) */
+RTC_API RTCGeometry rtcNewGeometry(RTCDevice device, enum RTCGeometryType type);
+RTC_API void rtcRetainGeometry(RTCGeometry geometry);
+RTC_API void rtcReleaseGeometry(RTCGeometry geometry);
+RTC_API void rtcCommitGeometry(RTCGeometry geometry);
+RTC_API void rtcEnableGeometry(RTCGeometry geometry);
+RTC_API void rtcDisableGeometry(RTCGeometry geometry);
+RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry geometry, unsigned int timeStepCount);
+RTC_API void rtcSetGeometryVertexAttributeCount(RTCGeometry geometry, unsigned int vertexAttributeCount);
+RTC_API void rtcSetGeometryBuildQuality(RTCGeometry geometry, enum RTCBuildQuality quality);
+RTC_API void rtcSetSharedGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot, enum RTCFormat format,
+                                        const void* ptr, size_t byteOffset, size_t byteStride, size_t itemCount);
+RTC_API void* rtcSetNewGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot, enum RTCFormat format,
+                                      size_t byteStride, size_t itemCount);
+RTC_API void* rtcGetGeometryBufferData(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot);
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot);
+RTC_API void rtcSetGeometryUserData(RTCGeometry geometry, void* ptr);
+RTC_API void* rtcGetGeometryUserData(RTCGeometry geometry);
+RTC_API void rtcSetGeometryTessellationRate(RTCGeometry geometry, float tessellationRate);
+RTC_API void rtcSetGeometryTopologyCount(RTCGeometry geometry, unsigned int topologyCount);
+RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry geometry, unsigned int topologyID, enum RTCSubdivisionMode mode);
+RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry geometry, unsigned int vertexAttributeID, unsigned int topologyID);
+RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry geometry, RTCDisplacementFunctionN displacement);
+RTC_API void rtcInterpolate(const struct RTCInterpolateArguments* args);
+/* scene (rtcore_scene.h) */
+RTC_API RTCScene rtcNewScene(RTCDevice device);
+RTC_API void rtcRetainScene(RTCScene scene);
+RTC_API void rtcReleaseScene(RTCScene scene);
+RTC_API unsigned int rtcAttachGeometry(RTCScene scene, RTCGeometry geometry);
+RTC_API void rtcAttachGeometryByID(RTCScene scene, RTCGeometry geometry, unsigned int geomID);
+RTC_API void rtcDetachGeometry(RTCScene scene, unsigned int geomID);
+RTC_API RTCGeometry rtcGetGeometry(RTCScene scene, unsigned int geomID);
+RTC_API void rtcSetSceneLevels(RTCScene scene, unsigned subdivisionLevel, unsigned compressionLevel); /* rtcore_scene.h:65 */
+RTC_API void rtcCommitScene(RTCScene scene);
+RTC_API void rtcJoinCommitScene(RTCScene scene);
+RTC_API void rtcSetSceneBuildQuality(RTCScene scene, enum RTCBuildQuality quality);
+RTC_API void rtcSetSceneFlags(RTCScene scene, enum RTCSceneFlags flags);
+RTC_API enum RTCSceneFlags rtcGetSceneFlags(RTCScene scene);
+RTC_API void rtcGetSceneBounds(RTCScene scene, struct RTCBounds* bounds_o);
+RTC_API void rtcIntersect1(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit* rayhit);
+RTC_API void rtcIntersect4(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit4* rayhit);
+RTC_API void rtcIntersect8(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit8* rayhit);
+RTC_API void rtcIntersect16(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit16* rayhit);
+RTC_API void rtcIntersect1M(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit* rayhit, unsigned int M, size_t byteStride);
+RTC_API void rtcOccluded1(RTCScene scene, struct RTCIntersectContext* context, struct RTCRay* ray);
+RTC_API void rtcOccluded4(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay4* ray);
+RTC_API void rtcOccluded8(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay8* ray);
+RTC_API void rtcOccluded16(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay16* ray);
+RTC_API void rtcOccluded1M(RTCScene scene, struct RTCIntersectContext* context, struct RTCRay* ray, unsigned int M, size_t byteStride);
+
+/* ---- additions of this repo ----------------------------------------------------------------------------------- */
+/* What the host Embree must export so that rtcCommitScene can hand the committed compressed accel to the plugin
+ * (INTEGRATION.md shows the accessor a maintainer adds to kernels/common/rtcore.cpp; oracle/refhost.cpp supplies it
+ * for the test build of the reference). */
+struct RTCCompressedBVHInfo_b200 { uint64_t root; uint32_t leaf_kind, subdiv_level, comp_level, proj_col_major, n_accels; float bounds[6]; };
+typedef int (*rtcGetCompressedBVH_b200_t)(RTCScene host_scene, struct RTCCompressedBVHInfo_b200* info);
+/* Pinned host memory for ray arrays (fast DMA path of rtcIntersect1M / rtcOccluded1M); plain malloc memory also works. */
+RTC_API void* rtcAllocRays_b200(size_t bytes);
+RTC_API void rtcFreeRays_b200(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

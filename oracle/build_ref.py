@@ -189,7 +189,9 @@ def build(force=False):
     run("g++ %s %s %s %s -I%s -c %s -o %s" % (COMMON.replace("-fvisibility=hidden", ""), DEFS,
                                                 FLAGS_ISA["sse2"] + " -DEMBREE_LOWEST_ISA", include_flags(), HERE,
                                                 os.path.join(HERE, "refhost.cpp"), host_o))
-    run("g++ -shared -o %s %s %s -lpthread -ldl -Wl,-z,noexecstack" % (so, " ".join(objs), host_o))
+    # -Bsymbolic: the library's own references to rtc* bind locally, so that it can be dlopen'ed by a process that
+    # also exports rtc* symbols (the drop-in shim libembree3_b200.so) without being interposed
+    run("g++ -shared -Wl,-Bsymbolic -o %s %s %s -lpthread -ldl -Wl,-z,noexecstack" % (so, " ".join(objs), host_o))
     os.makedirs(os.path.join(OUT, "assets"), exist_ok=True)
     shutil.copyfile(os.path.join(REF, "build", "bomberman.obj"), os.path.join(OUT, "assets", "bomberman.obj"))
     json.dump({"digest": digest, "units": len(objs), "isas": ["sse2", "sse42", "avx", "avx2"],

@@ -443,3 +443,34 @@ REF_API size_t ref_scene_dump_image(RefScene* s, void* buf, size_t cap) {
   d.put(0, &h, sizeof(h));
   return (size_t)h.total_bytes;
 }
+
+// ---- the accessor a maintainer adds to the reference, supplied here for the test build ----
+// Everything the plugin needs at commit time, from the reference's own objects: root of the compressed accel
+// (same walk as ref_scene_compressed_root), leaf flavour from Device::subdiv_accel (kernels/common/state.h:109),
+// S and C from Scene::subdivisionLevel / compressionLevel (kernels/common/scene.h:231-232).
+struct RTCCompressedBVHInfo_b200 { uint64_t root; uint32_t leaf_kind, subdiv_level, comp_level, proj_col_major, n_accels; float bounds[6]; };
+REF_API int rtcGetCompressedBVH_b200(RTCScene hscene, RTCCompressedBVHInfo_b200* out) {
+  using namespace embree;
+  Scene* scene = (Scene*)hscene;
+  memset(out, 0, sizeof(*out));
+  const std::string& a = scene->device->subdiv_accel;
+  if (a == "bvh4.compressed.grid") out->leaf_kind = 0;
+  else if (a == "bvh4.compressed.leaf") out->leaf_kind = 1;
+  else if (a == "bvh4.compressed.box") out->leaf_kind = 2;
+  else return -1;
+  RefScene tmp;
+  tmp.scene = hscene;
+  int n = 0;
+  out->root = ref_scene_compressed_root(&tmp, &n);
+  out->n_accels = (uint32_t)n;
+  out->subdiv_level = scene->subdivisionLevel;
+  out->comp_level = scene->compressionLevel;
+  RefLayout lay;
+  ref_layout(&lay);
+  out->proj_col_major = lay.proj_col_major;
+  RTCBounds b;
+  rtcGetSceneBounds(hscene, &b);
+  out->bounds[0] = b.lower_x; out->bounds[1] = b.lower_y; out->bounds[2] = b.lower_z;
+  out->bounds[3] = b.upper_x; out->bounds[4] = b.upper_y; out->bounds[5] = b.upper_z;
+  return out->root ? 0 : -2;
+}

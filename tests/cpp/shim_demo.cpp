@@ -1,0 +1,124 @@
+// shim_demo.cpp -- an "unmodified embree3 application" for the drop-in test: it only speaks the embree3 C API
+// (declarations from include/embree3_b200/rtcore_subset.h, which restate the reference's headers) and is linked
+// against libembree3_b200.so instead of libembree3.so.
+//
+//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin>
+// builds the displaced cube of tutorials/displacement_geometry through rtc* calls (subdivision mesh + displacement
+// callback), commits, and traces the RTCRayHit records of rays.bin four ways, writing one result block per way:
+//   [0] rtcIntersect1M   [1] rtcIntersect16 packets   [2] rtcIntersect1 per ray (first 64 rays)   [3] rtcOccluded1M
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/embree3_b200/rtcore_subset.h"
+
+static float cube_vertices[8][4] = {{-1, -1, -1, 0}, {1, -1, -1, 0}, {1, -1, 1, 0}, {-1, -1, 1, 0},
+                                    {-1, 1, -1, 0},  {1, 1, -1, 0},  {1, 1, 1, 0},  {-1, 1, 1, 0}};
+static unsigned cube_indices[24] = {0, 4, 5, 1, 1, 5, 6, 2, 2, 6, 7, 3, 0, 3, 7, 4, 4, 7, 6, 5, 0, 1, 2, 3};
+static unsigned cube_faces[6] = {4, 4, 4, 4, 4, 4};
+
+// same closed-form displacement as the reference harness uses for this scene (oracle/refhost.cpp)
+static float displacement(float x, float y, float z) {
+  float dN = 0.0f;
+  for (float freq = 1.0f; freq < 40.0f; freq *= 2.0f) {
+    const float n = std::sin(freq * (1.7f * x + 0.3f)) * std::sin(freq * (1.3f * y + 1.1f)) * std::sin(freq * (1.9f * z + 2.3f));
+    dN += 1.4f * n * n / freq;
+  }
+  return dN;
+}
+static void displacement_cb(const RTCDisplacementFunctionNArguments* a) {
+  for (unsigned i = 0; i < a->N; i++) {
+    const float d = displacement(a->P_x[i], a->P_y[i], a->P_z[i]);
+    a->P_x[i] += d * a->Ng_x[i];
+    a->P_y[i] += d * a->Ng_y[i];
+    a->P_z[i] += d * a->Ng_z[i];
+  }
+}
+static void on_error(void*, RTCError code, const char* str) { fprintf(stderr, "RTC error %d: %s\n", (int)code, str); }
+
+int main(int argc, char** argv) {
+  if (argc < 6) { fprintf(stderr, "usage: shim_demo leaf S C rays.bin out.bin\n"); return 2; }
+  const std::string cfg = std::string("subdiv_accel=bvh4.compressed.") + argv[1] + ",set_affinity=0,start_threads=0";
+  RTCDevice device = rtcNewDevice(cfg.c_str());
+  if (!device) { fprintf(stderr, "rtcNewDevice failed (%d)\n", (int)rtcGetDeviceError(nullptr)); return 3; }
+  rtcSetDeviceErrorFunction(device, on_error, nullptr);
+  RTCScene scene = rtcNewScene(device);
+  rtcSetSceneFlags(scene, RTC_SCENE_FLAG_ROBUST);
+  rtcSetSceneLevels(scene, (unsigned)atoi(argv[2]), (unsigned)atoi(argv[3]));
+  RTCGeometry geom = rtcNewGeometry(device, RTC_GEOMETRY_TYPE_SUBDIVISION);
+  rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, cube_vertices, 0, 16, 8);
+  rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, cube_indices, 0, 4, 24);
+  rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_FACE, 0, RTC_FORMAT_UINT, cube_faces, 0, 4, 6);
+  float* level = (float*)rtcSetNewGeometryBuffer(geom, RTC_BUFFER_TYPE_LEVEL, 0, RTC_FORMAT_FLOAT, 4, 24);
+  for (int i = 0; i < 24; i++) level[i] = 1.0f;
+  rtcSetGeometryDisplacementFunction(geom, displacement_cb);
+  rtcCommitGeometry(geom);
+  rtcAttachGeometry(scene, geom);
+  rtcReleaseGeometry(geom);
+  rtcCommitScene(scene);
+  if (RTCError e = rtcGetDeviceError(device)) { fprintf(stderr, "commit failed: %d\n", (int)e); return 4; }
+
+  FILE* f = fopen(argv[4], "rb");
+  if (!f) return 5;
+  fseek(f, 0, SEEK_END);
+  const size_t bytes = (size_t)ftell(f);
+  fseek(f, 0, SEEK_SET);
+  const size_t n = bytes / sizeof(RTCRayHit);
+  std::vector<RTCRayHit> rays(n);
+  if (fread(rays.data(), sizeof(RTCRayHit), n, f) != n) return 5;
+  fclose(f);
+  FILE* out = fopen(argv[5], "wb");
+  RTCIntersectContext ctx;
+  rtcInitIntersectContext(&ctx);
+
+  {  // [0] stream call on pinned memory
+    RTCRayHit* r = (RTCRayHit*)rtcAllocRays_b200(bytes);
+    memcpy(r, rays.data(), bytes);
+    rtcIntersect1M(scene, &ctx, r, (unsigned)n, sizeof(RTCRayHit));
+    fwrite(r, sizeof(RTCRayHit), n, out);
+    rtcFreeRays_b200(r);
+  }
+  {  // [1] packets of 16 with every 5th lane masked out
+    std::vector<RTCRayHit> r(rays);
+    const size_t packets = n / 16 < 32 ? n / 16 : 32;
+    for (size_t p = 0; p < packets; p++) {
+      RTCRayHit16 pk;
+      int valid[16];
+      unsigned* soa = (unsigned*)&pk;
+      for (int l = 0; l < 16; l++) {
+        valid[l] = (l % 5 == 4) ? 0 : -1;
+        const unsigned* a = (const unsigned*)&r[p * 16 + l];
+        for (int fld = 0; fld < 20; fld++) soa[fld * 16 + l] = a[fld];
+      }
+      rtcIntersect16(valid, scene, &ctx, &pk);
+      for (int l = 0; l < 16; l++) {
+        unsigned* a = (unsigned*)&r[p * 16 + l];
+        for (int fld = 0; fld < 20; fld++) a[fld] = soa[fld * 16 + l];
+      }
+    }
+    fwrite(r.data(), sizeof(RTCRayHit), packets * 16, out);
+  }
+  {  // [2] single-ray calls (pageable stack memory)
+    const size_t m = n < 64 ? n : 64;
+    std::vector<RTCRayHit> r(rays.begin(), rays.begin() + m);
+    for (size_t i = 0; i < m; i++) rtcIntersect1(scene, &ctx, &r[i]);
+    fwrite(r.data(), sizeof(RTCRayHit), m, out);
+  }
+  {  // [3] any-hit stream on pageable memory with a 64-byte stride
+    struct Padded { RTCRay ray; float pad[4]; };
+    std::vector<Padded> r(n);
+    for (size_t i = 0; i < n; i++) { r[i].ray = rays[i].ray; for (int k = 0; k < 4; k++) r[i].pad[k] = 7.f; }
+    rtcOccluded1M(scene, &ctx, &r[0].ray, (unsigned)n, sizeof(Padded));
+    for (size_t i = 0; i < n; i++) fwrite(&r[i], sizeof(Padded), 1, out);
+  }
+  fclose(out);
+  const RTCError e = rtcGetDeviceError(device);
+  rtcReleaseScene(scene);
+  rtcReleaseDevice(device);
+  if (e) { fprintf(stderr, "device error %d\n", (int)e); return 6; }
+  printf("shim_demo ok: %zu rays\n", n);
+  return 0;
+}

@@ -1,0 +1,54 @@
+"""GPU test (-m gpu): the embree3 drop-in library.  tests/cpp/shim_demo is an application that only speaks the embree3
+C API; it is linked against libembree3_b200.so (host builder = the compiled reference, traversal = CUDA) and its
+results are compared with the reference tracing the same scene and rays through its own rtcIntersect1/rtcOccluded1."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+from embree_compressed_b200 import raygen as rg
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "tests", "cpp", "shim_demo")
+
+
+@pytest.mark.parametrize("leaf,S,C", [("leaf", 5, 3), ("grid", 4, 2), ("box", 5, 2)])
+def test_unmodified_embree3_application_runs_on_the_shim(ecb, reference, ref_scene, tmp_path, leaf, S, C):
+    assert os.path.exists(DEMO), "tests/cpp/shim_demo not built (run __graft_entry__.build())"
+    cam = dict(vp=(1.6, 1.45, -1.35), vi=(0.05, -0.02, 0.03), vu=(0.0, 1.0, 0.0), fov=90.0)
+    rays = rg.primary_rays(160, 128, **cam)
+    n = len(rays)
+    rays_path, out_path = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rays_path)
+    env = dict(os.environ, ECB200_HOST_EMBREE=reference.REF_SO)
+    r = subprocess.run([DEMO, leaf, str(S), str(C), rays_path, out_path], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.float32)
+    n_pk = min(n // 16, 32) * 16
+    n_one = min(n, 64)
+    sizes = [n * 20, n_pk * 20, n_one * 20, n * 16]
+    assert raw.size == sum(sizes)
+    stream, packets, singles, occ = np.split(raw, np.cumsum(sizes)[:-1])
+    stream, packets, singles, occ = stream.reshape(n, 20), packets.reshape(n_pk, 20), singles.reshape(n_one, 20), occ.reshape(n, 16)
+
+    ref = ref_scene("cube", leaf, S, C)      # the same scene committed by the reference in this process
+    port = reference.PortScene.from_ref(ref)
+    truth = rays.copy()
+    ref.intersect(truth)
+    cand = port.candidates(rays)
+    c = parity.assert_reference_parity(stream, truth, cand, "shim rtcIntersect1M %s" % leaf)
+    assert c["hits_ref"] > 1000
+    # packets: masked lanes (every 5th) come back untouched, active lanes equal the stream result
+    lanes = np.arange(n_pk) % 16
+    masked = lanes % 5 == 4
+    assert (packets[masked].view(np.uint32) == rays[:n_pk][masked].view(np.uint32)).all()
+    assert (packets[~masked].view(np.uint32) == stream[:n_pk][~masked].view(np.uint32)).all()
+    assert (singles.view(np.uint32) == stream[:n_one].view(np.uint32)).all()
+    # any-hit stream with stride 64: padding untouched, tfar == reference's rtcOccluded1
+    o_truth = rg.rays_only(rays)
+    ref.occluded(o_truth)
+    assert (occ[:, 12:] == 7.0).all()
+    assert (occ[:, :12].view(np.uint32) == o_truth.view(np.uint32)).all()
