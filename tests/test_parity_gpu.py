@@ -212,14 +212,20 @@ def test_full_size_configs(ecb, reference, ref_scene, leaf):
         b = ref.bounds()
         bounce = rg.diffuse_rays(truth, ref.hit_normals(truth), float(np.linalg.norm(b[3:] - b[:3])))
         _check_intersect(scene, port, ref, bounce, "%s %s full diffuse" % (kind, leaf))
-        # size-independent property: re-tracing the result never finds anything farther, never turns a hit into a
-        # miss, and moves t by at most the tolerance (a hit at t == tfar may be re-found within rounding)
-        again = got.copy()
-        scene.intersect1M(again)
-        # (the pizza-box path maps t through the local frame and back, t/zFactor + near, so a re-found hit may land one
-        # rounding step beyond the old tfar -- the reference does the same)
-        assert (again[:, 8] <= got[:, 8] * (1 + 1e-6)).all()
-        assert (again.view(np.uint32)[:, 18] == got.view(np.uint32)[:, 18]).all()
-        hit = got.view(np.uint32)[:, 18] != 0xFFFFFFFF
-        assert (np.abs(again[hit, 8] - got[hit, 8]) <= 1e-5 * np.abs(got[hit, 8])).all()
+        # size-independent properties at full size.
+        # (1) rays are independent and the dynamic ray scheduler must not leak between lanes: any permutation of the
+        #     batch, traced in one call or in unequal pieces, gives bit-identical per-ray results
+        perm = np.random.default_rng(5).permutation(len(rays))
+        shuffled = rays[perm].copy()
+        scene.intersect1M(shuffled[: len(rays) // 3])
+        scene.intersect1M(shuffled[len(rays) // 3:])
+        assert (shuffled.view(np.uint32) == got[perm].view(np.uint32)).all()
+        # (2) exact micro-triangles only: re-tracing a result changes nothing (the recorded hit sits at t == tfar and
+        #     the test is tt < tfar).  The pizza-box / voxel paths are not idempotent in the reference either: their
+        #     local ray is the chord between the frustum entry point and the point at tfar (compressed.h:470-476), which
+        #     moves when tfar shrinks.
+        if leaf == "grid":
+            again = got.copy()
+            scene.intersect1M(again)
+            assert (again.view(np.uint32) == got.view(np.uint32)).all()
         scene.release()
