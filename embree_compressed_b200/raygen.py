@@ -169,3 +169,29 @@ def incoherent_rays(n, bounds, seed=1):
 def rays_only(rayhits):
     """RTCRay (48-byte) view copy of an RTCRayHit array, for the occluded entry points."""
     return np.ascontiguousarray(rayhits[:, :12])
+
+
+def shadow_rays(rayhits, light_center, light_radius, seed=3):
+    """One shadow ray per hit toward a uniformly sampled point on a sphere light (BASELINE config 3): RTCRay records
+    (N,12) with tnear = 1e-3, tfar = distance to the sample; misses become inactive rays."""
+    n = rayhits.shape[0]
+    ri = rayhits.view(np.uint32)
+    hit = ri[:, GEOMID] != INVALID
+    rng = np.random.default_rng(seed)
+    z = 2.0 * rng.random(n) - 1.0
+    phi = 2.0 * np.pi * rng.random(n)
+    s = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    target = np.asarray(light_center, np.float64) + light_radius * np.stack([s * np.cos(phi), s * np.sin(phi), z], -1)
+    P = rayhits[:, ORG].astype(np.float64) + rayhits[:, TFAR:TFAR + 1].astype(np.float64) * rayhits[:, DIR].astype(np.float64)
+    P = np.where(hit[:, None], P, 0.0)
+    d = target - P
+    dist = np.linalg.norm(d, axis=-1)
+    r = np.zeros((n, 12), np.float32)
+    r[:, ORG] = P.astype(np.float32)
+    r[:, DIR] = (d / np.maximum(dist, 1e-30)[:, None]).astype(np.float32)
+    r[:, TNEAR] = np.float32(1e-3)
+    r[:, TFAR] = dist.astype(np.float32)
+    r.view(np.uint32)[:, MASK] = INVALID
+    r[~hit, TNEAR] = 1.0
+    r[~hit, TFAR] = 0.0
+    return r
