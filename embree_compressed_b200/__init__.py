@@ -35,6 +35,11 @@ class ImportDesc(C.Structure):
                 ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32), ("bounds", C.c_float * 6)]
 
 
+class InstanceDesc(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("n_instances", C.c_uint32), ("reserved", C.c_uint32),
+                ("geomIDs", C.c_void_p), ("world2local", C.c_void_p), ("objects", C.c_void_p), ("bounds", C.c_float * 6)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("leaf_kind", C.c_uint32), ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32),
                 ("n_top_nodes", C.c_uint32), ("n_blocks", C.c_uint32), ("top_depth", C.c_uint32),
@@ -47,6 +52,7 @@ class SceneInfo(C.Structure):
 _vp, _u32, _u64, _sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
 SYMBOLS = {
     "ecbSceneImportBVH4": (C.c_int, [C.POINTER(ImportDesc), C.POINTER(_vp)]),
+    "ecbSceneImportInstances": (C.c_int, [C.POINTER(InstanceDesc), C.POINTER(_vp)]),
     "ecbSceneImportImage": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "ecbSceneImportImageFile": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "ecbSceneSave": (C.c_int, [_vp, C.c_char_p]),
@@ -133,6 +139,25 @@ class Scene:
         h = _vp()
         _check(_lib().ecbSceneImportBVH4(C.byref(d), C.byref(h)), "ecbSceneImportBVH4")
         return cls(h.value)
+
+    @classmethod
+    def import_instances(cls, root, geom_ids, world2local, objects, base=0, bounds=None):
+        """ecbSceneImportInstances: objects[i] is the imported Scene instance i refers to (entries may repeat)."""
+        ids = np.ascontiguousarray(geom_ids, np.uint32)
+        xf = np.ascontiguousarray(world2local, np.float32).reshape(-1, 12)
+        handles = (C.c_void_p * len(objects))(*[o._h for o in objects])
+        d = InstanceDesc()
+        d.base = base
+        d.root = root
+        d.n_instances = len(ids)
+        d.geomIDs = ids.ctypes.data
+        d.world2local = xf.ctypes.data
+        d.objects = C.cast(handles, C.c_void_p).value
+        for i in range(6):
+            d.bounds[i] = float(bounds[i]) if bounds is not None else 0.0
+        h = _vp()
+        _check(_lib().ecbSceneImportInstances(C.byref(d), C.byref(h)), "ecbSceneImportInstances")
+        return cls(h.value, keepalive=list(objects))
 
     @classmethod
     def from_image(cls, image):

@@ -60,6 +60,42 @@ struct Staging {
 
 namespace {
 
+ecbError ensure_resident(ecbScene* s, int device);
+
+// instancing scene: object scenes first, then instance-level nodes / items / instance records / object table
+ecbError upload_instanced(ecbScene* s, int device) {
+  std::vector<EcbDeviceScene> objs;
+  for (ecbScene* o : s->objects) {
+    ecbError e = ensure_resident(o, device);
+    if (e != ECB_SUCCESS) return e;
+    objs.push_back(o->dev);
+  }
+  auto up = [](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, bytes);
+    return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CU(up(&s->d_top, s->top.data(), s->top.size() * sizeof(EcbTopNode)));
+  CU(up(&s->d_items, s->items.data(), s->items.size() * 4));
+  CU(up(&s->d_instances, s->instances.data(), s->instances.size() * sizeof(EcbInstance)));
+  CU(up(&s->d_objects, objs.data(), objs.size() * sizeof(EcbDeviceScene)));
+  EcbDeviceInstScene& d = s->inst_dev;
+  d.nodes = static_cast<const EcbTopNode*>(s->d_top);
+  d.items = static_cast<const uint32_t*>(s->d_items);
+  d.instances = static_cast<const EcbInstance*>(s->d_instances);
+  d.objects = static_cast<const EcbDeviceScene*>(s->d_objects);
+  d.root = s->root;
+  d.n_nodes = (uint32_t)s->top.size();
+  d.n_items = (uint32_t)s->items.size();
+  d.n_instances = (uint32_t)s->instances.size();
+  d.n_objects = (uint32_t)objs.size();
+  CU(cudaMalloc(reinterpret_cast<void**>(&s->d_queues), kQueueRing * sizeof(unsigned long long)));
+  CU(cudaMemset(s->d_queues, 0, kQueueRing * sizeof(unsigned long long)));
+  s->device = device;
+  s->info.device = device;
+  return ECB_SUCCESS;
+}
+
 ecbError ensure_resident(ecbScene* s, int device) {
   std::lock_guard<std::mutex> lock(s->mutex);
   if (s->device >= 0) {
@@ -79,6 +115,7 @@ ecbError ensure_resident(ecbScene* s, int device) {
     CU(cudaGetDevice(&device));
   }
   CU(cudaSetDevice(device));
+  if (s->instanced) return upload_instanced(s, device);
   const size_t top_bytes = s->top.size() * sizeof(EcbTopNode);
   if (top_bytes) {
     CU(cudaMalloc(&s->d_top, top_bytes));
@@ -191,6 +228,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     L.counters = nullptr;
     L.queue = next_queue(s);
     g_launches.fetch_add(1);
+    if (s->instanced) return ecb_launch_instanced(s->inst_dev, s->device, L, occluded, st->stream[k]);
     return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
   };
 
@@ -286,7 +324,13 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
   L.block_out = d_block_out;
   L.counters = d_counters;
   L.queue = next_queue(s);
-  cudaError_t le = occluded ? ecb_launch_occluded(s->dev, s->device, L, q) : ecb_launch_intersect(s->dev, s->device, L, q);
+  if (s->instanced && (d_block_out || d_counters)) {
+    g_last_error = "block output / work counters are not available on instancing scenes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
+  cudaError_t le = s->instanced ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
+                   : occluded   ? ecb_launch_occluded(s->dev, s->device, L, q)
+                                : ecb_launch_intersect(s->dev, s->device, L, q);
   if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
   g_launches.fetch_add(1);
   return ECB_SUCCESS;
@@ -298,6 +342,7 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
 extern "C" {
 
 ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out) { return ecb_import_bvh4(desc, scene_out); }
+ecbError ecbSceneImportInstances(const ecbInstanceDesc* desc, ecbScene** scene_out) { return ecb_import_instances(desc, scene_out); }
 
 ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out) {
   // header of oracle/rimg.h restated as offsets (plain data: magic[8], 8 x u32, root u64, total u64, bounds[6])
@@ -342,6 +387,10 @@ ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out) {
 
 ecbError ecbSceneSave(const ecbScene* s, const char* path) {
   if (!s || !path) return ECB_ERROR_INVALID_ARGUMENT;
+  if (s->instanced) {
+    g_last_error = "instancing scenes are not serialisable (save the object scenes)";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
   EcbBlobHeader h;
   memset(&h, 0, sizeof(h));
   memcpy(h.magic, "ECB200S1", 8);
@@ -445,12 +494,17 @@ ecbError ecbSceneGetInfo(const ecbScene* s, ecbSceneInfo* info) {
 
 void ecbSceneRelease(ecbScene* s) {
   if (!s) return;
+  if (--s->refs > 0) return;  // still referenced by an instancing scene
+  for (ecbScene* o : s->objects) ecbSceneRelease(o);
   if (s->device >= 0) {
     cudaSetDevice(s->device);
     delete s->staging;
     if (s->d_top) cudaFree(s->d_top);
     if (s->d_blocks) cudaFree(s->d_blocks);
     if (s->d_queues) cudaFree(s->d_queues);
+    if (s->d_items) cudaFree(s->d_items);
+    if (s->d_instances) cudaFree(s->d_instances);
+    if (s->d_objects) cudaFree(s->d_objects);
   }
   delete s;
 }
@@ -504,7 +558,7 @@ ecbError ecbOccludedDevice(ecbScene* s, uint32_t instID, void* d_ray, uint64_t M
 }
 
 ecbError ecbSceneBlockNormals(const ecbScene* s, float* out, size_t cap) {
-  if (!s || !out) return ECB_ERROR_INVALID_ARGUMENT;
+  if (!s || !out || s->instanced) return ECB_ERROR_INVALID_ARGUMENT;
   if (cap < 3 * (size_t)s->info.n_blocks) return ECB_ERROR_INVALID_ARGUMENT;
   for (uint32_t b = 0; b < s->info.n_blocks; b++) {
     const EcbBlockHeader* h = reinterpret_cast<const EcbBlockHeader*>(s->blocks.data() + (size_t)b * s->block_stride);

@@ -53,6 +53,26 @@ struct EcbDeviceScene {
   float rcp_edges;        // 1/2^C
 };
 
+// ---- instanced scenes: a BVH4 over instances of object scenes ----
+// Instance-level nodes reuse EcbTopNode; a leaf ref is ECB_REF_LEAF | first_item << 3 | count (count <= 7 Object
+// primitives per leaf, kernels/bvh/bvh.h:140); items[] holds the instance index of every Object primitive.
+struct EcbInstance {
+  float world2local[12];  // vx, vy, vz, p of Instance::world2local0 (kernels/common/scene_instance.h:91)
+  uint32_t geomID;        // reported as hit.instID
+  uint32_t object;        // index into EcbDeviceInstScene::objects
+  uint32_t pad[2];
+};
+static_assert(sizeof(EcbInstance) == 64, "instance record is 4 x 16 bytes");
+
+struct EcbDeviceInstScene {
+  const EcbTopNode* nodes;
+  const uint32_t* items;
+  const EcbInstance* instances;
+  const EcbDeviceScene* objects;
+  uint32_t root;
+  uint32_t n_nodes, n_items, n_instances, n_objects;
+};
+
 // native blob header (ecbSceneSave / ecbSceneLoad)
 struct EcbBlobHeader {
   char magic[8];  // "ECB200S1"

@@ -173,3 +173,106 @@ ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out) {
   *out = s;
   return ECB_SUCCESS;
 }
+
+// ---- instancing scene: BVH4 over Object{geomID,primID} arrays (kernels/geometry/object.h, 8 bytes per primitive) ----
+namespace {
+struct InstImporter {
+  const ecbInstanceDesc& d;
+  ecbScene& s;
+  const uint8_t* base;
+  std::vector<uint32_t> geom_to_instance;
+  uint32_t max_depth = 0;
+  std::string err;
+  InstImporter(const ecbInstanceDesc& desc, ecbScene& scene) : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+
+  uint32_t import_ref(uint64_t ref, uint32_t depth) {
+    if (!err.empty() || ref == kEmpty) return ECB_REF_EMPTY;
+    if (ref & kTyLeaf) {
+      const uint32_t num = (uint32_t)((ref & kAlignMask) - kTyLeaf);
+      if (num > 7) { err = "instance leaf with more than 7 primitives"; return ECB_REF_EMPTY; }
+      const uint8_t* prims = base + (ref & ~kAlignMask);
+      const uint32_t first = (uint32_t)s.items.size();
+      uint32_t kept = 0;
+      for (uint32_t i = 0; i < num; i++) {
+        const uint32_t geomID = rd<uint32_t>(prims + 8 * i);
+        if (geomID >= geom_to_instance.size() || geom_to_instance[geomID] == 0xFFFFFFFFu) {
+          err = "user geometry " + std::to_string(geomID) + " is not an instance handed to ecbSceneImportInstances";
+          return ECB_REF_EMPTY;
+        }
+        s.items.push_back(geom_to_instance[geomID]);
+        kept++;
+      }
+      if (first >= (1u << 27)) { err = "too many instance primitives"; return ECB_REF_EMPTY; }
+      if (depth > max_depth) max_depth = depth;
+      return ECB_REF_LEAF | (first << 3) | kept;
+    }
+    if ((ref & kAlignMask) != 0) { err = "instance BVH node is not an AlignedNode (use object_accel=bvh4.object)"; return ECB_REF_EMPTY; }
+    if (depth > 512) { err = "instance BVH deeper than 512"; return ECB_REF_EMPTY; }
+    const uint8_t* n = base + (ref & ~kAlignMask);
+    const uint32_t index = (uint32_t)s.top.size();
+    s.top.emplace_back();
+    EcbTopNode node;
+    memcpy(node.bounds, n + kAN_Bounds, 96);
+    for (int i = 0; i < 4; i++) node.child[i] = import_ref(rd<uint64_t>(n + kAN_Children + 8 * i), depth + 1);
+    s.top[index] = node;
+    return index;
+  }
+};
+}  // namespace
+
+ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
+  if (!desc || !out || (desc->n_instances && (!desc->geomIDs || !desc->world2local || !desc->objects))) return ECB_ERROR_INVALID_ARGUMENT;
+  ecbScene* s = new (std::nothrow) ecbScene;
+  if (!s) return ECB_ERROR_OUT_OF_MEMORY;
+  s->instanced = true;
+  InstImporter imp(*desc, *s);
+  uint32_t max_geom = 0;
+  for (uint32_t i = 0; i < desc->n_instances; i++) max_geom = desc->geomIDs[i] > max_geom ? desc->geomIDs[i] : max_geom;
+  imp.geom_to_instance.assign((size_t)max_geom + 1, 0xFFFFFFFFu);
+  for (uint32_t i = 0; i < desc->n_instances; i++) {
+    ecbScene* obj = desc->objects[i];
+    if (!obj || obj->instanced) {
+      ecb_set_error("instance " + std::to_string(i) + " does not refer to an imported (non-instanced) scene");
+      delete s;
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+    uint32_t oi = 0;
+    for (; oi < s->objects.size(); oi++)
+      if (s->objects[oi] == obj) break;
+    if (oi == s->objects.size()) {
+      obj->refs++;
+      s->objects.push_back(obj);
+    }
+    EcbInstance in;
+    memset(&in, 0, sizeof(in));
+    memcpy(in.world2local, desc->world2local + 12 * (size_t)i, 48);
+    in.geomID = desc->geomIDs[i];
+    in.object = oi;
+    imp.geom_to_instance[desc->geomIDs[i]] = (uint32_t)s->instances.size();
+    s->instances.push_back(in);
+  }
+  s->root = imp.import_ref(desc->root, 0);
+  if (imp.err.empty() && 3 * imp.max_depth + 4 > ECB_MAX_TOP_STACK) imp.err = "instance BVH too deep for the traversal stack";
+  if (!imp.err.empty()) {
+    ecb_set_error(imp.err);
+    for (ecbScene* o : s->objects) o->refs--;
+    delete s;
+    return ECB_ERROR_UNSUPPORTED;
+  }
+  ecbSceneInfo& in = s->info;
+  memset(&in, 0, sizeof(in));
+  in.n_top_nodes = (uint32_t)s->top.size();
+  in.top_depth = imp.max_depth;
+  in.top_node_bytes = sizeof(EcbTopNode);
+  in.device_bytes = s->top.size() * sizeof(EcbTopNode) + s->items.size() * 4 + s->instances.size() * sizeof(EcbInstance);
+  for (const EcbInstance& i : s->instances) {
+    in.micro_triangles += s->objects[i.object]->info.micro_triangles;
+    in.n_blocks += s->objects[i.object]->info.n_blocks;
+  }
+  for (ecbScene* o : s->objects) in.device_bytes += o->info.device_bytes;
+  in.leaf_kind = s->objects.empty() ? 0 : s->objects[0]->info.leaf_kind;
+  memcpy(in.bounds, desc->bounds, sizeof(in.bounds));
+  in.device = -1;
+  *out = s;
+  return ECB_SUCCESS;
+}

@@ -711,6 +711,209 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// instanced scenes: BVHNIntersector1<4,BVH_AN1,robust=false,ArrayIntersector1<ObjectIntersector1>> over the instances
+// (kernels/bvh/bvh_intersector1_bvh4.cpp:81), FastInstanceIntersectorN::intersect1/occluded1 per instance
+// (kernels/geometry/instance_intersector.cpp:45-83).  One thread per ray, two stacks (instance level, object level).
+// ---------------------------------------------------------------------------------------------------------------
+struct FastRay {
+  float rdir[3], org_rdir[3];
+  int nu[3];
+  float tnear, tfar;
+};
+
+__device__ __forceinline__ void fastray_init(FastRay& r, const float org[3], const float dir[3], float tnear, float tfar) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    r.rdir[k] = 1.0f / zero_fix(dir[k]);  // rcp_safe (node_intersector1.h:41)
+    r.org_rdir[k] = org[k] * r.rdir[k];
+    r.nu[k] = r.rdir[k] >= 0.0f ? 0 : 1;
+  }
+  r.tnear = tnear;
+  r.tfar = tfar;
+}
+
+// intersectNode<4,4> AVX2 / SSE4.1 path (node_intersector1.h:208-232): fused plane*rdir - org*rdir, integer max/min
+// on the float bits (maxi/mini), integer compare for the mask
+__device__ __forceinline__ float maxi_f(float a, float b) { return __float_as_int(a) > __float_as_int(b) ? a : b; }
+__device__ __forceinline__ float mini_f(float a, float b) { return __float_as_int(a) < __float_as_int(b) ? a : b; }
+
+__device__ __forceinline__ unsigned fast_node(const EcbTopNode* nodes, uint32_t index, const FastRay& tr, float tNear[4], uint32_t child[4]) {
+  const float4* p = reinterpret_cast<const float4*>(nodes + index);
+  const float4 nx = __ldg(p + tr.nu[0]), fx = __ldg(p + (1 - tr.nu[0]));
+  const float4 ny = __ldg(p + 2 + tr.nu[1]), fy = __ldg(p + (3 - tr.nu[1]));
+  const float4 nz = __ldg(p + 4 + tr.nu[2]), fz = __ldg(p + (5 - tr.nu[2]));
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(p + 6));
+  child[0] = c.x; child[1] = c.y; child[2] = c.z; child[3] = c.w;
+  unsigned mask = 0;
+#define ECB_FAST_CHILD(i, m)                                                                           \
+  {                                                                                                    \
+    const float tnx = __fmaf_rn(nx.m, tr.rdir[0], -tr.org_rdir[0]), tny = __fmaf_rn(ny.m, tr.rdir[1], -tr.org_rdir[1]); \
+    const float tnz = __fmaf_rn(nz.m, tr.rdir[2], -tr.org_rdir[2]);                                    \
+    const float tfx = __fmaf_rn(fx.m, tr.rdir[0], -tr.org_rdir[0]), tfy = __fmaf_rn(fy.m, tr.rdir[1], -tr.org_rdir[1]); \
+    const float tfz = __fmaf_rn(fz.m, tr.rdir[2], -tr.org_rdir[2]);                                    \
+    const float tn = maxi_f(maxi_f(tnx, tny), maxi_f(tnz, tr.tnear));                                  \
+    const float tf = mini_f(mini_f(tfx, tfy), mini_f(tfz, tr.tfar));                                   \
+    tNear[i] = tn;                                                                                     \
+    if (!(__float_as_int(tn) > __float_as_int(tf))) mask |= 1u << i;                                   \
+  }
+  ECB_FAST_CHILD(0, x)
+  ECB_FAST_CHILD(1, y)
+  ECB_FAST_CHILD(2, z)
+  ECB_FAST_CHILD(3, w)
+#undef ECB_FAST_CHILD
+  return mask;
+}
+
+// closest hit inside one object scene (what rtcIntersect1 on the instanced scene does)
+template <int LEAF>
+__device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
+                                          float ray_tnear, Hit& hit) {
+  uint32_t stack_ref[ECB_MAX_TOP_STACK];
+  uint32_t stack_dist[ECB_MAX_TOP_STACK];
+  if (sc.root == ECB_REF_EMPTY) return;
+  Work work = {0u, 0u, 0u, 0u};
+  TravRay tr;
+  travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(hit.tfar, 0.0f));
+  stack_ref[0] = sc.root;
+  stack_dist[0] = 0xff800000u;
+  int sp = 1;
+  for (;;) {
+    const uint32_t leaf = next_block<false>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+    if (leaf == ECB_REF_EMPTY) break;
+    block_intersect<LEAF, false>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+    tr.tfar = hit.tfar;
+  }
+}
+
+__device__ __forceinline__ void instance_ray(const EcbInstance* in, const float o[3], const float d[3], float lo[3], float ld[3],
+                                             uint32_t& geomID, uint32_t& object) {
+  const float4* q = reinterpret_cast<const float4*>(in);
+  const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  const uint4 e = __ldg(reinterpret_cast<const uint4*>(q + 3));
+  const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // xfmPoint / xfmVector: nested madd = FMA on AVX2 (affinespace.h:110-111)
+    lo[k] = __fmaf_rn(o[0], m[k], __fmaf_rn(o[1], m[3 + k], __fmaf_rn(o[2], m[6 + k], m[9 + k])));
+    ld[k] = __fmaf_rn(d[0], m[k], __fmaf_rn(d[1], m[3 + k], d[2] * m[6 + k]));
+  }
+  geomID = e.x;
+  object = e.y;
+}
+
+template <bool ANYHIT>
+__global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceInstScene is, EcbLaunch L) {
+  __shared__ float lut[32];
+  init_lut(lut);
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* rp = L.in + i * L.in_stride;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+    if (r0.w > tfar_in) continue;
+    if (ANYHIT && tfar_in < 0.0f) continue;
+    if (is.root == ECB_REF_EMPTY) continue;
+    const float org[3] = {r0.x, r0.y, r0.z};
+    const float dir[3] = {r1.x, r1.y, r1.z};
+    Hit hit;
+    hit.tfar = tfar_in;
+    hit.u = hit.v = 0.f;
+    hit.primID = hit.geomID = hit.block = 0xFFFFFFFFu;
+    uint32_t hit_inst = 0xFFFFFFFFu;
+    bool occluded = false;
+    FastRay tr;
+    fastray_init(tr, org, dir, sse_max_exact(r0.w, 0.0f), sse_max_exact(tfar_in, 0.0f));
+    uint32_t stack_ref[ECB_MAX_TOP_STACK];
+    uint32_t stack_dist[ECB_MAX_TOP_STACK];
+    int sp = 1;
+    stack_ref[0] = is.root;
+    stack_dist[0] = 0xff800000u;
+    while (sp > 0 && !occluded) {
+      sp--;
+      uint32_t cur = stack_ref[sp];
+      if (!ANYHIT && __uint_as_float(stack_dist[sp]) > hit.tfar) continue;
+      bool popped = false;
+      while (!(cur & ECB_REF_LEAF)) {
+        float tNear[4];
+        uint32_t child[4];
+        const unsigned mask = fast_node(is.nodes, cur, tr, tNear, child);
+        if (mask == 0) { popped = true; break; }
+        uint32_t c[4], d[4];
+        int nh = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (mask & (1u << r)) { c[nh] = child[r]; d[nh] = __float_as_uint(tNear[r]); nh++; }
+        if (ANYHIT) {  // traverseAnyHit: push all but the last hit child in index order
+          for (int k = 0; k + 1 < nh; k++) stack_ref[sp++] = c[k];
+          cur = c[nh - 1];
+          continue;
+        }
+        if (nh == 1) { cur = c[0]; continue; }
+        if (nh == 2) {
+          if (d[0] < d[1]) { stack_ref[sp] = c[1]; stack_dist[sp] = d[1]; sp++; cur = c[0]; }
+          else             { stack_ref[sp] = c[0]; stack_dist[sp] = d[0]; sp++; cur = c[1]; }
+          continue;
+        }
+        if (nh == 3) {
+          uint32_t r1_ = c[2], d1 = d[2], r2 = c[1], d2 = d[1], r3 = c[0], d3 = d[0];
+          cswap(r1_, d1, r2, d2);
+          cswap(r2, d2, r3, d3);
+          cswap(r1_, d1, r2, d2);
+          stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
+          stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
+          cur = r1_;
+          continue;
+        }
+        {
+          uint32_t r1_ = c[3], d1 = d[3], r2 = c[2], d2 = d[2], r3 = c[1], d3 = d[1], r4 = c[0], d4 = d[0];
+          cswap(r1_, d1, r2, d2);
+          cswap(r3, d3, r4, d4);
+          cswap(r1_, d1, r3, d3);
+          cswap(r2, d2, r4, d4);
+          cswap(r2, d2, r3, d3);
+          stack_ref[sp] = r4; stack_dist[sp] = d4; sp++;
+          stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
+          stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
+          cur = r1_;
+        }
+      }
+      if (popped || cur == ECB_REF_EMPTY) continue;
+      const uint32_t first = (cur & ~ECB_REF_LEAF) >> 3, num = cur & 7u;
+      for (uint32_t k = 0; k < num && !occluded; k++) {
+        const EcbInstance* in = is.instances + __ldg(is.items + first + k);
+        float lo[3], ld[3];
+        uint32_t geomID, object;
+        instance_ray(in, org, dir, lo, ld, geomID, object);
+        const EcbDeviceScene sc = is.objects[object];
+        if (ANYHIT) {
+          if (sc.root != ECB_REF_EMPTY && trace_any(sc, lo, ld, r0.w, hit.tfar)) occluded = true;
+        } else {
+          const uint32_t before = hit.block;
+          hit.block = 0xFFFFFFFFu;
+          switch (sc.leaf_kind) {
+            case 0: trace_object<0>(sc, lut, lo, ld, r0.w, hit); break;
+            case 1: trace_object<1>(sc, lut, lo, ld, r0.w, hit); break;
+            default: trace_object<2>(sc, lut, lo, ld, r0.w, hit); break;
+          }
+          if (hit.block != 0xFFFFFFFFu) hit_inst = geomID;
+          else hit.block = before;
+        }
+      }
+      tr.tfar = hit.tfar;
+    }
+    uint8_t* op = L.out + i * L.out_stride;
+    if (ANYHIT) {
+      if (occluded) *reinterpret_cast<float*>(op + 32) = __int_as_float(0xff800000);
+    } else if (hit_inst != 0xFFFFFFFFu) {
+      *reinterpret_cast<float*>(op + 32) = hit.tfar;
+      *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);
+      *reinterpret_cast<float4*>(op + 64) =
+          make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(hit_inst));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
@@ -768,5 +971,13 @@ cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbL
   if (L.M == 0) return cudaSuccess;
   const int grid = grid_for(L.M, device);
   ecb_occluded_kernel<<<grid, ECB_THREADS, 0, stream>>>(sc, L);
+  return cudaGetLastError();
+}
+
+cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream) {
+  if (L.M == 0) return cudaSuccess;
+  const int grid = grid_for(L.M, device);
+  if (any_hit) ecb_instanced_kernel<true><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  else ecb_instanced_kernel<false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
   return cudaGetLastError();
 }

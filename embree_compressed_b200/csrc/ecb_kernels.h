@@ -37,3 +37,4 @@ struct EcbLaunch {
 
 cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
 cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
+cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);

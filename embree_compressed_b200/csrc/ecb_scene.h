@@ -25,6 +25,17 @@ struct ecbScene {
   void* d_blocks = nullptr;
   EcbDeviceScene dev{};
 
+  // instanced scenes: instance-level BVH4 (in `top`), Object items, instance records, retained object scenes
+  bool instanced = false;
+  std::vector<uint32_t> items;
+  std::vector<EcbInstance> instances;
+  std::vector<ecbScene*> objects;
+  void* d_items = nullptr;
+  void* d_instances = nullptr;
+  void* d_objects = nullptr;
+  EcbDeviceInstScene inst_dev{};
+  std::atomic<int> refs{1};
+
   // ring of device words used as dynamic ray-fetch cursors, one per launch in flight
   unsigned long long* d_queues = nullptr;
   std::atomic<uint32_t> next_queue{0};
@@ -35,3 +46,4 @@ struct ecbScene {
 
 void ecb_set_error(const std::string& msg);
 ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out);
+ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out);

@@ -79,9 +79,25 @@ typedef struct ecbSceneInfo {
   int32_t device;              /* CUDA device ordinal the scene is resident on, -1 if host only */
 } ecbSceneInfo;
 
+/* An instancing scene: the host's user-geometry BVH4 over RTC_GEOMETRY_TYPE_INSTANCE geometries
+ * (device config object_accel=bvh4.object) plus, per instance, what kernels/common/scene_instance.h holds. */
+typedef struct ecbInstanceDesc {
+  const void* base;          /* as in ecbImportDesc */
+  uint64_t root;             /* BVH4::root of the accel created by BVH4Factory::BVH4UserGeometry (bvh4_factory.cpp:1678) */
+  uint32_t n_instances;
+  uint32_t reserved;
+  const uint32_t* geomIDs;   /* geomID of each instance geometry inside the instancing scene (becomes hit.instID) */
+  const float* world2local;  /* 12 floats per instance: l.vx, l.vy, l.vz, p of Instance::world2local0 */
+  ecbScene* const* objects;  /* imported scene each instance refers to (entries may repeat; retained by the new scene) */
+  float bounds[6];
+} ecbInstanceDesc;
+
 /* ---- scene ---------------------------------------------------------------------------------------- */
 /* Converts the reference's committed compressed BVH4 into the device scene format (host work only). */
 ECB_API ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out);
+/* Builds the device structure of an instancing scene; ray queries on it restate FastInstanceIntersectorN::intersect1 /
+ * occluded1 (kernels/geometry/instance_intersector.cpp:45-83) over the non-robust BVH4 traversal of the instance level. */
+ECB_API ecbError ecbSceneImportInstances(const ecbInstanceDesc* desc, ecbScene** scene_out);
 /* Convenience: import from an RIMG file / buffer (header carries root, leaf kind, S, C, bounds). */
 ECB_API ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out);
 ECB_API ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out);

@@ -642,8 +642,160 @@ void cbvh_occluded1(const cbvh_scene* s, cbvh_ray* ray, cbvh_stats* st) {
   }
 }
 
+/* ---- instancing: BVHNIntersector1<4,BVH_AN1,robust=false,ArrayIntersector1<ObjectIntersector1>> over instances ----
+ * kernels/bvh/bvh_intersector1_bvh4.cpp:81 ; non-robust TravRay (node_intersector1.h:38-55) and
+ * intersectNode<4,4> AVX2/SSE4.1 path (:208-232): t = plane*rdir - org*rdir as ONE fused multiply-subtract, integer
+ * max/min on the float bits (maxi/mini) and an integer compare for the hit mask. */
+typedef struct travray_fast {
+  float rdir[3], org_rdir[3];
+  int near_is_upper[3];
+  float tnear, tfar;
+} travray_fast;
+
+static inline int32_t ibits(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+static inline float maxi_f(float a, float b) { return ibits(a) > ibits(b) ? a : b; } /* _mm_max_epi32 on float bits */
+static inline float mini_f(float a, float b) { return ibits(a) < ibits(b) ? a : b; }
+
+static void travray_fast_init(travray_fast* r, const float org[3], const float dir[3], float tnear, float tfar) {
+  for (int k = 0; k < 3; k++) {
+    r->rdir[k] = 1.0f / zero_fix(dir[k]); /* rcp_safe: rcpps + Newton in the reference */
+    r->org_rdir[k] = org[k] * r->rdir[k];
+    r->near_is_upper[k] = r->rdir[k] >= 0.0f ? 0 : 1;
+  }
+  r->tnear = tnear;
+  r->tfar = tfar;
+}
+
+static unsigned node4_intersect_fast(const node4* n, const travray_fast* r, float tNear[4]) {
+  unsigned mask = 0;
+  for (int i = 0; i < 4; i++) {
+    const float tnx = fmaf(n->b[0 + r->near_is_upper[0]][i], r->rdir[0], -r->org_rdir[0]);
+    const float tny = fmaf(n->b[2 + r->near_is_upper[1]][i], r->rdir[1], -r->org_rdir[1]);
+    const float tnz = fmaf(n->b[4 + r->near_is_upper[2]][i], r->rdir[2], -r->org_rdir[2]);
+    const float tfx = fmaf(n->b[1 - r->near_is_upper[0]][i], r->rdir[0], -r->org_rdir[0]);
+    const float tfy = fmaf(n->b[3 - r->near_is_upper[1]][i], r->rdir[1], -r->org_rdir[1]);
+    const float tfz = fmaf(n->b[5 - r->near_is_upper[2]][i], r->rdir[2], -r->org_rdir[2]);
+    const float tn = maxi_f(maxi_f(tnx, tny), maxi_f(tnz, r->tnear));
+    const float tf = mini_f(mini_f(tfx, tfy), mini_f(tfz, r->tfar));
+    tNear[i] = tn;
+    if (!(ibits(tn) > ibits(tf))) mask |= 1u << i;
+  }
+  return mask;
+}
+
+/* FastInstanceIntersectorN::intersect1 / occluded1 (instance_intersector.cpp:45-83): xfmPoint / xfmVector of
+ * AffineSpace3fa are nested madd (common/math/affinespace.h:110-111, linearspace3.h:168-169) = FMA on AVX2 */
+static void instance_ray(const cbvh_instance* in, const float o[3], const float d[3], float lo[3], float ld[3]) {
+  const float* m = in->world2local;
+  for (int k = 0; k < 3; k++) {
+    lo[k] = fmaf(o[0], m[0 + k], fmaf(o[1], m[3 + k], fmaf(o[2], m[6 + k], m[9 + k])));
+    ld[k] = fmaf(d[0], m[0 + k], fmaf(d[1], m[3 + k], d[2] * m[6 + k]));
+  }
+}
+
+static void inst_traverse(const cbvh_inst_scene* s, cbvh_rayhit* rh, int any_hit, cbvh_stats* st) {
+  stack_item stack[256];
+  int sp = 1;
+  stack[0].ref = s->root;
+  stack[0].dist = 0xff800000u;
+  const float org[3] = {rh->ray.org_x, rh->ray.org_y, rh->ray.org_z};
+  const float dir[3] = {rh->ray.dir_x, rh->ray.dir_y, rh->ray.dir_z};
+  travray_fast tr;
+  travray_fast_init(&tr, org, dir, sse_max(rh->ray.tnear, 0.0f), sse_max(rh->ray.tfar, 0.0f));
+  while (sp > 0) {
+    sp--;
+    uint64_t cur = stack[sp].ref;
+    if (!any_hit && bitsf(stack[sp].dist) > rh->ray.tfar) continue;
+    for (;;) {
+      if (cur & REF_TY_LEAF) break;
+      const uint8_t* np = s->base + (cur & ~REF_ALIGN_MASK);
+      node4 n;
+      load_aligned_node(np, &n);
+      float tNear[4];
+      unsigned mask = node4_intersect_fast(&n, &tr, tNear);
+      if (mask == 0) goto pop;
+      unsigned c[4];
+      int nh = 0;
+      for (unsigned r = 0; r < 4; r++)
+        if (mask & (1u << r)) c[nh++] = r;
+      if (any_hit) { /* traverseAnyHit */
+        for (int i = 0; i + 1 < nh; i++) stack[sp++].ref = ldq(np + AN_CHILDREN + 8 * c[i]);
+        cur = ldq(np + AN_CHILDREN + 8 * c[nh - 1]);
+        continue;
+      }
+      const uint64_t c0 = ldq(np + AN_CHILDREN + 8 * c[0]);
+      if (nh == 1) { cur = c0; continue; }
+      const uint32_t d0 = fbits(tNear[c[0]]);
+      const uint64_t c1 = ldq(np + AN_CHILDREN + 8 * c[1]);
+      const uint32_t d1 = fbits(tNear[c[1]]);
+      if (nh == 2) {
+        if (d0 < d1) { stack[sp].ref = c1; stack[sp].dist = d1; sp++; cur = c0; }
+        else         { stack[sp].ref = c0; stack[sp].dist = d0; sp++; cur = c1; }
+        continue;
+      }
+      stack[sp].ref = c0; stack[sp].dist = d0; sp++;
+      stack[sp].ref = c1; stack[sp].dist = d1; sp++;
+      stack[sp].ref = ldq(np + AN_CHILDREN + 8 * c[2]); stack[sp].dist = fbits(tNear[c[2]]); sp++;
+      if (nh == 3) {
+        stack_item *s1 = &stack[sp - 1], *s2 = &stack[sp - 2], *s3 = &stack[sp - 3];
+        if (s2->dist < s1->dist) xchg(s2, s1);
+        if (s3->dist < s2->dist) xchg(s3, s2);
+        if (s2->dist < s1->dist) xchg(s2, s1);
+        cur = stack[sp - 1].ref; sp--;
+        continue;
+      }
+      stack[sp].ref = ldq(np + AN_CHILDREN + 8 * c[3]); stack[sp].dist = fbits(tNear[c[3]]); sp++;
+      {
+        stack_item *s1 = &stack[sp - 1], *s2 = &stack[sp - 2], *s3 = &stack[sp - 3], *s4 = &stack[sp - 4];
+        if (s2->dist < s1->dist) xchg(s2, s1);
+        if (s4->dist < s3->dist) xchg(s4, s3);
+        if (s3->dist < s1->dist) xchg(s3, s1);
+        if (s4->dist < s2->dist) xchg(s4, s2);
+        if (s3->dist < s2->dist) xchg(s3, s2);
+        cur = stack[sp - 1].ref; sp--;
+      }
+    }
+    if (cur == REF_TY_LEAF) continue;
+    { /* leaf: `num` Object primitives {geomID, primID} (ArrayIntersector1, intersector_iterators.h:27-45) */
+      const unsigned num = (unsigned)((cur & REF_ALIGN_MASK) - REF_TY_LEAF);
+      const uint8_t* prims = s->base + (cur & ~REF_ALIGN_MASK);
+      for (unsigned i = 0; i < num; i++) {
+        const uint32_t geomID = ldu(prims + 8 * i);
+        if (geomID >= s->n_geoms || s->geom_to_instance[geomID] == 0xffffffffu) continue;
+        const cbvh_instance* in = &s->instances[s->geom_to_instance[geomID]];
+        cbvh_rayhit local = *rh;
+        float lo[3], ld[3];
+        instance_ray(in, org, dir, lo, ld);
+        local.ray.org_x = lo[0]; local.ray.org_y = lo[1]; local.ray.org_z = lo[2];
+        local.ray.dir_x = ld[0]; local.ray.dir_y = ld[1]; local.ray.dir_z = ld[2];
+        if (any_hit) {
+          cbvh_occluded1(&s->objects[in->object], &local.ray, st);
+          if (local.ray.tfar < 0.0f) { rh->ray.tfar = -INFINITY; return; } /* object_intersector.h:61, bvh_intersector1.cpp:199 */
+        } else {
+          cbvh_intersect1(&s->objects[in->object], &local, in->geomID, st);
+          rh->ray.tfar = local.ray.tfar;
+          rh->hit = local.hit;
+        }
+      }
+      tr.tfar = rh->ray.tfar;
+    }
+  pop:;
+  }
+}
+
+void cbvh_inst_intersect1(const cbvh_inst_scene* scene, cbvh_rayhit* rh, cbvh_stats* stats) { inst_traverse(scene, rh, 0, stats); }
+void cbvh_inst_occluded1(const cbvh_inst_scene* scene, cbvh_ray* ray, cbvh_stats* stats) {
+  if (ray->tfar < 0.0f) return;
+  cbvh_rayhit tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  tmp.ray = *ray;
+  inst_traverse(scene, &tmp, 1, stats);
+  ray->tfar = tmp.ray.tfar;
+}
+
 /* ---- threaded drivers ---- */
 typedef struct job {
+  const cbvh_inst_scene* inst;
   const cbvh_scene* scene;
   char* base;
   size_t n, stride;
@@ -670,16 +822,24 @@ static void* worker(void* arg) {
         cbvh_ray* r = (cbvh_ray*)p;
         if (r->tnear > r->tfar) continue;
         cbvh_occluded1(j->scene, r, &j->stats);
-      } else {
+      } else if (j->mode == 2) {
         cbvh_candidates1(j->scene, (const cbvh_rayhit*)p, &j->cand[i]);
+      } else if (j->mode == 3) {
+        cbvh_rayhit* rh = (cbvh_rayhit*)p;
+        if (rh->ray.tnear > rh->ray.tfar) continue;
+        cbvh_inst_intersect1(j->inst, rh, &j->stats);
+      } else {
+        cbvh_ray* r = (cbvh_ray*)p;
+        if (r->tnear > r->tfar) continue;
+        cbvh_inst_occluded1(j->inst, r, &j->stats);
       }
     }
   }
   return NULL;
 }
 
-static double run(const cbvh_scene* scene, void* base, size_t n, size_t stride, int nthreads, int mode,
-                  cbvh_stats* stats, cbvh_candidates* cand) {
+static double run_ex(const cbvh_scene* scene, const cbvh_inst_scene* inst, void* base, size_t n, size_t stride, int nthreads,
+                     int mode, cbvh_stats* stats, cbvh_candidates* cand) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   volatile size_t next = 0;
@@ -688,7 +848,7 @@ static double run(const cbvh_scene* scene, void* base, size_t n, size_t stride, 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int i = 0; i < nthreads; i++) {
-    jobs[i].scene = scene; jobs[i].base = (char*)base; jobs[i].n = n; jobs[i].stride = stride;
+    jobs[i].scene = scene; jobs[i].inst = inst; jobs[i].base = (char*)base; jobs[i].n = n; jobs[i].stride = stride;
     jobs[i].mode = mode; jobs[i].next = &next; jobs[i].cand = cand;
     if (nthreads > 1) pthread_create(&th[i], NULL, worker, &jobs[i]);
   }
@@ -708,6 +868,16 @@ static double run(const cbvh_scene* scene, void* base, size_t n, size_t stride, 
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+static double run(const cbvh_scene* scene, void* base, size_t n, size_t stride, int nthreads, int mode, cbvh_stats* stats,
+                  cbvh_candidates* cand) {
+  return run_ex(scene, NULL, base, n, stride, nthreads, mode, stats, cand);
+}
+double cbvh_inst_intersectN(const cbvh_inst_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats) {
+  return run_ex(NULL, scene, rayhits, n, stride, nthreads, 3, stats, NULL);
+}
+double cbvh_inst_occludedN(const cbvh_inst_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats) {
+  return run_ex(NULL, scene, rays, n, stride, nthreads, 4, stats, NULL);
+}
 double cbvh_intersectN(const cbvh_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats) {
   return run(scene, rayhits, n, stride, nthreads, 0, stats, NULL);
 }

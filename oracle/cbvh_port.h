@@ -70,6 +70,33 @@ double cbvh_occludedN(const cbvh_scene* scene, void* rays, size_t n, size_t stri
 void cbvh_candidates1(const cbvh_scene* scene, const cbvh_rayhit* rh, cbvh_candidates* out);
 void cbvh_candidatesN(const cbvh_scene* scene, const void* rayhits, size_t n, size_t stride, int nthreads, cbvh_candidates* out);
 
+/* ---- instanced scenes --------------------------------------------------------------------------
+ * Top level: the reference's user-geometry BVH4 (NON-robust node test, leaves = arrays of Object{geomID,primID});
+ * each instance transforms the ray with world2local, sets instID = its geomID and runs cbvh_intersect1 /
+ * cbvh_occluded1 on the instanced scene (kernels/geometry/instance_intersector.cpp:45-83). */
+typedef struct cbvh_instance {
+  float world2local[12];   /* vx, vy, vz, p */
+  uint32_t geomID;
+  uint32_t object;         /* index into cbvh_inst_scene::objects */
+} cbvh_instance;
+
+typedef struct cbvh_inst_scene {
+  const uint8_t* base;
+  uint64_t root;                 /* root NodeRef of the user-geometry BVH4 */
+  const cbvh_instance* instances;
+  uint32_t n_instances;
+  uint32_t reserved;
+  const uint32_t* geom_to_instance; /* geomID -> index into instances (0xFFFFFFFF if not an instance) */
+  uint32_t n_geoms;
+  uint32_t reserved2;
+  const cbvh_scene* objects;
+} cbvh_inst_scene;
+
+void cbvh_inst_intersect1(const cbvh_inst_scene* scene, cbvh_rayhit* rh, cbvh_stats* stats);
+void cbvh_inst_occluded1(const cbvh_inst_scene* scene, cbvh_ray* ray, cbvh_stats* stats);
+double cbvh_inst_intersectN(const cbvh_inst_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
+double cbvh_inst_occludedN(const cbvh_inst_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

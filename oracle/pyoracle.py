@@ -88,6 +88,8 @@ def ref_lib():
         L.ref_scene_dump_image.restype = C.c_size_t
         L.ref_scene_dump_image.argtypes = [vp, vp, C.c_size_t]
         L.ref_hardware_threads.restype = C.c_int
+        L.ref_scene_instance_info.restype = C.c_int
+        L.ref_scene_instance_info.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint, vp, vp, vp]
         _ref = L
     return _ref
 
@@ -169,6 +171,18 @@ class RefScene:
         n = np.zeros((rayhits.shape[0], 3), np.float32)
         self.L.ref_hit_normals(self.h, rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0], n.ctypes.data)
         return n
+
+    def instance_info(self, cap=4096):
+        """(root of the user-geometry BVH4, geomIDs[n], world2local[n,12], instanced RTCScene handles[n])."""
+        root = C.c_uint64()
+        ids = np.zeros(cap, np.uint32)
+        xf = np.zeros((cap, 12), np.float32)
+        objs = (C.c_void_p * cap)()
+        n = self.L.ref_scene_instance_info(self.h, C.byref(root), cap, ids.ctypes.data, xf.ctypes.data, objs)
+        if n < 0:
+            raise RuntimeError("scene has no instance accel")
+        assert n <= cap
+        return root.value, ids[:n].copy(), xf[:n].copy(), [objs[i] for i in range(n)]
 
     def dump_image(self):
         size = self.L.ref_scene_dump_image(self.h, None, 0)
@@ -267,3 +281,56 @@ class PortScene:
         self.L.cbvh_candidatesN(C.byref(self.s), rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0],
                                 threads or hardware_threads(), out.ctypes.data)
         return out  # columns: t_best, t_second, prim_best(bits), prim_second(bits)
+
+
+# ---------------------------------------------------------------------------------------------- instanced port
+class _PortInstance(C.Structure):
+    _fields_ = [("world2local", C.c_float * 12), ("geomID", C.c_uint32), ("object", C.c_uint32)]
+
+
+class _PortInstScene(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("instances", C.POINTER(_PortInstance)), ("n_instances", C.c_uint32),
+                ("reserved", C.c_uint32), ("geom_to_instance", C.POINTER(C.c_uint32)), ("n_geoms", C.c_uint32),
+                ("reserved2", C.c_uint32), ("objects", C.POINTER(_PortScene))]
+
+
+class PortInstancedScene:
+    """The C restatement of the instancing path bound to a live reference scene of instances."""
+
+    def __init__(self, ref_top, object_scenes):
+        """ref_top: committed RefScene whose geometries are instances of the RefScenes in object_scenes."""
+        self.L = port_lib()
+        self.L.cbvh_inst_intersectN.restype = C.c_double
+        self.L.cbvh_inst_intersectN.argtypes = [C.POINTER(_PortInstScene), C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                                C.POINTER(_Stats)]
+        self.L.cbvh_inst_occludedN.restype = C.c_double
+        self.L.cbvh_inst_occludedN.argtypes = self.L.cbvh_inst_intersectN.argtypes
+        root, ids, xf, handles = ref_top.instance_info()
+        by_handle = {o.handle(): i for i, o in enumerate(object_scenes)}
+        self.objects = (_PortScene * len(object_scenes))()
+        lay = ref_layout()
+        for i, o in enumerate(object_scenes):
+            r, _ = o.root()
+            self.objects[i] = _PortScene(0, r, LEAF_KINDS[o.leaf.split(",")[0]], lay["proj_col_major"])
+        self.instances = (_PortInstance * len(ids))()
+        n_geoms = int(ids.max()) + 1 if len(ids) else 0
+        self.g2i = (C.c_uint32 * max(1, n_geoms))(*([INVALID] * max(1, n_geoms)))
+        for k in range(len(ids)):
+            self.instances[k].geomID = int(ids[k])
+            self.instances[k].object = by_handle[handles[k]]
+            for j in range(12):
+                self.instances[k].world2local[j] = float(xf[k, j])
+            self.g2i[int(ids[k])] = k
+        self.s = _PortInstScene(0, root, self.instances, len(ids), 0, self.g2i, n_geoms, 0, self.objects)
+        self.keepalive = (ref_top, object_scenes)
+        self.info = (root, ids, xf, [by_handle[h] for h in handles])
+
+    def intersect(self, rayhits, threads=None):
+        st = _Stats()
+        return self.L.cbvh_inst_intersectN(C.byref(self.s), rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0],
+                                           threads or hardware_threads(), C.byref(st))
+
+    def occluded(self, rays, threads=None):
+        st = _Stats()
+        return self.L.cbvh_inst_occludedN(C.byref(self.s), rays.ctypes.data, rays.shape[0], rays.strides[0],
+                                          threads or hardware_threads(), C.byref(st))

@@ -20,6 +20,8 @@
 #include "kernels/geometry/subdivpatch1cached.h"
 #include "kernels/geometry/grid_soa.h"
 #include "kernels/geometry/compressed.h"
+#include "kernels/geometry/object.h"
+#include "kernels/common/scene_instance.h"
 
 #include <atomic>
 #include <chrono>
@@ -52,7 +54,8 @@ RTCDevice get_device(const std::string& leaf, int threads) {
   std::lock_guard<std::mutex> lock(g_mutex);
   std::string accel = leaf.compare(0, 5, "eager") == 0 ? "bvh4.grid." + leaf : "bvh4.compressed." + leaf;
   // set_affinity=0: with the internal tasking system the default pins the calling thread (kernels/common/state.cpp:123-128)
-  std::string cfg = "subdiv_accel=" + accel + ",set_affinity=0,start_threads=0";
+  // object_accel=bvh4.object: instances go into a BVH4 (the default on AVX hardware is a BVH8, kernels/common/scene.cpp:531-555)
+  std::string cfg = "subdiv_accel=" + accel + ",object_accel=bvh4.object,set_affinity=0,start_threads=0";
   if (threads > 0) cfg += ",threads=" + std::to_string(threads);
   auto it = g_devices.find(cfg);
   if (it != g_devices.end()) return it->second;
@@ -473,4 +476,42 @@ REF_API int rtcGetCompressedBVH_b200(RTCScene hscene, RTCCompressedBVHInfo_b200*
   out->bounds[0] = b.lower_x; out->bounds[1] = b.lower_y; out->bounds[2] = b.lower_z;
   out->bounds[3] = b.upper_x; out->bounds[4] = b.upper_y; out->bounds[5] = b.upper_z;
   return out->root ? 0 : -2;
+}
+
+// ---- instancing: what the host hands over for a scene whose geometries are instances ----
+// root of the user-geometry BVH4 (leaves = arrays of Object{geomID,primID}, kernels/geometry/object.h) and, per
+// instance geometry, its world2local transform, geomID and instanced scene (kernels/common/scene_instance.h:54-56,91).
+REF_API int ref_scene_instance_info(RefScene* s, uint64_t* root_out, unsigned cap, unsigned* geomIDs, float* world2local12,
+                                    void** object_scenes) {
+  using namespace embree;
+  Scene* scene = (Scene*)s->scene;
+  *root_out = 0;
+  AccelData* accel = ((Accel*)s->scene)->intersectors.ptr;
+  BVH4* bvh = nullptr;
+  if (accel && accel->type == AccelData::TY_BVH4) bvh = (BVH4*)accel;
+  else if (accel && accel->type == AccelData::TY_ACCELN) {
+    AccelN* an = (AccelN*)accel;
+    for (size_t i = 0; i < an->accels.size(); i++) {
+      AccelData* a = an->accels[i]->intersectors.ptr;
+      if (a && a->type == AccelData::TY_BVH4 && ((BVH4*)a)->primTy == &Object::type) bvh = (BVH4*)a;
+    }
+  }
+  if (!bvh || bvh->primTy != &Object::type) return -1;
+  *root_out = (uint64_t)(size_t)bvh->root;
+  unsigned n = 0;
+  for (size_t i = 0; i < scene->size(); i++) {
+    Geometry* g = scene->get(i);
+    // an Instance is an AccelSet registered as USER_GEOMETRY (kernels/common/scene_instance.cpp:31-39)
+    Instance* inst = g ? dynamic_cast<Instance*>(g) : nullptr;
+    if (!inst) continue;
+    if (n < cap) {
+      geomIDs[n] = (unsigned)i;
+      const AffineSpace3fa w = inst->getWorld2Local();
+      const float m[12] = {w.l.vx.x, w.l.vx.y, w.l.vx.z, w.l.vy.x, w.l.vy.y, w.l.vy.z, w.l.vz.x, w.l.vz.y, w.l.vz.z, w.p.x, w.p.y, w.p.z};
+      memcpy(world2local12 + 12 * n, m, sizeof(m));
+      object_scenes[n] = (void*)inst->object;
+    }
+    n++;
+  }
+  return (int)n;
 }

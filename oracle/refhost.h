@@ -69,6 +69,10 @@ void ref_hit_normals(RefScene*, const void* rayhits, size_t n, size_t stride, fl
  * their tag bits kept.  Layout of the 96-byte header: see rimg.h.  Returns the image size (call with cap=0 to size). */
 size_t ref_scene_dump_image(RefScene*, void* buf, size_t cap);
 
+/* Instanced scenes: root NodeRef of the user-geometry BVH4 and, for each instance geometry (up to cap), its geomID,
+ * world2local (vx,vy,vz,p = 12 floats) and the RTCScene it instances.  Returns the number of instances, <0 if none. */
+int ref_scene_instance_info(RefScene*, uint64_t* root_out, unsigned cap, unsigned* geomIDs, float* world2local12, void** object_scenes);
+
 int ref_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,78 @@
+"""GPU tests (-m gpu): instanced scenes (BASELINE config 4) -- instance-level BVH4 + per-instance ray transform on the
+device, against the oracle port (bit-exact) and the compiled reference (tolerance), incl. tile-sharded frames."""
+import numpy as np
+import pytest
+
+import parity
+from embree_compressed_b200 import raygen as rg
+from embree_compressed_b200 import sharding as sh
+from instancing_util import build_instanced, import_instanced
+
+pytestmark = pytest.mark.gpu
+CAM = dict(vp=(9.0, 7.0, -10.0), vi=(0.0, 0.0, 0.0), vu=(0.0, 1.0, 0.0), fov=70.0)
+
+
+@pytest.mark.parametrize("leaf", ["grid", "leaf", "box"])
+def test_instanced_scene_matches_reference(ecb, reference, leaf):
+    top, objs = build_instanced(reference, leaf, [("cube", 5, 3), ("cube", 4, 3)])
+    port = reference.PortInstancedScene(top, objs)
+    inst, scenes = import_instanced(ecb, reference, top, objs)
+    assert inst.info()["n_blocks"] > 0 and inst.info()["device"] == -1
+    rays = rg.primary_rays(480, 300, **CAM)
+    got, want, truth = rays.copy(), rays.copy(), rays.copy()
+    inst.intersect1M(got)
+    port.intersect(want)
+    top.intersect(truth)
+    bad = parity.bit_exact_mismatches(got, want)
+    assert len(bad) == 0, "instanced CUDA vs port: %d rays differ" % len(bad)
+    c = parity.assert_reference_parity(got, truth, None, "instanced %s primary" % leaf)
+    hit = truth.view(np.uint32)[:, 18] != 0xFFFFFFFF
+    assert c["hits_ref"] > 5000 and len(np.unique(got.view(np.uint32)[hit, 19])) == 25, "every instance must be hit"
+    # incoherent rays + any-hit
+    inc = rg.incoherent_rays(150_000, top.bounds(), seed=11)
+    g2, w2, t2 = inc.copy(), inc.copy(), inc.copy()
+    inst.intersect1M(g2)
+    port.intersect(w2)
+    top.intersect(t2)
+    assert len(parity.bit_exact_mismatches(g2, w2)) == 0
+    parity.assert_reference_parity(g2, t2, None, "instanced %s incoherent" % leaf)
+    o = rg.rays_only(inc)
+    og, ot = o.copy(), o.copy()
+    inst.occluded1M(og)
+    top.occluded(ot)
+    assert (og.view(np.uint32) == ot.view(np.uint32)).all()
+    inst.release()
+    for s in scenes:
+        s.release()
+
+
+def test_config4_tile_sharded_frame(ecb, reference):
+    """Config 4 in miniature: instanced bomberman + cube, cGrid, a frame traced as the tile shards of 4 ranks
+    (each shard through its own call) and reassembled; equal to tracing the whole frame at once."""
+    top, objs = build_instanced(reference, "grid", [("bomberman", 5, 3), ("cube", 5, 3)], grid=1, spacing=30.0)
+    port = reference.PortInstancedScene(top, objs)
+    inst, scenes = import_instanced(ecb, reference, top, objs)
+    W, H = 512, 288
+    cam = dict(vp=(60.0, 45.0, -70.0), vi=(0.0, 0.0, 0.0), vu=(0.0, 1.0, 0.0), fov=60.0)
+    whole = rg.primary_rays(W, H, **cam)
+    full = whole.copy()
+    inst.intersect1M(full)
+    want = whole.copy()
+    port.intersect(want)
+    assert len(parity.bit_exact_mismatches(full, want)) == 0
+    truth = whole.copy()
+    top.intersect(truth)
+    parity.assert_reference_parity(full, truth, None, "config 4 frame")
+    world = 4
+    records = []
+    for rank in range(world):
+        tiles, idx = sh.shard_frame(W, H, rank, world, tile=32)
+        part = np.concatenate([rg.primary_rays(W, H, x0=x0, y0=y0, w=w, h=h, **cam) for x0, y0, w, h in tiles])
+        inst.intersect1M(part)
+        assert (part.view(np.uint32) == full[idx].view(np.uint32)).all()
+        records.append(part[:, sh.HIT_RECORD_COLUMNS].copy())
+    frame = sh.assemble_frame(records, W, H, world, tile=32)
+    assert (frame.view(np.uint32) == full[:, sh.HIT_RECORD_COLUMNS].view(np.uint32)).all()
+    inst.release()
+    for s in scenes:
+        s.release()
