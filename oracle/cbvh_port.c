@@ -693,7 +693,7 @@ static void instance_ray(const cbvh_instance* in, const float o[3], const float 
   }
 }
 
-static void inst_traverse(const cbvh_inst_scene* s, cbvh_rayhit* rh, int any_hit, cbvh_stats* st) {
+static void inst_traverse(const cbvh_inst_scene* s, cbvh_rayhit* rh, int any_hit, cbvh_stats* st, collector* col) {
   stack_item stack[256];
   int sp = 1;
   stack[0].ref = s->root;
@@ -772,6 +772,7 @@ static void inst_traverse(const cbvh_inst_scene* s, cbvh_rayhit* rh, int any_hit
           cbvh_occluded1(&s->objects[in->object], &local.ray, st);
           if (local.ray.tfar < 0.0f) { rh->ray.tfar = -INFINITY; return; } /* object_intersector.h:61, bvh_intersector1.cpp:199 */
         } else {
+          if (col) { top_intersect(&s->objects[in->object], &local, in->geomID, NULL, col); continue; }
           cbvh_intersect1(&s->objects[in->object], &local, in->geomID, st);
           rh->ray.tfar = local.ray.tfar;
           rh->hit = local.hit;
@@ -783,13 +784,20 @@ static void inst_traverse(const cbvh_inst_scene* s, cbvh_rayhit* rh, int any_hit
   }
 }
 
-void cbvh_inst_intersect1(const cbvh_inst_scene* scene, cbvh_rayhit* rh, cbvh_stats* stats) { inst_traverse(scene, rh, 0, stats); }
+void cbvh_inst_intersect1(const cbvh_inst_scene* scene, cbvh_rayhit* rh, cbvh_stats* stats) { inst_traverse(scene, rh, 0, stats, NULL); }
+void cbvh_inst_candidates1(const cbvh_inst_scene* scene, const cbvh_rayhit* rh, cbvh_candidates* out) {
+  cbvh_rayhit tmp = *rh;
+  out->t_best = out->t_second = INFINITY;
+  out->prim_best = out->prim_second = 0xffffffffu;
+  collector c = {out};
+  inst_traverse(scene, &tmp, 0, NULL, &c);
+}
 void cbvh_inst_occluded1(const cbvh_inst_scene* scene, cbvh_ray* ray, cbvh_stats* stats) {
   if (ray->tfar < 0.0f) return;
   cbvh_rayhit tmp;
   memset(&tmp, 0, sizeof(tmp));
   tmp.ray = *ray;
-  inst_traverse(scene, &tmp, 1, stats);
+  inst_traverse(scene, &tmp, 1, stats, NULL);
   ray->tfar = tmp.ray.tfar;
 }
 
@@ -828,10 +836,12 @@ static void* worker(void* arg) {
         cbvh_rayhit* rh = (cbvh_rayhit*)p;
         if (rh->ray.tnear > rh->ray.tfar) continue;
         cbvh_inst_intersect1(j->inst, rh, &j->stats);
-      } else {
+      } else if (j->mode == 4) {
         cbvh_ray* r = (cbvh_ray*)p;
         if (r->tnear > r->tfar) continue;
         cbvh_inst_occluded1(j->inst, r, &j->stats);
+      } else {
+        cbvh_inst_candidates1(j->inst, (const cbvh_rayhit*)p, &j->cand[i]);
       }
     }
   }
@@ -877,6 +887,10 @@ double cbvh_inst_intersectN(const cbvh_inst_scene* scene, void* rayhits, size_t 
 }
 double cbvh_inst_occludedN(const cbvh_inst_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats) {
   return run_ex(NULL, scene, rays, n, stride, nthreads, 4, stats, NULL);
+}
+void cbvh_inst_candidatesN(const cbvh_inst_scene* scene, const void* rayhits, size_t n, size_t stride, int nthreads,
+                           cbvh_candidates* out) {
+  run_ex(NULL, scene, (void*)rayhits, n, stride, nthreads, 5, NULL, out);
 }
 double cbvh_intersectN(const cbvh_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats) {
   return run(scene, rayhits, n, stride, nthreads, 0, stats, NULL);

@@ -95,6 +95,8 @@ typedef struct cbvh_inst_scene {
 void cbvh_inst_intersect1(const cbvh_inst_scene* scene, cbvh_rayhit* rh, cbvh_stats* stats);
 void cbvh_inst_occluded1(const cbvh_inst_scene* scene, cbvh_ray* ray, cbvh_stats* stats);
 double cbvh_inst_intersectN(const cbvh_inst_scene* scene, void* rayhits, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
+void cbvh_inst_candidates1(const cbvh_inst_scene* scene, const cbvh_rayhit* rh, cbvh_candidates* out);
+void cbvh_inst_candidatesN(const cbvh_inst_scene* scene, const void* rayhits, size_t n, size_t stride, int nthreads, cbvh_candidates* out);
 double cbvh_inst_occludedN(const cbvh_inst_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
 
 #ifdef __cplusplus

@@ -330,6 +330,13 @@ class PortInstancedScene:
         return self.L.cbvh_inst_intersectN(C.byref(self.s), rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0],
                                            threads or hardware_threads(), C.byref(st))
 
+    def candidates(self, rayhits, threads=None):
+        self.L.cbvh_inst_candidatesN.argtypes = [C.POINTER(_PortInstScene), C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+        out = np.zeros((rayhits.shape[0], 4), np.float32)
+        self.L.cbvh_inst_candidatesN(C.byref(self.s), rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0],
+                                     threads or hardware_threads(), out.ctypes.data)
+        return out
+
     def occluded(self, rays, threads=None):
         st = _Stats()
         return self.L.cbvh_inst_occludedN(C.byref(self.s), rays.ctypes.data, rays.shape[0], rays.strides[0],

@@ -59,9 +59,18 @@ def classify(x, ref, candidates=None):
             "fragile_rows": np.nonzero(fragile)[0]}
 
 
-def assert_reference_parity(x, ref, candidates, what):
+def assert_reference_parity(x, ref, candidates, what, ref_other_isa=None):
+    """ref_other_isa: the same rays traced by ANOTHER ISA code path of the reference (e.g. max_isa=sse4.2).  When
+    given, the fragile budget is the larger of MAX_FRAGILE_FRACTION and 1.25 x the reference's own disagreement with
+    itself on these rays (ill-conditioned workloads: distant cameras over tiny micro-triangles amplify the last ulp of
+    the Cramer's-rule barycentrics beyond 1e-5 for every implementation, the reference's included)."""
     c = classify(x, ref, candidates)
     msg = "%s: %s" % (what, {k: v for k, v in c.items() if k != "fragile_rows"})
-    assert c["fragile_fraction"] <= MAX_FRAGILE_FRACTION, msg
+    budget = MAX_FRAGILE_FRACTION * c["n"]
+    if ref_other_isa is not None:
+        spread = classify(ref_other_isa, ref, candidates)
+        budget = max(budget, 1.25 * spread["fragile"] + 8)
+        msg += " | reference vs its other ISA: fragile %d" % spread["fragile"]
+    assert c["fragile"] <= budget, msg
     assert c["near_tie_fraction"] <= MAX_TIE_FRACTION, msg
     return c

@@ -25,7 +25,7 @@ def test_instanced_scene_matches_reference(ecb, reference, leaf):
     top.intersect(truth)
     bad = parity.bit_exact_mismatches(got, want)
     assert len(bad) == 0, "instanced CUDA vs port: %d rays differ" % len(bad)
-    c = parity.assert_reference_parity(got, truth, None, "instanced %s primary" % leaf)
+    c = parity.assert_reference_parity(got, truth, port.candidates(rays), "instanced %s primary" % leaf)
     hit = truth.view(np.uint32)[:, 18] != 0xFFFFFFFF
     assert c["hits_ref"] > 5000 and len(np.unique(got.view(np.uint32)[hit, 19])) == 25, "every instance must be hit"
     # incoherent rays + any-hit
@@ -35,7 +35,7 @@ def test_instanced_scene_matches_reference(ecb, reference, leaf):
     port.intersect(w2)
     top.intersect(t2)
     assert len(parity.bit_exact_mismatches(g2, w2)) == 0
-    parity.assert_reference_parity(g2, t2, None, "instanced %s incoherent" % leaf)
+    parity.assert_reference_parity(g2, t2, port.candidates(inc), "instanced %s incoherent" % leaf)
     o = rg.rays_only(inc)
     og, ot = o.copy(), o.copy()
     inst.occluded1M(og)
@@ -62,7 +62,12 @@ def test_config4_tile_sharded_frame(ecb, reference):
     assert len(parity.bit_exact_mismatches(full, want)) == 0
     truth = whole.copy()
     top.intersect(truth)
-    parity.assert_reference_parity(full, truth, None, "config 4 frame")
+    # the camera is ~140 units from 0.05-unit micro-triangles: u,v are ill-conditioned for every implementation, so the
+    # budget is calibrated with the reference's own SSE4.2 path on the same scene and rays
+    top_sse, objs_sse = build_instanced(reference, "grid,max_isa=sse4.2", [("bomberman", 5, 3), ("cube", 5, 3)], grid=1, spacing=30.0)
+    other = whole.copy()
+    top_sse.intersect(other)
+    parity.assert_reference_parity(full, truth, port.candidates(whole), "config 4 frame", ref_other_isa=other)
     world = 4
     records = []
     for rank in range(world):
