@@ -12,14 +12,14 @@
 #define ECB_BLOCKS_PER_SM 8    // persistent grid = SMs x this
 #endif
 #ifndef ECB_MIN_BLOCKS
-#define ECB_MIN_BLOCKS 4       // __launch_bounds__ occupancy target (caps registers per thread)
+#define ECB_MIN_BLOCKS 5       // __launch_bounds__ occupancy target (caps registers per thread at 96)
 #endif
 
 #ifndef ECB_CHUNK
-#define ECB_CHUNK 128          // ray indices a warp takes from the global queue per atomic
+#define ECB_CHUNK 32           // ray indices a warp takes from the global queue per atomic (measured: 32 < 64 < 128)
 #endif
 #ifndef ECB_REFILL_MIN
-#define ECB_REFILL_MIN 20      // a warp goes back to fetch rays when fewer lanes than this are still traversing
+#define ECB_REFILL_MIN 12      // a warp goes back to fetch rays when fewer lanes than this are still traversing
 #endif
 
 // One launch: where rays are read, where hits are written (may be the same array, may be mapped host memory).
