@@ -627,78 +627,89 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
   int sp = 0;
   travray_init(tr, org, dir, 0.f, 0.f);
 
+  // lane states: idle (no ray), busy && pending == EMPTY (traversing the top level), busy && pending != EMPTY (waiting
+  // at a block).  Block traversal is the expensive phase, so lanes WAIT at their block until at least ECB_BLOCK_MIN
+  // lanes have one (or no other work can be found) -- the other lanes keep fetching and traversing meanwhile.
+  uint32_t pending = ECB_REF_EMPTY;
   for (;;) {
-    // ---- refill idle lanes ----
-    unsigned need = __ballot_sync(0xffffffffu, !busy);
-    while (need && !exhausted) {
-      if (chunk_next == chunk_end) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(L.queue, (unsigned long long)ECB_CHUNK);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= L.M) { exhausted = true; break; }
-        chunk_next = base;
-        chunk_end = base + ECB_CHUNK < L.M ? base + ECB_CHUNK : L.M;
-      }
-      const unsigned avail = (unsigned)(chunk_end - chunk_next);
-      const unsigned n_need = __popc(need);
-      const unsigned take = avail < n_need ? avail : n_need;
-      const unsigned rank = __popc(need & lt_mask);
-      const bool mine = ((need >> lane) & 1u) && rank < take;
-      if (mine) {
-        index = chunk_next + rank;
-        const uint8_t* rp = L.in + index * L.in_stride;
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));       // org.xyz, tnear
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
-        const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
-        if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
-        if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY) {  // tnear > tfar: inactive stream ray
-          org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
-          dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
-          ray_tnear = r0.w;
-          hit.tfar = tfar_in;
-          hit.block = 0xFFFFFFFFu;
-          travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(tfar_in, 0.0f));
-          stack_ref[0] = sc.root;
-          stack_dist[0] = 0xff800000u;  // -inf
-          sp = 1;
-          busy = true;
-          if (STATS) n_rays++;
-        }
-      }
-      chunk_next += take;
-      // lanes served in this round (busy or consumed an inactive ray) leave the need mask
-      need &= ~__ballot_sync(0xffffffffu, mine);
-    }
-    if (!__any_sync(0xffffffffu, busy)) {
-      if (exhausted) break;
-      continue;
-    }
+    unsigned idle_mask = __ballot_sync(0xffffffffu, !busy);
+    const unsigned n_trav0 = __popc(__ballot_sync(0xffffffffu, busy && pending == ECB_REF_EMPTY));
+    const unsigned n_pend0 = __popc(__ballot_sync(0xffffffffu, busy && pending != ECB_REF_EMPTY));
 
-    // ---- traverse until too few lanes are busy ----
-    for (;;) {
-      uint32_t leaf = ECB_REF_EMPTY;
-      if (busy) {
-        leaf = next_block<STATS>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
-        if (leaf == ECB_REF_EMPTY) {
-          // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
-          busy = false;
-          if (hit.block != 0xFFFFFFFFu) {
-            uint8_t* op = L.out + index * L.out_stride;
-            *reinterpret_cast<float*>(op + 32) = hit.tfar;
-            *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
-            *reinterpret_cast<float4*>(op + 64) =
-                make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(L.instID));
-            if (L.block_out) L.block_out[index] = hit.block;
-            if (STATS) n_hits++;
+    // ---- refill idle lanes (when enough are idle to make the ray set-up worth a pass, or nothing else can run) ----
+    if (!exhausted && idle_mask && (__popc(idle_mask) >= ECB_REFILL_IDLE_MIN || (n_trav0 == 0 && n_pend0 < ECB_BLOCK_MIN))) {
+      unsigned need = idle_mask;
+      while (need && !exhausted) {
+        if (chunk_next == chunk_end) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(L.queue, (unsigned long long)ECB_CHUNK);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base >= L.M) { exhausted = true; break; }
+          chunk_next = base;
+          chunk_end = base + ECB_CHUNK < L.M ? base + ECB_CHUNK : L.M;
+        }
+        const unsigned avail = (unsigned)(chunk_end - chunk_next);
+        const unsigned n_need = __popc(need);
+        const unsigned take = avail < n_need ? avail : n_need;
+        const unsigned rank = __popc(need & lt_mask);
+        const bool mine = ((need >> lane) & 1u) && rank < take;
+        if (mine) {
+          index = chunk_next + rank;
+          const uint8_t* rp = L.in + index * L.in_stride;
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));       // org.xyz, tnear
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
+          const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+          if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
+          if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY) {  // tnear > tfar: inactive stream ray
+            org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
+            dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
+            ray_tnear = r0.w;
+            hit.tfar = tfar_in;
+            hit.block = 0xFFFFFFFFu;
+            travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(tfar_in, 0.0f));
+            stack_ref[0] = sc.root;
+            stack_dist[0] = 0xff800000u;  // -inf
+            sp = 1;
+            busy = true;
+            pending = ECB_REF_EMPTY;
+            if (STATS) n_rays++;
           }
         }
+        chunk_next += take;
+        // lanes served in this round (busy or consumed an inactive ray) leave the need mask
+        need &= ~__ballot_sync(0xffffffffu, mine);
       }
-      if (leaf != ECB_REF_EMPTY) {
-        block_intersect<LEAF, STATS>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+    }
+
+    // ---- top level: every traversing lane runs to its next block or terminates ----
+    if (busy && pending == ECB_REF_EMPTY) {
+      pending = next_block<STATS>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+      if (pending == ECB_REF_EMPTY) {
+        // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
+        busy = false;
+        if (hit.block != 0xFFFFFFFFu) {
+          uint8_t* op = L.out + index * L.out_stride;
+          *reinterpret_cast<float*>(op + 32) = hit.tfar;
+          *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
+          *reinterpret_cast<float4*>(op + 64) =
+              make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(L.instID));
+          if (L.block_out) L.block_out[index] = hit.block;
+          if (STATS) n_hits++;
+        }
+      }
+    }
+
+    // ---- blocks: when enough lanes wait at one, or the idle lanes cannot be given other work ----
+    const unsigned n_pend = __popc(__ballot_sync(0xffffffffu, busy && pending != ECB_REF_EMPTY));
+    const unsigned n_idle = __popc(__ballot_sync(0xffffffffu, !busy));
+    if (n_pend >= ECB_BLOCK_MIN || (n_pend > 0 && (exhausted || n_idle < ECB_REFILL_IDLE_MIN))) {
+      if (busy && pending != ECB_REF_EMPTY) {
+        block_intersect<LEAF, STATS>(sc, lut, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
         tr.tfar = hit.tfar;  // bvh_intersector1.cpp:117
+        pending = ECB_REF_EMPTY;
       }
-      const unsigned alive = __popc(__ballot_sync(0xffffffffu, busy));
-      if (alive == 0 || (alive < ECB_REFILL_MIN && !exhausted)) break;
+    } else if (n_pend == 0 && exhausted && n_idle == 32u) {
+      break;
     }
   }
   if (STATS) {

@@ -18,8 +18,11 @@
 #ifndef ECB_CHUNK
 #define ECB_CHUNK 32           // ray indices a warp takes from the global queue per atomic (measured: 32 < 64 < 128)
 #endif
-#ifndef ECB_REFILL_MIN
-#define ECB_REFILL_MIN 12      // a warp goes back to fetch rays when fewer lanes than this are still traversing
+#ifndef ECB_REFILL_IDLE_MIN
+#define ECB_REFILL_IDLE_MIN 8  // idle lanes are given new rays once at least this many are idle
+#endif
+#ifndef ECB_BLOCK_MIN
+#define ECB_BLOCK_MIN 16       // lanes wait at their block until this many have one (or no other work is left)
 #endif
 
 // One launch: where rays are read, where hits are written (may be the same array, may be mapped host memory).
