@@ -19,8 +19,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/ecb200.h"
 #include "../../include/embree3_b200/rtcore_subset.h"
@@ -67,6 +69,9 @@ struct HostApi {
   HOST_FN(RTCSceneFlags, rtcGetSceneFlags, (RTCScene))
   HOST_FN(void, rtcGetSceneBounds, (RTCScene, RTCBounds*))
   HOST_FN(int, rtcGetCompressedBVH_b200, (RTCScene, RTCCompressedBVHInfo_b200*))
+  HOST_FN(void, rtcSetGeometryInstancedScene, (RTCGeometry, RTCScene))
+  HOST_FN(void, rtcSetGeometryTransform, (RTCGeometry, unsigned, RTCFormat, const void*))
+  HOST_FN(int, rtcGetInstanceBVH_b200, (RTCScene, RTCInstanceBVHInfo_b200*, unsigned, unsigned*, float*, RTCScene*))
 #undef HOST_FN
 };
 
@@ -109,6 +114,9 @@ inline ShimScene* S(RTCScene s) { return reinterpret_cast<ShimScene*>(s); }
 // the device of a geometry is not recoverable from the host handle, so pass-through geometry calls use the last
 // device that created a geometry on this thread's process (one host library per process in practice)
 std::atomic<ShimDevice*> g_any_device{nullptr};
+// host scene handle -> wrapper, so that instances can find the device scene of the scene they refer to
+std::mutex g_scene_map_mutex;
+std::map<RTCScene, ShimScene*> g_scene_map;
 thread_local RTCError g_thread_error = RTC_ERROR_NONE;  // errors without a device (rtcore.cpp:79-98)
 
 RTCError map_error(ecbError e) {
@@ -139,9 +147,11 @@ bool load_host(HostApi& h, const std::string& path, std::string& err) {
   RESOLVE(rtcSetGeometryTopologyCount) RESOLVE(rtcSetGeometrySubdivisionMode) RESOLVE(rtcSetGeometryVertexAttributeTopology)
   RESOLVE(rtcSetGeometryDisplacementFunction) RESOLVE(rtcInterpolate) RESOLVE(rtcNewScene) RESOLVE(rtcReleaseScene)
   RESOLVE(rtcAttachGeometry) RESOLVE(rtcAttachGeometryByID) RESOLVE(rtcDetachGeometry) RESOLVE(rtcGetGeometry) RESOLVE(rtcSetSceneLevels)
+  RESOLVE(rtcSetGeometryInstancedScene) RESOLVE(rtcSetGeometryTransform)
   RESOLVE(rtcCommitScene) RESOLVE(rtcSetSceneBuildQuality) RESOLVE(rtcSetSceneFlags) RESOLVE(rtcGetSceneFlags) RESOLVE(rtcGetSceneBounds)
 #undef RESOLVE
   h.rtcGetCompressedBVH_b200 = reinterpret_cast<decltype(h.rtcGetCompressedBVH_b200)>(dlsym(h.lib, "rtcGetCompressedBVH_b200"));
+  h.rtcGetInstanceBVH_b200 = reinterpret_cast<decltype(h.rtcGetInstanceBVH_b200)>(dlsym(h.lib, "rtcGetInstanceBVH_b200"));  // optional
   if (!h.rtcGetCompressedBVH_b200) {
     err = "host embree does not export rtcGetCompressedBVH_b200 (apply the accessor of INTEGRATION.md)";
     return false;
@@ -301,6 +311,8 @@ RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry g, unsigned t, RTCSubdivi
 RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry g, unsigned a, unsigned t) { HOST().rtcSetGeometryVertexAttributeTopology(g, a, t); }
 RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry g, RTCDisplacementFunctionN f) { HOST().rtcSetGeometryDisplacementFunction(g, f); }
 RTC_API void rtcInterpolate(const RTCInterpolateArguments* args) { HOST().rtcInterpolate(args); }
+RTC_API void rtcSetGeometryInstancedScene(RTCGeometry g, RTCScene scene) { HOST().rtcSetGeometryInstancedScene(g, scene ? reinterpret_cast<ShimScene*>(scene)->hscene : nullptr); }
+RTC_API void rtcSetGeometryTransform(RTCGeometry g, unsigned t, RTCFormat f, const void* xfm) { HOST().rtcSetGeometryTransform(g, t, f, xfm); }
 
 // ---- scene ------------------------------------------------------------------------------------------------------------
 RTC_API RTCScene rtcNewScene(RTCDevice device) {
@@ -309,6 +321,10 @@ RTC_API RTCScene rtcNewScene(RTCDevice device) {
   s->dev = D(device);
   s->dev->refs++;
   s->hscene = s->dev->host.rtcNewScene(s->dev->hdev);
+  {
+    std::lock_guard<std::mutex> lock(g_scene_map_mutex);
+    g_scene_map[s->hscene] = s;
+  }
   return reinterpret_cast<RTCScene>(s);
 }
 RTC_API void rtcRetainScene(RTCScene scene) { if (scene) S(scene)->refs++; }
@@ -317,6 +333,10 @@ RTC_API void rtcReleaseScene(RTCScene scene) {
   ShimScene* s = S(scene);
   if (--s->refs == 0) {
     if (s->gpu) ecbSceneRelease(s->gpu);
+    {
+      std::lock_guard<std::mutex> lock(g_scene_map_mutex);
+      g_scene_map.erase(s->hscene);
+    }
     s->dev->host.rtcReleaseScene(s->hscene);
     rtcReleaseDevice(reinterpret_cast<RTCDevice>(s->dev));
     delete s;
@@ -341,6 +361,47 @@ RTC_API void rtcCommitScene(RTCScene scene) {
   if (s->gpu) { ecbSceneRelease(s->gpu); s->gpu = nullptr; }
   RTCCompressedBVHInfo_b200 info;
   const int rc = s->dev->host.rtcGetCompressedBVH_b200(s->hscene, &info);
+  if (rc == -2 && s->dev->host.rtcGetInstanceBVH_b200) {
+    // not a compressed accel: a scene of instances of (already committed) compressed scenes?  
+    RTCInstanceBVHInfo_b200 ii;
+    const unsigned cap = 1u << 16;
+    std::vector<unsigned> ids(cap);
+    std::vector<float> xf(12 * (size_t)cap);
+    std::vector<RTCScene> hobj(cap);
+    if (s->dev->host.rtcGetInstanceBVH_b200(s->hscene, &ii, cap, ids.data(), xf.data(), hobj.data()) == 0 && ii.n_instances <= cap) {
+      std::vector<ecbScene*> objs(ii.n_instances);
+      {
+        std::lock_guard<std::mutex> map_lock(g_scene_map_mutex);
+        for (unsigned i = 0; i < ii.n_instances; i++) {
+          auto it = g_scene_map.find(hobj[i]);
+          objs[i] = (it != g_scene_map.end()) ? it->second->gpu : nullptr;
+        }
+      }
+      for (unsigned i = 0; i < ii.n_instances; i++)
+        if (!objs[i]) {
+          s->dev->raise(RTC_ERROR_INVALID_OPERATION, "instanced scene must be committed (on the B200 path) before the scene that instances it");
+          return;
+        }
+      ecbInstanceDesc d;
+      memset(&d, 0, sizeof(d));
+      d.root = ii.root;
+      d.n_instances = ii.n_instances;
+      d.geomIDs = ids.data();
+      d.world2local = xf.data();
+      d.objects = objs.data();
+      memcpy(d.bounds, ii.bounds, sizeof(d.bounds));
+      ecbScene* g = nullptr;
+      ecbError e = ecbSceneImportInstances(&d, &g);
+      if (e == ECB_SUCCESS) e = ecbSceneUpload(g, -1);
+      if (e != ECB_SUCCESS) {
+        if (g) ecbSceneRelease(g);
+        s->dev->raise(map_error(e), std::string("rtcCommitScene (instances): ") + ecbErrorString(e) + " " + ecbLastErrorMessage());
+        return;
+      }
+      s->gpu = g;
+      return;
+    }
+  }
   if (rc != 0 || info.n_accels != 1) {
     s->dev->raise(RTC_ERROR_INVALID_OPERATION,
                   rc == -1 ? "device config must select subdiv_accel=bvh4.compressed.{grid,leaf,box}"

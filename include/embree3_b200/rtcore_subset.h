@@ -104,6 +104,8 @@ RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry geometry, unsigned int to
 RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry geometry, unsigned int vertexAttributeID, unsigned int topologyID);
 RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry geometry, RTCDisplacementFunctionN displacement);
 RTC_API void rtcInterpolate(const struct RTCInterpolateArguments* args);
+RTC_API void rtcSetGeometryInstancedScene(RTCGeometry geometry, RTCScene scene);
+RTC_API void rtcSetGeometryTransform(RTCGeometry geometry, unsigned int timeStep, enum RTCFormat format, const void* xfm);
 /* scene (rtcore_scene.h) */
 RTC_API RTCScene rtcNewScene(RTCDevice device);
 RTC_API void rtcRetainScene(RTCScene scene);
@@ -136,6 +138,9 @@ RTC_API void rtcOccluded1M(RTCScene scene, struct RTCIntersectContext* context, 
  * for the test build of the reference). */
 struct RTCCompressedBVHInfo_b200 { uint64_t root; uint32_t leaf_kind, subdiv_level, comp_level, proj_col_major, n_accels; float bounds[6]; };
 typedef int (*rtcGetCompressedBVH_b200_t)(RTCScene host_scene, struct RTCCompressedBVHInfo_b200* info);
+struct RTCInstanceBVHInfo_b200 { uint64_t root; uint32_t n_instances; uint32_t reserved; float bounds[6]; };
+typedef int (*rtcGetInstanceBVH_b200_t)(RTCScene host_scene, struct RTCInstanceBVHInfo_b200* info, unsigned cap, unsigned* geomIDs,
+                                        float* world2local12, RTCScene* objects);
 /* Pinned host memory for ray arrays (fast DMA path of rtcIntersect1M / rtcOccluded1M); plain malloc memory also works. */
 RTC_API void* rtcAllocRays_b200(size_t bytes);
 RTC_API void rtcFreeRays_b200(void* ptr);

@@ -515,3 +515,17 @@ REF_API int ref_scene_instance_info(RefScene* s, uint64_t* root_out, unsigned ca
   }
   return (int)n;
 }
+
+// instancing scenes: second accessor of INTEGRATION.md (instance-level BVH4 root + per-instance data)
+struct RTCInstanceBVHInfo_b200 { uint64_t root; uint32_t n_instances; uint32_t reserved; float bounds[6]; };
+REF_API int rtcGetInstanceBVH_b200(RTCScene hscene, RTCInstanceBVHInfo_b200* info, unsigned cap, unsigned* geomIDs, float* world2local12,
+                                   RTCScene* objects) {
+  RefScene tmp;
+  tmp.scene = hscene;
+  memset(info, 0, sizeof(*info));
+  const int n = ref_scene_instance_info(&tmp, &info->root, cap, geomIDs, world2local12, (void**)objects);
+  if (n < 0) return n;
+  info->n_instances = (uint32_t)n;
+  ref_scene_bounds(&tmp, info->bounds);
+  return 0;
+}

@@ -2,7 +2,7 @@
 // (declarations from include/embree3_b200/rtcore_subset.h, which restate the reference's headers) and is linked
 // against libembree3_b200.so instead of libembree3.so.
 //
-//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin>
+//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin> [instanced]
 // builds the displaced cube of tutorials/displacement_geometry through rtc* calls (subdivision mesh + displacement
 // callback), commits, and traces the RTCRayHit records of rays.bin four ways, writing one result block per way:
 //   [0] rtcIntersect1M   [1] rtcIntersect16 packets   [2] rtcIntersect1 per ray (first 64 rays)   [3] rtcOccluded1M
@@ -41,7 +41,7 @@ static void on_error(void*, RTCError code, const char* str) { fprintf(stderr, "R
 
 int main(int argc, char** argv) {
   if (argc < 6) { fprintf(stderr, "usage: shim_demo leaf S C rays.bin out.bin\n"); return 2; }
-  const std::string cfg = std::string("subdiv_accel=bvh4.compressed.") + argv[1] + ",set_affinity=0,start_threads=0";
+  const std::string cfg = std::string("subdiv_accel=bvh4.compressed.") + argv[1] + ",object_accel=bvh4.object,set_affinity=0,start_threads=0";
   RTCDevice device = rtcNewDevice(cfg.c_str());
   if (!device) { fprintf(stderr, "rtcNewDevice failed (%d)\n", (int)rtcGetDeviceError(nullptr)); return 3; }
   rtcSetDeviceErrorFunction(device, on_error, nullptr);
@@ -60,6 +60,23 @@ int main(int argc, char** argv) {
   rtcReleaseGeometry(geom);
   rtcCommitScene(scene);
   if (RTCError e = rtcGetDeviceError(device)) { fprintf(stderr, "commit failed: %d\n", (int)e); return 4; }
+  RTCScene object_scene = nullptr;
+  if (argc > 6 && std::string(argv[6]) == "instanced") {
+    // two instances of the cube scene (tutorials/instanced_geometry style): the object scene stays alive, the queries go to the top scene
+    object_scene = scene;
+    scene = rtcNewScene(device);
+    const float xfm[2][12] = {{1, 0, 0, 0, 1, 0, 0, 0, 1, -1.6f, 0, 0}, {0.5f, 0, 0, 0, 0.5f, 0, 0, 0, 0.5f, 1.4f, 0.3f, 0}};
+    for (int i = 0; i < 2; i++) {
+      RTCGeometry inst = rtcNewGeometry(device, RTC_GEOMETRY_TYPE_INSTANCE);
+      rtcSetGeometryInstancedScene(inst, object_scene);
+      rtcSetGeometryTransform(inst, 0, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, xfm[i]);
+      rtcCommitGeometry(inst);
+      rtcAttachGeometry(scene, inst);
+      rtcReleaseGeometry(inst);
+    }
+    rtcCommitScene(scene);
+    if (RTCError e = rtcGetDeviceError(device)) { fprintf(stderr, "instanced commit failed: %d\n", (int)e); return 4; }
+  }
 
   FILE* f = fopen(argv[4], "rb");
   if (!f) return 5;
@@ -117,6 +134,7 @@ int main(int argc, char** argv) {
   fclose(out);
   const RTCError e = rtcGetDeviceError(device);
   rtcReleaseScene(scene);
+  if (object_scene) rtcReleaseScene(object_scene);
   rtcReleaseDevice(device);
   if (e) { fprintf(stderr, "device error %d\n", (int)e); return 6; }
   printf("shim_demo ok: %zu rays\n", n);

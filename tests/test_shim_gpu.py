@@ -52,3 +52,29 @@ def test_unmodified_embree3_application_runs_on_the_shim(ecb, reference, ref_sce
     ref.occluded(o_truth)
     assert (occ[:, 12:] == 7.0).all()
     assert (occ[:, :12].view(np.uint32) == o_truth.view(np.uint32)).all()
+
+
+def test_instanced_scene_through_the_shim(ecb, reference, tmp_path):
+    """rtcSetGeometryInstancedScene / rtcSetGeometryTransform on the shim: two instances of the displaced cube."""
+    cam = dict(vp=(1.0, 2.5, -4.5), vi=(0.0, 0.0, 0.0), vu=(0.0, 1.0, 0.0), fov=70.0)
+    rays = rg.primary_rays(160, 128, **cam)
+    n = len(rays)
+    rays_path, out_path = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rays_path)
+    env = dict(os.environ, ECB200_HOST_EMBREE=reference.REF_SO)
+    r = subprocess.run([DEMO, "leaf", "5", "3", rays_path, out_path, "instanced"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    stream = np.fromfile(out_path, np.float32)[: n * 20].reshape(n, 20)
+    obj = reference.RefScene("leaf", 5, 3)
+    obj.add_cube(1, 1.0)
+    obj.commit()
+    top = reference.RefScene("leaf", 5, 3)
+    top.add_instance(obj, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, -1.6, 0, 0], np.float32))
+    top.add_instance(obj, np.array([0.5, 0, 0, 0, 0.5, 0, 0, 0, 0.5, 1.4, 0.3, 0], np.float32))
+    top.commit()
+    truth = rays.copy()
+    top.intersect(truth)
+    port = reference.PortInstancedScene(top, [obj])
+    c = parity.assert_reference_parity(stream, truth, port.candidates(rays), "shim instanced")
+    hit = truth.view(np.uint32)[:, 18] != 0xFFFFFFFF
+    assert c["hits_ref"] > 500 and set(np.unique(stream.view(np.uint32)[hit, 19])) == {0, 1}
