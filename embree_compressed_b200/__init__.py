@@ -65,6 +65,8 @@ SYMBOLS = {
     "ecbIntersect16": (C.c_int, [_vp, _vp, _u32, _vp]),
     "ecbOccluded1": (C.c_int, [_vp, _u32, _vp]),
     "ecbOccluded1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
+    "ecbOccludedExact1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
+    "ecbOccludedExactDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
     "ecbIntersectDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
     "ecbIntersectDeviceEx": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
     "ecbIntersectDeviceStats": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
@@ -230,6 +232,11 @@ class Scene:
     def occluded1M(self, rays, inst_id=INVALID_GEOMETRY_ID):
         p, n, stride = self._host_args(rays, 12)
         _check(_lib().ecbOccluded1M(self._h, inst_id, p, n, stride), "ecbOccluded1M")
+
+    def occluded_exact1M(self, rays, inst_id=INVALID_GEOMETRY_ID):
+        """Opt-in exact shadow query (not the reference's conservative any-hit): enters the blocks."""
+        p, n, stride = self._host_args(rays, 12)
+        _check(_lib().ecbOccludedExact1M(self._h, inst_id, p, n, stride), "ecbOccludedExact1M")
 
     def intersect1(self, rayhit, inst_id=INVALID_GEOMETRY_ID):
         _check(_lib().ecbIntersect1(self._h, inst_id, rayhit.ctypes.data), "ecbIntersect1")

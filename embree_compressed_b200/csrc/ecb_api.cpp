@@ -191,8 +191,12 @@ int host_path_mode() {  // 0 copy, 1 zero-copy results + contiguous H2D, 2 zero-
 bool use_zero_copy() { return host_path_mode() != 0; }
 
 // Shared by intersect (elem = 80) and occluded (elem = 48).
-ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride) {
+ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact = false) {
   if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
+  if (exact && s->instanced) {
+    g_last_error = "exact any-hit is not available on instancing scenes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
   const size_t elem = occluded ? kRayBytes : kRayHitBytes;
   if (stride < elem || (stride & 3)) {
     g_last_error = "byteStride must be a multiple of 4 and at least the struct size";
@@ -224,11 +228,13 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     L.out_stride = out_stride;
     L.M = n;
     L.instID = instID;
+    L.any_hit_exact = exact ? 1u : 0u;
     L.block_out = nullptr;
     L.counters = nullptr;
     L.queue = next_queue(s);
     g_launches.fetch_add(1);
     if (s->instanced) return ecb_launch_instanced(s->inst_dev, s->device, L, occluded, st->stream[k]);
+    if (exact) return ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
     return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
   };
 
@@ -303,7 +309,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
 }
 
 ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, uint64_t M, size_t stride, uint32_t* d_block_out,
-                    void* stream, unsigned long long* d_counters = nullptr) {
+                    void* stream, unsigned long long* d_counters = nullptr, bool exact = false) {
   if (!s || (!d_rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
   const size_t elem = occluded ? kRayBytes : kRayHitBytes;
   if (stride < elem || (stride & 15) || (reinterpret_cast<uintptr_t>(d_rays) & 15)) {
@@ -321,6 +327,7 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
   L.out_stride = stride;
   L.M = M;
   L.instID = instID;
+  L.any_hit_exact = exact ? 1u : 0u;
   L.block_out = d_block_out;
   L.counters = d_counters;
   L.queue = next_queue(s);
@@ -328,7 +335,12 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
     g_last_error = "block output / work counters are not available on instancing scenes";
     return ECB_ERROR_INVALID_OPERATION;
   }
+  if (exact && s->instanced) {
+    g_last_error = "exact any-hit is not available on instancing scenes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
   cudaError_t le = s->instanced ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
+                   : exact      ? ecb_launch_intersect(s->dev, s->device, L, q)
                    : occluded   ? ecb_launch_occluded(s->dev, s->device, L, q)
                                 : ecb_launch_intersect(s->dev, s->device, L, q);
   if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
@@ -516,6 +528,13 @@ ecbError ecbIntersect1M(ecbScene* s, uint32_t instID, void* rayhit, uint32_t M, 
 ecbError ecbOccluded1(ecbScene* s, uint32_t instID, void* ray) { return run_host(s, true, instID, ray, 1, kRayBytes); }
 ecbError ecbOccluded1M(ecbScene* s, uint32_t instID, void* ray, uint32_t M, size_t byteStride) {
   return run_host(s, true, instID, ray, M, byteStride);
+}
+
+ecbError ecbOccludedExact1M(ecbScene* s, uint32_t instID, void* ray, uint32_t M, size_t byteStride) {
+  return run_host(s, true, instID, ray, M, byteStride, true);
+}
+ecbError ecbOccludedExactDevice(ecbScene* s, uint32_t instID, void* d_ray, uint64_t M, size_t byteStride, void* stream) {
+  return run_device(s, true, instID, d_ray, M, byteStride, nullptr, stream, nullptr, true);
 }
 
 // RTCRayHit16 (include/embree3/rtcore_ray.h:149-187) is the SoA transpose of 16 RTCRayHit: 20 arrays of 16 words.

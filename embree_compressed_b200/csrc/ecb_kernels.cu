@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
           const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
-          if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY) {  // tnear > tfar: inactive stream ray
+          if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
             org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
             dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
             ray_tnear = r0.w;
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
       if (pending == ECB_REF_EMPTY) {
         // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
         busy = false;
-        if (hit.block != 0xFFFFFFFFu) {
+        if (hit.block != 0xFFFFFFFFu && !L.any_hit_exact) {
           uint8_t* op = L.out + index * L.out_stride;
           *reinterpret_cast<float*>(op + 32) = hit.tfar;
           *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
@@ -707,6 +707,13 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         block_intersect<LEAF, STATS>(sc, lut, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
         tr.tfar = hit.tfar;  // bvh_intersector1.cpp:117
         pending = ECB_REF_EMPTY;
+        if (L.any_hit_exact && hit.block != 0xFFFFFFFFu) {
+          // opt-in exact shadow query (NOT the reference's behaviour, which stops at the block's bounding box): any
+          // accepted leaf hit inside [tnear, tfar] occludes
+          *reinterpret_cast<float*>(L.out + index * L.out_stride + 32) = __int_as_float(0xff800000);
+          busy = false;
+          if (STATS) n_hits++;
+        }
       }
     } else if (n_pend == 0 && exhausted && n_idle == 32u) {
       break;

@@ -33,6 +33,7 @@ struct EcbLaunch {
   size_t out_stride;
   uint64_t M;
   uint32_t instID;
+  uint32_t any_hit_exact;         // 1: shadow-ray mode (first accepted leaf hit terminates the ray, only tfar = -inf is written)
   uint32_t* block_out;            // optional: index of the block of the final hit per ray
   unsigned long long* counters;   // optional: instrumented variant (6 counters)
   unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)

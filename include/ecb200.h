@@ -120,6 +120,12 @@ ECB_API ecbError ecbIntersect16(const int* valid, ecbScene* scene, uint32_t inst
 ECB_API ecbError ecbOccluded1(ecbScene* scene, uint32_t instID, void* ray);
 ECB_API ecbError ecbOccluded1M(ecbScene* scene, uint32_t instID, void* ray, uint32_t M, size_t byteStride);
 
+/* Opt-in EXACT shadow query (NOT the reference's semantics): the ray is occluded iff the closest-hit
+ * traversal would accept a leaf hit inside [tnear, tfar] -- the blocks are entered instead of stopping at their world
+ * boxes.  Same RTCRay records, tfar = -inf when occluded.  Not available on instancing scenes. */
+ECB_API ecbError ecbOccludedExact1M(ecbScene* scene, uint32_t instID, void* ray, uint32_t M, size_t byteStride);
+ECB_API ecbError ecbOccludedExactDevice(ecbScene* scene, uint32_t instID, void* d_ray, uint64_t M, size_t byteStride, void* stream);
+
 /* ---- traversal, device-resident buffers (extension; what the benchmark's `value` times) ------------
  * d_rayhit / d_ray are device pointers on the scene's device; stream is a cudaStream_t (NULL = default stream).
  * Asynchronous: returns after the launch. */

@@ -138,3 +138,32 @@ def test_config5_full_64M_rays_determinism(ecb, reference, ref_scene):
         got = dev[lo:hi].cpu().numpy()[pick]
         assert (got.view(np.uint32) == want.view(np.uint32)).all()
     scene.release()
+
+
+@pytest.mark.parametrize("leaf", ["leaf", "grid", "box"])
+def test_exact_shadow_query_opt_in(ecb, reference, ref_scene, leaf):
+    """SURVEY 8f-4: the opt-in exact any-hit.  It is NOT parity (the reference answers `occluded` from block boxes);
+    it must agree with the closest-hit kernel: occluded <=> a closest hit exists inside [tnear, tfar]."""
+    ref = ref_scene("bomberman", leaf, 6, 3)
+    scene, port = _pair(ecb, reference, ref)
+    prim = rg.primary_rays(480, 270, **rg.BOMBERMAN_CAMERA)
+    first = prim.copy()
+    scene.intersect1M(first)
+    shadow = rg.shadow_rays(first, light_center=(40.0, 60.0, 25.0), light_radius=4.0)
+    exact = shadow.copy()
+    scene.occluded_exact1M(exact)
+    as_hits = rg.new_rayhits(len(shadow))
+    as_hits[:, :12] = shadow
+    closest = as_hits.copy()
+    scene.intersect1M(closest)
+    active = shadow[:, 3] <= shadow[:, 8]
+    want = (closest.view(np.uint32)[:, 18] != 0xFFFFFFFF) & active
+    got = exact[:, 8] < 0
+    assert (got == want).all()
+    assert (exact[~got].view(np.uint32) == shadow[~got].view(np.uint32)).all()
+    conservative = shadow.copy()
+    scene.occluded1M(conservative)
+    cons = conservative[:, 8] < 0
+    assert (got <= cons).all(), "exact occlusion must imply box-level occlusion"
+    assert 0 < got.sum() < cons.sum()
+    scene.release()
