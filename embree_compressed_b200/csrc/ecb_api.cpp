@@ -21,8 +21,8 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
-constexpr int kStages = 3;
-constexpr size_t kChunkRays = 1u << 18;  // 256 Ki rays per pipeline stage
+constexpr int kStages = 4;
+constexpr size_t kChunkRaysMax = 1u << 18;  // capacity of a staging buffer: 256 Ki rays
 constexpr uint32_t kQueueRing = 256;
 
 ecbError cuda_fail(cudaError_t e, const char* what) {
@@ -154,7 +154,7 @@ ecbError ensure_staging(ecbScene* s) {
   st->device = s->device;
   for (int i = 0; i < kStages; i++) {
     cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRays * kRayHitBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRaysMax * kRayHitBytes);
     if (e != cudaSuccess) {
       delete st;
       return cuda_fail(e, "staging allocation");
@@ -179,6 +179,18 @@ bool is_pinned(const void* p) {
 //   zerocopy      : contiguous H2D DMA, kernel writes tfar + hit of the rays that hit straight into the caller's array
 //                   through its mapped device address (no D2H copy)                     -> 363 Mrays/s (small PCIe writes)
 //   zerocopy2d    : as above with a 2-D H2D copy of the 48-byte RTCRay part only        ->  35 Mrays/s (row-sized DMAs)
+// rays per pipeline stage of the host-buffer entry points (ECB200_HOST_CHUNK overrides for experiments)
+size_t pipeline_chunk() {
+  static const size_t n = [] {
+    const char* e = getenv("ECB200_HOST_CHUNK");
+    size_t v = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(1u << 16);
+    if (v < 1024) v = 1024;
+    if (v > kChunkRaysMax) v = kChunkRaysMax;
+    return v;
+  }();
+  return n;
+}
+
 int host_path_mode() {  // 0 copy, 1 zero-copy results + contiguous H2D, 2 zero-copy results + 48-byte 2-D H2D
   static const int mode = [] {
     const char* e = getenv("ECB200_HOST_PATH");
@@ -211,7 +223,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   if (err != ECB_SUCCESS) return err;
   Staging* st = s->staging;
   uint8_t* base = static_cast<uint8_t*>(rays);
-  const size_t chunk = kChunkRays;
+  const size_t chunk = pipeline_chunk();
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
 
   void* mapped = nullptr;
@@ -263,7 +275,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
 
   if (!pinned) {
     for (int i = 0; i < kStages; i++)
-      if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRays * kRayHitBytes));
+      if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRaysMax * kRayHitBytes));
   }
   auto unpack = [&](uint64_t c, int k) {  // bounce buffer -> caller's array
     const uint64_t first = c * chunk;

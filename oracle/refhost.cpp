@@ -21,6 +21,7 @@
 #include "kernels/geometry/grid_soa.h"
 #include "kernels/geometry/compressed.h"
 #include "kernels/geometry/object.h"
+#include "kernels/geometry/trianglev.h"
 #include "kernels/common/scene_instance.h"
 
 #include <atomic>
@@ -55,7 +56,9 @@ RTCDevice get_device(const std::string& leaf, int threads) {
   std::string accel = leaf.compare(0, 5, "eager") == 0 ? "bvh4.grid." + leaf : "bvh4.compressed." + leaf;
   // set_affinity=0: with the internal tasking system the default pins the calling thread (kernels/common/state.cpp:123-128)
   // object_accel=bvh4.object: instances go into a BVH4 (the default on AVX hardware is a BVH8, kernels/common/scene.cpp:531-555)
-  std::string cfg = "subdiv_accel=" + accel + ",object_accel=bvh4.object,set_affinity=0,start_threads=0";
+  // tri_accel=bvh4.triangle4v: triangle meshes of a ROBUST scene go into a BVH4 of Triangle4v blocks with the Pluecker
+  // intersector (the default on AVX hardware is the BVH8 flavour of the same thing, kernels/common/scene.cpp:158-164)
+  std::string cfg = "subdiv_accel=" + accel + ",object_accel=bvh4.object,tri_accel=bvh4.triangle4v,set_affinity=0,start_threads=0";
   if (threads > 0) cfg += ",threads=" + std::to_string(threads);
   auto it = g_devices.find(cfg);
   if (it != g_devices.end()) return it->second;
@@ -528,4 +531,30 @@ REF_API int rtcGetInstanceBVH_b200(RTCScene hscene, RTCInstanceBVHInfo_b200* inf
   info->n_instances = (uint32_t)n;
   ref_scene_bounds(&tmp, info->bounds);
   return 0;
+}
+
+// mixed scenes: root of the BVH4 over Triangle4v blocks, and the position of both accels in the AccelN list
+REF_API uint64_t ref_scene_triangle_root(RefScene* s, int* tri_index, int* subdiv_index, unsigned* sizeof_block) {
+  using namespace embree;
+  if (tri_index) *tri_index = -1;
+  if (subdiv_index) *subdiv_index = -1;
+  if (sizeof_block) *sizeof_block = (unsigned)sizeof(Triangle4v);
+  AccelData* accel = ((Accel*)s->scene)->intersectors.ptr;
+  uint64_t root = 0;
+  if (accel && accel->type == AccelData::TY_BVH4) {
+    BVH4* bvh = (BVH4*)accel;
+    if (bvh->primTy == &Triangle4v::type) { root = (uint64_t)(size_t)bvh->root; if (tri_index) *tri_index = 0; }
+    return root;
+  }
+  if (accel && accel->type == AccelData::TY_ACCELN) {
+    AccelN* an = (AccelN*)accel;
+    for (size_t i = 0; i < an->accels.size(); i++) {
+      AccelData* a = an->accels[i]->intersectors.ptr;
+      if (!a || a->type != AccelData::TY_BVH4) continue;
+      BVH4* bvh = (BVH4*)a;
+      if (bvh->primTy == &Triangle4v::type) { root = (uint64_t)(size_t)bvh->root; if (tri_index) *tri_index = (int)i; }
+      if (bvh->primTy == &SubdivPatch1Cached::type && subdiv_index) *subdiv_index = (int)i;
+    }
+  }
+  return root;
 }

@@ -73,6 +73,10 @@ size_t ref_scene_dump_image(RefScene*, void* buf, size_t cap);
  * world2local (vx,vy,vz,p = 12 floats) and the RTCScene it instances.  Returns the number of instances, <0 if none. */
 int ref_scene_instance_info(RefScene*, uint64_t* root_out, unsigned cap, unsigned* geomIDs, float* world2local12, void** object_scenes);
 
+/* Mixed scenes: root of the BVH4 over Triangle4v blocks (0 if none); positions of the triangle and the compressed accel
+ * in the scene's AccelN list (the order rtcIntersect1 visits them, kernels/common/acceln.cpp:51-56). */
+uint64_t ref_scene_triangle_root(RefScene*, int* tri_index, int* subdiv_index, unsigned* sizeof_block);
+
 int ref_hardware_threads(void);
 
 #ifdef __cplusplus
