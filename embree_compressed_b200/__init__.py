@@ -40,6 +40,10 @@ class InstanceDesc(C.Structure):
                 ("geomIDs", C.c_void_p), ("world2local", C.c_void_p), ("objects", C.c_void_p), ("bounds", C.c_float * 6)]
 
 
+class TriangleDesc(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("leaf_kind", C.c_uint32), ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32),
                 ("n_top_nodes", C.c_uint32), ("n_blocks", C.c_uint32), ("top_depth", C.c_uint32),
@@ -53,6 +57,7 @@ _vp, _u32, _u64, _sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
 SYMBOLS = {
     "ecbSceneImportBVH4": (C.c_int, [C.POINTER(ImportDesc), C.POINTER(_vp)]),
     "ecbSceneImportInstances": (C.c_int, [C.POINTER(InstanceDesc), C.POINTER(_vp)]),
+    "ecbSceneAttachTriangles4v": (C.c_int, [_vp, C.POINTER(TriangleDesc)]),
     "ecbSceneImportImage": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "ecbSceneImportImageFile": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "ecbSceneSave": (C.c_int, [_vp, C.c_char_p]),
@@ -160,6 +165,14 @@ class Scene:
         h = _vp()
         _check(_lib().ecbSceneImportInstances(C.byref(d), C.byref(h)), "ecbSceneImportInstances")
         return cls(h.value, keepalive=list(objects))
+
+    def attach_triangles4v(self, root, base=0):
+        """ecbSceneAttachTriangles4v: the scene's BVH4 over Triangle4v blocks (mixed scenes; before upload)."""
+        d = TriangleDesc()
+        d.base = base
+        d.root = root
+        _check(_lib().ecbSceneAttachTriangles4v(self._h, C.byref(d)), "ecbSceneAttachTriangles4v")
+        return self
 
     @classmethod
     def from_image(cls, image):

@@ -138,6 +138,22 @@ ecbError ensure_resident(ecbScene* s, int device) {
   d.elems = s->elems;
   d.grid_width = s->grid_width;
   d.rcp_edges = s->rcp_edges;
+  s->tri_dev = EcbDeviceTriScene{nullptr, nullptr, ECB_REF_EMPTY, 0u, 0u};
+  if (s->has_triangles()) {  // mixed scene: triangle accel next to the compressed one
+    if (!s->tri_top.empty()) {
+      CU(cudaMalloc(&s->d_tri_top, s->tri_top.size() * sizeof(EcbTopNode)));
+      CU(cudaMemcpy(s->d_tri_top, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode), cudaMemcpyHostToDevice));
+    }
+    if (!s->tri_blocks.empty()) {
+      CU(cudaMalloc(&s->d_tri_blocks, s->tri_blocks.size() * sizeof(EcbTriBlock)));
+      CU(cudaMemcpy(s->d_tri_blocks, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock), cudaMemcpyHostToDevice));
+    }
+    s->tri_dev.nodes = static_cast<const EcbTopNode*>(s->d_tri_top);
+    s->tri_dev.blocks = static_cast<const EcbTriBlock*>(s->d_tri_blocks);
+    s->tri_dev.root = s->tri_root;
+    s->tri_dev.n_nodes = (uint32_t)s->tri_top.size();
+    s->tri_dev.n_blocks = (uint32_t)s->tri_blocks.size();
+  }
   CU(cudaMalloc(reinterpret_cast<void**>(&s->d_queues), kQueueRing * sizeof(unsigned long long)));
   CU(cudaMemset(s->d_queues, 0, kQueueRing * sizeof(unsigned long long)));
   s->device = device;
@@ -228,7 +244,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
 
   void* mapped = nullptr;
   const bool pinned = is_pinned(rays);
-  const bool zero_copy = pinned && use_zero_copy() && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(rays) & 15) == 0) &&
+  const bool zero_copy = pinned && use_zero_copy() && !s->has_triangles() && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(rays) & 15) == 0) &&
                          (stride % 16 == 0) && cudaHostGetDevicePointer(&mapped, rays, 0) == cudaSuccess && mapped;
   if (!zero_copy) cudaGetLastError();
 
@@ -246,6 +262,11 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     L.queue = next_queue(s);
     g_launches.fetch_add(1);
     if (s->instanced) return ecb_launch_instanced(s->inst_dev, s->device, L, occluded, st->stream[k]);
+    if (s->has_triangles()) {  // AccelN order: triangle accel first, in place, then the compressed accel on the same rays
+      cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, st->stream[k]);
+      if (te != cudaSuccess) return te;
+      g_launches.fetch_add(1);
+    }
     if (exact) return ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
     return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
   };
@@ -351,6 +372,11 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
     g_last_error = "exact any-hit is not available on instancing scenes";
     return ECB_ERROR_INVALID_OPERATION;
   }
+  if (!s->instanced && s->has_triangles()) {
+    cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, q);
+    if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
+    g_launches.fetch_add(1);
+  }
   cudaError_t le = s->instanced ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
                    : exact      ? ecb_launch_intersect(s->dev, s->device, L, q)
                    : occluded   ? ecb_launch_occluded(s->dev, s->device, L, q)
@@ -367,6 +393,8 @@ extern "C" {
 
 ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out) { return ecb_import_bvh4(desc, scene_out); }
 ecbError ecbSceneImportInstances(const ecbInstanceDesc* desc, ecbScene** scene_out) { return ecb_import_instances(desc, scene_out); }
+
+ecbError ecbSceneAttachTriangles4v(ecbScene* scene, const ecbTriangleDesc* desc) { return ecb_import_triangles(desc, scene); }
 
 ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out) {
   // header of oracle/rimg.h restated as offsets (plain data: magic[8], 8 x u32, root u64, total u64, bounds[6])
@@ -393,7 +421,20 @@ ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_o
   d.comp_level = w[3];
   d.proj_col_major = w[4];
   memcpy(d.bounds, p + 56, 24);
-  return ecb_import_bvh4(&d, scene_out);
+  ecbError e = ecb_import_bvh4(&d, scene_out);
+  uint64_t tri_root;
+  memcpy(&tri_root, p + 80, 8);  // mixed scene: the triangle accel travels in the same image
+  if (e == ECB_SUCCESS && tri_root) {
+    ecbTriangleDesc t;
+    t.base = image;
+    t.root = tri_root;
+    e = ecb_import_triangles(&t, *scene_out);
+    if (e != ECB_SUCCESS) {
+      ecbSceneRelease(*scene_out);
+      *scene_out = nullptr;
+    }
+  }
+  return e;
 }
 
 ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out) {
@@ -443,6 +484,18 @@ ecbError ecbSceneSave(const ecbScene* s, const char* path) {
   f.write(reinterpret_cast<const char*>(&h), sizeof(h));
   f.write(reinterpret_cast<const char*>(s->top.data()), (std::streamsize)h.top_bytes);
   f.write(reinterpret_cast<const char*>(s->blocks.data()), (std::streamsize)h.block_bytes);
+  if (s->has_triangles()) {
+    EcbBlobTriTrailer t;
+    memset(&t, 0, sizeof(t));
+    memcpy(t.magic, "ECB200T1", 8);
+    t.n_nodes = (uint32_t)s->tri_top.size();
+    t.n_blocks = (uint32_t)s->tri_blocks.size();
+    t.root = s->tri_root;
+    t.depth = s->tri_depth;
+    f.write(reinterpret_cast<const char*>(&t), sizeof(t));
+    f.write(reinterpret_cast<const char*>(s->tri_top.data()), (std::streamsize)(s->tri_top.size() * sizeof(EcbTopNode)));
+    f.write(reinterpret_cast<const char*>(s->tri_blocks.data()), (std::streamsize)(s->tri_blocks.size() * sizeof(EcbTriBlock)));
+  }
   return f ? ECB_SUCCESS : ECB_ERROR_UNKNOWN;
 }
 
@@ -501,6 +554,36 @@ ecbError ecbSceneLoad(const char* path, ecbScene** out) {
   in.micro_triangles = 2ull * (1ull << (2 * h.comp_level)) * h.n_blocks;
   memcpy(in.bounds, h.bounds, sizeof(in.bounds));
   in.device = -1;
+  EcbBlobTriTrailer t;
+  if (f.read(reinterpret_cast<char*>(&t), sizeof(t))) {  // optional: triangle accel of a mixed scene
+    bool ok = memcmp(t.magic, "ECB200T1", 8) == 0 && 3 * t.depth + 4 <= ECB_MAX_TOP_STACK && t.n_blocks < (1u << 27);
+    if (ok) {
+      s->tri_top.resize(t.n_nodes);
+      s->tri_blocks.resize(t.n_blocks);
+      f.read(reinterpret_cast<char*>(s->tri_top.data()), (std::streamsize)(t.n_nodes * sizeof(EcbTopNode)));
+      f.read(reinterpret_cast<char*>(s->tri_blocks.data()), (std::streamsize)(t.n_blocks * sizeof(EcbTriBlock)));
+      ok = (bool)f;
+    }
+    auto ref_ok = [&](uint32_t c) {
+      if (c == ECB_REF_EMPTY) return true;
+      if (!(c & ECB_REF_LEAF)) return c < t.n_nodes;
+      const uint32_t first = (c & ~ECB_REF_LEAF) >> 3, num = c & 7u;
+      return (uint64_t)first + num <= t.n_blocks;
+    };
+    if (ok) {
+      ok = ref_ok(t.root) && t.root != ECB_REF_EMPTY;
+      for (const EcbTopNode& n : s->tri_top)
+        for (int i = 0; i < 4; i++) ok = ok && ref_ok(n.child[i]);
+    }
+    if (!ok) {
+      delete s;
+      g_last_error = "corrupt triangle section in scene blob";
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+    s->tri_root = t.root;
+    s->tri_depth = t.depth;
+    in.device_bytes += t.n_nodes * sizeof(EcbTopNode) + (uint64_t)t.n_blocks * sizeof(EcbTriBlock);
+  }
   *out = s;
   return ECB_SUCCESS;
 }
@@ -529,6 +612,8 @@ void ecbSceneRelease(ecbScene* s) {
     if (s->d_items) cudaFree(s->d_items);
     if (s->d_instances) cudaFree(s->d_instances);
     if (s->d_objects) cudaFree(s->d_objects);
+    if (s->d_tri_top) cudaFree(s->d_tri_top);
+    if (s->d_tri_blocks) cudaFree(s->d_tri_blocks);
   }
   delete s;
 }

@@ -73,6 +73,24 @@ struct EcbDeviceInstScene {
   uint32_t n_nodes, n_items, n_instances, n_objects;
 };
 
+// ---- triangle meshes of a mixed scene: the host's BVH4 over Triangle4v blocks ----
+// Nodes reuse EcbTopNode; a leaf ref is ECB_REF_LEAF | first_block << 3 | count (count <= 7 blocks per leaf,
+// kernels/bvh/bvh.h:140,380-384).  A block is the reference's TriangleMv<4> verbatim (kernels/geometry/trianglev.h):
+// already pointer-free, SoA and a multiple of 16 bytes.
+struct EcbTriBlock {
+  float v0[3][4], v1[3][4], v2[3][4];  // x[4], y[4], z[4] of each vertex
+  uint32_t geomID[4];                  // 0xFFFFFFFF = unused lane (its vertices are zero)
+  uint32_t primID[4];
+};
+static_assert(sizeof(EcbTriBlock) == 176, "triangle block is 11 x 16 bytes");
+
+struct EcbDeviceTriScene {
+  const EcbTopNode* nodes;
+  const EcbTriBlock* blocks;
+  uint32_t root;  // ECB_REF_EMPTY: the scene has no triangle accel
+  uint32_t n_nodes, n_blocks;
+};
+
 // native blob header (ecbSceneSave / ecbSceneLoad)
 struct EcbBlobHeader {
   char magic[8];  // "ECB200S1"
@@ -84,4 +102,9 @@ struct EcbBlobHeader {
   uint32_t reserved;
   uint64_t reference_bytes;
   uint64_t top_bytes, block_bytes;
+};
+// optional trailer of a blob: the triangle accel of a mixed scene (nodes, then blocks)
+struct EcbBlobTriTrailer {
+  char magic[8];  // "ECB200T1"
+  uint32_t n_nodes, n_blocks, root, depth;
 };

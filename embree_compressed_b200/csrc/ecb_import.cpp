@@ -231,8 +231,8 @@ ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
   imp.geom_to_instance.assign((size_t)max_geom + 1, 0xFFFFFFFFu);
   for (uint32_t i = 0; i < desc->n_instances; i++) {
     ecbScene* obj = desc->objects[i];
-    if (!obj || obj->instanced) {
-      ecb_set_error("instance " + std::to_string(i) + " does not refer to an imported (non-instanced) scene");
+    if (!obj || obj->instanced || obj->has_triangles()) {
+      ecb_set_error("instance " + std::to_string(i) + " does not refer to an imported compressed-only (non-instanced, no triangle accel) scene");
       delete s;
       return ECB_ERROR_INVALID_ARGUMENT;
     }
@@ -274,5 +274,73 @@ ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
   memcpy(in.bounds, desc->bounds, sizeof(in.bounds));
   in.device = -1;
   *out = s;
+  return ECB_SUCCESS;
+}
+
+// ---- mixed scenes: BVH4 over Triangle4v blocks (kernels/geometry/trianglev.h) ----
+namespace {
+constexpr size_t kTri_Size = 176;
+struct TriImporter {
+  ecbScene& s;
+  const uint8_t* base;
+  uint32_t max_depth = 0;
+  std::string err;
+  TriImporter(const ecbTriangleDesc& desc, ecbScene& scene) : s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+
+  uint32_t import_ref(uint64_t ref, uint32_t depth) {
+    if (!err.empty() || ref == kEmpty) return ECB_REF_EMPTY;
+    if (ref & kTyLeaf) {
+      const uint32_t num = (uint32_t)((ref & kAlignMask) - kTyLeaf);
+      const uint32_t first = (uint32_t)s.tri_blocks.size();
+      if (first >= (1u << 27)) { err = "too many triangle blocks"; return ECB_REF_EMPTY; }
+      const uint8_t* blocks = base + (ref & ~kAlignMask);
+      for (uint32_t i = 0; i < num; i++) {
+        EcbTriBlock b;
+        memcpy(&b, blocks + kTri_Size * i, kTri_Size);
+        s.tri_blocks.push_back(b);
+      }
+      if (depth > max_depth) max_depth = depth;
+      return ECB_REF_LEAF | (first << 3) | num;
+    }
+    if ((ref & kAlignMask) != 0) { err = "triangle BVH node is not an AlignedNode (use tri_accel=bvh4.triangle4v)"; return ECB_REF_EMPTY; }
+    if (depth > 512) { err = "triangle BVH deeper than 512"; return ECB_REF_EMPTY; }
+    const uint8_t* n = base + (ref & ~kAlignMask);
+    const uint32_t index = (uint32_t)s.tri_top.size();
+    s.tri_top.emplace_back();
+    EcbTopNode node;
+    memcpy(node.bounds, n + kAN_Bounds, 96);
+    for (int i = 0; i < 4; i++) node.child[i] = import_ref(rd<uint64_t>(n + kAN_Children + 8 * i), depth + 1);
+    s.tri_top[index] = node;
+    return index;
+  }
+};
+}  // namespace
+
+ecbError ecb_import_triangles(const ecbTriangleDesc* desc, ecbScene* s) {
+  if (!desc || !s || !desc->root) return ECB_ERROR_INVALID_ARGUMENT;
+  if (s->instanced || s->device >= 0 || s->has_triangles() || s->refs.load() > 1) {
+    ecb_set_error("triangles attach to a freshly imported, non-instancing scene that is not yet resident or instanced");
+    return ECB_ERROR_INVALID_OPERATION;
+  }
+  TriImporter imp(*desc, *s);
+  uint32_t root;
+  try {
+    root = imp.import_ref(desc->root, 0);
+  } catch (const std::bad_alloc&) {
+    s->tri_top.clear();
+    s->tri_blocks.clear();
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+  if (imp.err.empty() && 3 * imp.max_depth + 4 > ECB_MAX_TOP_STACK) imp.err = "triangle BVH too deep for the traversal stack";
+  if (!imp.err.empty()) {
+    ecb_set_error(imp.err);
+    s->tri_top.clear();
+    s->tri_blocks.clear();
+    return ECB_ERROR_UNSUPPORTED;
+  }
+  s->tri_root = root;
+  s->tri_depth = imp.max_depth;
+  s->info.device_bytes += s->tri_top.size() * sizeof(EcbTopNode) + s->tri_blocks.size() * sizeof(EcbTriBlock);
+  s->info.reference_bytes += s->tri_top.size() * kAN_Size + s->tri_blocks.size() * kTri_Size;
   return ECB_SUCCESS;
 }

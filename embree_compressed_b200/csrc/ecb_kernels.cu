@@ -463,9 +463,9 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
 // ---------------------------------------------------------------------------------------------------------------
 // The near / far plane of each axis is picked by ADDRESS (like the reference's nearX/farX byte offsets,
 // node_intersector1.h:126-131): six 16-byte read-only loads deliver near and far planes of all four children.
-__device__ __forceinline__ unsigned top_node(const EcbDeviceScene& sc, uint32_t index, const TravRay& tr, float tNear[4],
+__device__ __forceinline__ unsigned top_node(const EcbTopNode* __restrict__ nodes, uint32_t index, const TravRay& tr, float tNear[4],
                                              uint32_t child[4]) {
-  const float4* p = reinterpret_cast<const float4*>(sc.top + index);
+  const float4* p = reinterpret_cast<const float4*>(nodes + index);
   const float4 nx = __ldg(p + tr.nu[0]), fx = __ldg(p + (1 - tr.nu[0]));
   const float4 ny = __ldg(p + 2 + tr.nu[1]), fy = __ldg(p + (3 - tr.nu[1]));
   const float4 nz = __ldg(p + 4 + tr.nu[2]), fz = __ldg(p + (5 - tr.nu[2]));
@@ -502,7 +502,7 @@ __device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, 
 // (returns ECB_REF_EMPTY).  Resumable: the caller keeps stack and sp between calls (one call per block entered).
 // Restates the pop loop + down loop of bvh_intersector1.cpp:73-105 with traverseClosestHit (bvh_traverser1.h:436-506).
 template <bool STATS>
-__device__ __forceinline__ uint32_t next_block(const EcbDeviceScene& sc, const TravRay& tr, uint32_t* stack_ref, uint32_t* stack_dist,
+__device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ nodes, const TravRay& tr, uint32_t* stack_ref, uint32_t* stack_dist,
                                                int& sp, float ray_tfar, Work& work) {
   while (sp > 0) {
     sp--;
@@ -513,7 +513,7 @@ __device__ __forceinline__ uint32_t next_block(const EcbDeviceScene& sc, const T
       if (STATS) work.top_nodes++;
       float tNear[4];
       uint32_t child[4];
-      const unsigned mask = top_node(sc, cur, tr, tNear, child);
+      const unsigned mask = top_node(nodes, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
       uint32_t c[4], d[4];
       int nh = 0;
@@ -571,7 +571,7 @@ __device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float 
     while (!(cur & ECB_REF_LEAF)) {
       float tNear[4];
       uint32_t child[4];
-      const unsigned mask = top_node(sc, cur, tr, tNear, child);
+      const unsigned mask = top_node(sc.top, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
       int last = -1;
 #pragma unroll
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
 
     // ---- top level: every traversing lane runs to its next block or terminates ----
     if (busy && pending == ECB_REF_EMPTY) {
-      pending = next_block<STATS>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+      pending = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
       if (pending == ECB_REF_EMPTY) {
         // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
         busy = false;
@@ -797,7 +797,7 @@ __device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float*
   stack_dist[0] = 0xff800000u;
   int sp = 1;
   for (;;) {
-    const uint32_t leaf = next_block<false>(sc, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+    const uint32_t leaf = next_block<false>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
     if (leaf == ECB_REF_EMPTY) break;
     block_intersect<LEAF, false>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
     tr.tfar = hit.tfar;
@@ -932,6 +932,199 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// mixed scenes: the triangle accel AccelN visits before the compressed accel.
+// BVHNIntersector1<4,BVH_AN1,true,ArrayIntersector1<TriangleMvIntersector1Pluecker<4,4,true>>> (bvh_intersector1_bvh4.cpp:44):
+// the same robust traversal, leaves = arrays of Triangle4v blocks, PlueckerIntersector1<4>::intersect
+// (triangle_intersector_pluecker.h:77-127) + Intersect1EpilogM / Occluded1EpilogM (intersector_epilog.h:227-306).
+// The reference runs the AVX (non-FMA) build of this intersector (bvh4_factory.cpp:408): madd/msub are separate
+// multiply and add -- which is what -fmad=false compiles the expressions below to.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float min_ps(float a, float b) { return a < b ? a : b; }  // _mm_min_ps operand order
+__device__ __forceinline__ float max_ps(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+__device__ __forceinline__ void cross3(const float a[3], const float b[3], float r[3]) {
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+struct TriHit {
+  float t, u, v, ng[3];
+  uint32_t primID, geomID;
+};
+
+// One Triangle4v block against one ray; returns whether a lane survived (and, for closest hit, the selected lane in `out`).
+template <bool ANYHIT>
+__device__ __forceinline__ bool tri4v_intersect(const EcbTriBlock* __restrict__ blk, const float O[3], const float D[3], float ray_tnear,
+                                                float ray_tfar, TriHit& out) {
+  const float4* q = reinterpret_cast<const float4*>(blk);
+  float P[9][4];  // v0.x[4], v0.y[4], v0.z[4], v1..., v2...
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    const float4 w = __ldg(q + r);
+    P[r][0] = w.x; P[r][1] = w.y; P[r][2] = w.z; P[r][3] = w.w;
+  }
+  float U[4], V[4], W[4], T[4], den[4], Ng[4][3];
+  unsigned valid = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float v0[3], v1[3], v2[3], e0[3], e1[3], e2[3], s[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      v0[k] = P[k][i] - O[k];
+      v1[k] = P[3 + k][i] - O[k];
+      v2[k] = P[6 + k][i] - O[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e0[k] = v2[k] - v0[k]; e1[k] = v0[k] - v1[k]; e2[k] = v1[k] - v2[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] = v2[k] + v0[k];
+    cross3(e0, s, c); U[i] = dot3(c, D);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] = v0[k] + v1[k];
+    cross3(e1, s, c); V[i] = dot3(c, D);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] = v1[k] + v2[k];
+    cross3(e2, s, c); W[i] = dot3(c, D);
+    const float minUVW = min_ps(min_ps(U[i], V[i]), W[i]);
+    const float maxUVW = max_ps(max_ps(U[i], V[i]), W[i]);
+    if (minUVW >= 0.0f || maxUVW <= 0.0f) valid |= 1u << i;
+    // stable_triangle_normal(e0,e1,e2) (common/math/vec3.h:200-212)
+    const float ab_x = e0[2] * e1[1], ab_y = e0[0] * e1[2], ab_z = e0[1] * e1[0];
+    const float bc_x = e1[2] * e2[1], bc_y = e1[0] * e2[2], bc_z = e1[1] * e2[0];
+    const float cab0 = e0[1] * e1[2] - ab_x, cab1 = e0[2] * e1[0] - ab_y, cab2 = e0[0] * e1[1] - ab_z;
+    const float cbc0 = e1[1] * e2[2] - bc_x, cbc1 = e1[2] * e2[0] - bc_y, cbc2 = e1[0] * e2[1] - bc_z;
+    Ng[i][0] = fabsf(ab_x) < fabsf(bc_x) ? cab0 : cbc0;
+    Ng[i][1] = fabsf(ab_y) < fabsf(bc_y) ? cab1 : cbc1;
+    Ng[i][2] = fabsf(ab_z) < fabsf(bc_z) ? cab2 : cbc2;
+    const float dn = dot3(Ng[i], D);
+    den[i] = dn + dn;
+    const float tt = dot3(v0, Ng[i]);
+    T[i] = tt + tt;
+  }
+  if (!valid) return false;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float absDen = fabsf(den[i]);
+    const float Ts = __uint_as_float(__float_as_uint(T[i]) ^ (__float_as_uint(den[i]) & 0x80000000u));
+    const bool keep = (absDen * ray_tnear < Ts) && (Ts <= absDen * ray_tfar) && (den[i] != 0.0f);
+    if (!keep) valid &= ~(1u << i);
+  }
+  if (!valid) return false;
+  if constexpr (ANYHIT) {
+    return true;
+  } else {
+    float vt[4], a[4], h[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      vt[i] = T[i] * (1.0f / den[i]);
+      a[i] = (valid & (1u << i)) ? vt[i] : __int_as_float(0x7f800000);
+    }
+    // select_min (common/simd/vfloat4_sse2.h:654-659)
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = min_ps(a[i ^ 1], a[i]);
+    unsigned vmin = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float m = min_ps(h[i ^ 2], h[i]);
+      if ((valid & (1u << i)) && a[i] == m) vmin |= 1u << i;
+    }
+    const int i = __ffs(vmin ? vmin : valid) - 1;
+    float Us = U[0], Vs = V[0], Ws = W[0];
+    out.t = vt[0]; out.ng[0] = Ng[0][0]; out.ng[1] = Ng[0][1]; out.ng[2] = Ng[0][2];
+#pragma unroll
+    for (int k = 1; k < 4; k++)
+      if (i == k) {
+        Us = U[k]; Vs = V[k]; Ws = W[k];
+        out.t = vt[k]; out.ng[0] = Ng[k][0]; out.ng[1] = Ng[k][1]; out.ng[2] = Ng[k][2];
+      }
+    const float UVW = (Us + Vs) + Ws;
+    const float rcpUVW = fabsf(UVW) < 1E-18f ? 0.0f : 1.0f / UVW;
+    out.u = Us * rcpUVW;
+    out.v = Vs * rcpUVW;
+    const uint32_t* ids = reinterpret_cast<const uint32_t*>(q + 9);
+    out.geomID = __ldg(ids + i);
+    out.primID = __ldg(ids + 4 + i);
+    return true;
+  }
+}
+
+template <bool ANYHIT>
+__global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriScene ts, EcbLaunch L) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* rp = L.in + i * L.in_stride;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+    if (r0.w > tfar_in) continue;               // inactive stream ray
+    if (ANYHIT && tfar_in < 0.0f) continue;     // bvh_intersector1.cpp:133
+    const float org[3] = {r0.x, r0.y, r0.z};
+    const float dir[3] = {r1.x, r1.y, r1.z};
+    TravRay tr;
+    travray_init(tr, org, dir, sse_max_exact(r0.w, 0.0f), sse_max_exact(tfar_in, 0.0f));
+    uint32_t stack_ref[ECB_MAX_TOP_STACK];
+    uint32_t stack_dist[ECB_MAX_TOP_STACK];
+    int sp = 1;
+    stack_ref[0] = ts.root;
+    stack_dist[0] = 0xff800000u;
+    uint8_t* op = L.out + i * L.out_stride;
+    if (ANYHIT) {
+      bool occluded = false;
+      while (sp > 0 && !occluded) {
+        sp--;
+        uint32_t cur = stack_ref[sp];
+        bool popped = false;
+        while (!(cur & ECB_REF_LEAF)) {
+          float tNear[4];
+          uint32_t child[4];
+          const unsigned mask = top_node(ts.nodes, cur, tr, tNear, child);
+          if (mask == 0) { popped = true; break; }
+          int last = -1;
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+            if (mask & (1u << r)) {
+              if (last >= 0) stack_ref[sp++] = child[last];
+              last = r;
+            }
+          cur = child[last];
+        }
+        if (popped || cur == ECB_REF_EMPTY) continue;
+        const uint32_t first = (cur & ~ECB_REF_LEAF) >> 3, num = cur & 7u;
+        TriHit th;
+        for (uint32_t k = 0; k < num && !occluded; k++)
+          occluded = tri4v_intersect<true>(ts.blocks + first + k, org, dir, r0.w, tfar_in, th);
+      }
+      if (occluded) *reinterpret_cast<float*>(op + 32) = __int_as_float(0xff800000);
+    } else {
+      Work work = {0u, 0u, 0u, 0u};
+      float tfar = tfar_in;
+      TriHit best;
+      bool found = false;
+      for (;;) {
+        const uint32_t leaf = next_block<false>(ts.nodes, tr, stack_ref, stack_dist, sp, tfar, work);
+        if (leaf == ECB_REF_EMPTY) break;
+        const uint32_t first = (leaf & ~ECB_REF_LEAF) >> 3, num = leaf & 7u;
+        for (uint32_t k = 0; k < num; k++) {
+          TriHit th;
+          if (tri4v_intersect<false>(ts.blocks + first + k, org, dir, r0.w, tfar, th)) {
+            best = th;
+            tfar = th.t;
+            found = true;
+          }
+        }
+        tr.tfar = tfar;  // bvh_intersector1.cpp:117
+      }
+      if (found) {
+        *reinterpret_cast<float*>(op + 32) = best.t;
+        *reinterpret_cast<float4*>(op + 48) = make_float4(best.ng[0], best.ng[1], best.ng[2], best.u);
+        *reinterpret_cast<float4*>(op + 64) =
+            make_float4(best.v, __uint_as_float(best.primID), __uint_as_float(best.geomID), __uint_as_float(L.instID));
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
@@ -997,5 +1190,13 @@ cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const
   const int grid = grid_for(L.M, device);
   if (any_hit) ecb_instanced_kernel<true><<<grid, ECB_THREADS, 0, stream>>>(is, L);
   else ecb_instanced_kernel<false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  return cudaGetLastError();
+}
+
+cudaError_t ecb_launch_triangles(const EcbDeviceTriScene& ts, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream) {
+  if (L.M == 0 || ts.root == ECB_REF_EMPTY) return cudaSuccess;
+  const int grid = grid_for(L.M, device);
+  if (any_hit) ecb_triangle_kernel<true><<<grid, ECB_THREADS, 0, stream>>>(ts, L);
+  else ecb_triangle_kernel<false><<<grid, ECB_THREADS, 0, stream>>>(ts, L);
   return cudaGetLastError();
 }

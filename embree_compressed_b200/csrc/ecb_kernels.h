@@ -42,3 +42,5 @@ struct EcbLaunch {
 cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
 cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
 cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);
+// mixed scenes: the triangle accel is traversed first, in place (L.in == L.out), then the compressed accel on the same rays
+cudaError_t ecb_launch_triangles(const EcbDeviceTriScene& ts, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);

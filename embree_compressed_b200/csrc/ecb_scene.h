@@ -25,6 +25,16 @@ struct ecbScene {
   void* d_blocks = nullptr;
   EcbDeviceScene dev{};
 
+  // mixed scenes: the triangle accel that AccelN visits before the compressed accel
+  std::vector<EcbTopNode> tri_top;
+  std::vector<EcbTriBlock> tri_blocks;
+  uint32_t tri_root = ECB_REF_EMPTY;
+  uint32_t tri_depth = 0;
+  void* d_tri_top = nullptr;
+  void* d_tri_blocks = nullptr;
+  EcbDeviceTriScene tri_dev{};
+  bool has_triangles() const { return tri_root != ECB_REF_EMPTY; }
+
   // instanced scenes: instance-level BVH4 (in `top`), Object items, instance records, retained object scenes
   bool instanced = false;
   std::vector<uint32_t> items;
@@ -47,3 +57,4 @@ struct ecbScene {
 void ecb_set_error(const std::string& msg);
 ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out);
 ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out);
+ecbError ecb_import_triangles(const ecbTriangleDesc* desc, ecbScene* scene);

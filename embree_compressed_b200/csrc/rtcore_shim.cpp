@@ -72,6 +72,7 @@ struct HostApi {
   HOST_FN(void, rtcSetGeometryInstancedScene, (RTCGeometry, RTCScene))
   HOST_FN(void, rtcSetGeometryTransform, (RTCGeometry, unsigned, RTCFormat, const void*))
   HOST_FN(int, rtcGetInstanceBVH_b200, (RTCScene, RTCInstanceBVHInfo_b200*, unsigned, unsigned*, float*, RTCScene*))
+  HOST_FN(int, rtcGetTriangleBVH_b200, (RTCScene, uint64_t*))
 #undef HOST_FN
 };
 
@@ -152,6 +153,7 @@ bool load_host(HostApi& h, const std::string& path, std::string& err) {
 #undef RESOLVE
   h.rtcGetCompressedBVH_b200 = reinterpret_cast<decltype(h.rtcGetCompressedBVH_b200)>(dlsym(h.lib, "rtcGetCompressedBVH_b200"));
   h.rtcGetInstanceBVH_b200 = reinterpret_cast<decltype(h.rtcGetInstanceBVH_b200)>(dlsym(h.lib, "rtcGetInstanceBVH_b200"));  // optional
+  h.rtcGetTriangleBVH_b200 = reinterpret_cast<decltype(h.rtcGetTriangleBVH_b200)>(dlsym(h.lib, "rtcGetTriangleBVH_b200"));  // optional
   if (!h.rtcGetCompressedBVH_b200) {
     err = "host embree does not export rtcGetCompressedBVH_b200 (apply the accessor of INTEGRATION.md)";
     return false;
@@ -402,10 +404,16 @@ RTC_API void rtcCommitScene(RTCScene scene) {
       return;
     }
   }
-  if (rc != 0 || info.n_accels != 1) {
+  // mixed scenes: a triangle accel (BVH4<Triangle4v>, tri_accel=bvh4.triangle4v) next to the compressed one
+  uint64_t tri_root = 0;
+  if (rc == 0 && info.n_accels == 2 && s->dev->host.rtcGetTriangleBVH_b200 &&
+      s->dev->host.rtcGetTriangleBVH_b200(s->hscene, &tri_root) != 0)
+    tri_root = 0;
+  if (rc != 0 || !(info.n_accels == 1 || (info.n_accels == 2 && tri_root))) {
     s->dev->raise(RTC_ERROR_INVALID_OPERATION,
                   rc == -1 ? "device config must select subdiv_accel=bvh4.compressed.{grid,leaf,box}"
-                           : "scene is not a single compressed subdivision accel (other geometry types are outside the B200 hot path)");
+                           : "scene is not a compressed subdivision accel, optionally with triangle meshes in a BVH4<Triangle4v> "
+                             "(tri_accel=bvh4.triangle4v); other geometry types are outside the B200 hot path");
     return;
   }
   ecbImportDesc d;
@@ -419,6 +427,12 @@ RTC_API void rtcCommitScene(RTCScene scene) {
   memcpy(d.bounds, info.bounds, sizeof(d.bounds));
   ecbScene* g = nullptr;
   ecbError e = ecbSceneImportBVH4(&d, &g);
+  if (e == ECB_SUCCESS && tri_root) {
+    ecbTriangleDesc t;
+    t.base = nullptr;
+    t.root = tri_root;
+    e = ecbSceneAttachTriangles4v(g, &t);
+  }
   if (e == ECB_SUCCESS) e = ecbSceneUpload(g, -1);
   if (e != ECB_SUCCESS) {
     if (g) ecbSceneRelease(g);

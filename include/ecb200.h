@@ -92,12 +92,26 @@ typedef struct ecbInstanceDesc {
   float bounds[6];
 } ecbInstanceDesc;
 
+/* Triangle meshes in the same scene (SURVEY 8f-1, config 1's ground plane): what the host hands over for the accel
+ * that AccelN::intersect visits BEFORE the compressed accel (kernels/common/acceln.cpp:51-56, creation order
+ * kernels/common/scene.cpp:650-654). */
+typedef struct ecbTriangleDesc {
+  const void* base;  /* as in ecbImportDesc */
+  uint64_t root;     /* BVH4::root of the accel created by BVH4Factory::BVH4Triangle4v (kernels/bvh/bvh4_factory.cpp:1368-1394):
+                        AlignedNodes, leaves = arrays of TriangleMv<4> blocks (kernels/geometry/trianglev.h, 176 bytes) */
+} ecbTriangleDesc;
+
 /* ---- scene ---------------------------------------------------------------------------------------- */
 /* Converts the reference's committed compressed BVH4 into the device scene format (host work only). */
 ECB_API ecbError ecbSceneImportBVH4(const ecbImportDesc* desc, ecbScene** scene_out);
 /* Builds the device structure of an instancing scene; ray queries on it restate FastInstanceIntersectorN::intersect1 /
  * occluded1 (kernels/geometry/instance_intersector.cpp:45-83) over the non-robust BVH4 traversal of the instance level. */
 ECB_API ecbError ecbSceneImportInstances(const ecbInstanceDesc* desc, ecbScene** scene_out);
+/* Attaches the scene's triangle accel to an imported (not yet uploaded, non-instancing) scene.  Ray queries then
+ * restate AccelN::intersect / occluded: BVHNIntersector1<4,BVH_AN1,true,ArrayIntersector1<TriangleMvIntersector1Pluecker<4,4,true>>>
+ * (kernels/bvh/bvh_intersector1_bvh4.cpp:44, kernels/geometry/triangle_intersector_pluecker.h:77-127) first, the
+ * compressed accel second, on the same ray.  Triangle hits carry the real geometry normal in Ng. */
+ECB_API ecbError ecbSceneAttachTriangles4v(ecbScene* scene, const ecbTriangleDesc* desc);
 /* Convenience: import from an RIMG file / buffer (header carries root, leaf kind, S, C, bounds). */
 ECB_API ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_out);
 ECB_API ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out);

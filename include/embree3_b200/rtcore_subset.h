@@ -141,6 +141,8 @@ typedef int (*rtcGetCompressedBVH_b200_t)(RTCScene host_scene, struct RTCCompres
 struct RTCInstanceBVHInfo_b200 { uint64_t root; uint32_t n_instances; uint32_t reserved; float bounds[6]; };
 typedef int (*rtcGetInstanceBVH_b200_t)(RTCScene host_scene, struct RTCInstanceBVHInfo_b200* info, unsigned cap, unsigned* geomIDs,
                                         float* world2local12, RTCScene* objects);
+/* optional third accessor: root of the BVH4<Triangle4v> that AccelN visits before the compressed accel (0 if none) */
+typedef int (*rtcGetTriangleBVH_b200_t)(RTCScene host_scene, uint64_t* root);
 /* Pinned host memory for ray arrays (fast DMA path of rtcIntersect1M / rtcOccluded1M); plain malloc memory also works. */
 RTC_API void* rtcAllocRays_b200(size_t bytes);
 RTC_API void rtcFreeRays_b200(void* ptr);

@@ -509,6 +509,116 @@ static void block_intersect(const cbvh_scene* s, const uint8_t* blk, cbvh_rayhit
   }
 }
 
+
+/* ---- triangle meshes in the same scene -------------------------------------------------------------
+ * A ROBUST scene puts its triangle meshes into a BVH4 over Triangle4v blocks (kernels/common/scene.cpp:158-164 with
+ * tri_accel=bvh4.triangle4v; kernels/geometry/trianglev.h: v0,v1,v2 as Vec3vf4 SoA + geomIDs + primIDs = 176 bytes),
+ * leaves = arrays of `num` blocks (NodeRef::leaf, kernels/bvh/bvh.h:380-384).  Traversal is the same robust
+ * BVHNIntersector1<4,BVH_AN1,true,...> as above; the leaf test is PlueckerIntersector1<4>
+ * (kernels/geometry/triangle_intersector_pluecker.h:77-127) with Intersect1EpilogM<4,4,true> / Occluded1EpilogM
+ * (kernels/geometry/intersector_epilog.h:227-306).  That intersector exists for SSE4.2 / AVX / AVX512SKX only
+ * (bvh4_factory.cpp:408), so an AVX2 host runs the AVX build: madd/msub are a separate multiply and add/subtract
+ * (common/math/math.h), i.e. no fused operations anywhere below. */
+#define TRI_BLOCK_BYTES 176
+#define TRI_V0 0
+#define TRI_V1 48
+#define TRI_V2 96
+#define TRI_GEOMIDS 144
+#define TRI_PRIMIDS 160
+
+static inline void cross3(const float a[3], const float b[3], float r[3]) { /* common/math/vec3.h:198, msub(a,b,c) = a*b-c */
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline float dot3(const float a[3], const float b[3]) { /* vec3.h:193, madd(a.x,b.x,madd(a.y,b.y,a.z*b.z)) */
+  return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);
+}
+static inline void stable_triangle_normal(const float a[3], const float b[3], const float c[3], float n[3]) { /* vec3.h:200-212 */
+  const float ab_x = a[2] * b[1], ab_y = a[0] * b[2], ab_z = a[1] * b[0];
+  const float bc_x = b[2] * c[1], bc_y = b[0] * c[2], bc_z = b[1] * c[0];
+  const float cab[3] = {a[1] * b[2] - ab_x, a[2] * b[0] - ab_y, a[0] * b[1] - ab_z};
+  const float cbc[3] = {b[1] * c[2] - bc_x, b[2] * c[0] - bc_y, b[0] * c[1] - bc_z};
+  n[0] = fabsf(ab_x) < fabsf(bc_x) ? cab[0] : cbc[0];
+  n[1] = fabsf(ab_y) < fabsf(bc_y) ? cab[1] : cbc[1];
+  n[2] = fabsf(ab_z) < fabsf(bc_z) ? cab[2] : cbc[2];
+}
+
+/* One Triangle4v block against one ray.  any_hit: Occluded1EpilogM (returns 1 as soon as a lane survives).
+ * col != NULL: candidate collection (ray not updated). */
+static int tri4v_intersect(const uint8_t* blk, cbvh_rayhit* rh, uint32_t instID, int any_hit, collector* col) {
+  const float O[3] = {rh->ray.org_x, rh->ray.org_y, rh->ray.org_z};
+  const float D[3] = {rh->ray.dir_x, rh->ray.dir_y, rh->ray.dir_z};
+  float U[4], V[4], W[4], T[4], den[4], Ng[4][3];
+  unsigned valid = 0;
+  for (int i = 0; i < 4; i++) {
+    float v0[3], v1[3], v2[3], e0[3], e1[3], e2[3], s[3], c[3];
+    for (int k = 0; k < 3; k++) {
+      v0[k] = ldf(blk + TRI_V0 + 16 * k + 4 * i) - O[k];
+      v1[k] = ldf(blk + TRI_V1 + 16 * k + 4 * i) - O[k];
+      v2[k] = ldf(blk + TRI_V2 + 16 * k + 4 * i) - O[k];
+    }
+    for (int k = 0; k < 3; k++) { e0[k] = v2[k] - v0[k]; e1[k] = v0[k] - v1[k]; e2[k] = v1[k] - v2[k]; }
+    for (int k = 0; k < 3; k++) s[k] = v2[k] + v0[k];
+    cross3(e0, s, c); U[i] = dot3(c, D);
+    for (int k = 0; k < 3; k++) s[k] = v0[k] + v1[k];
+    cross3(e1, s, c); V[i] = dot3(c, D);
+    for (int k = 0; k < 3; k++) s[k] = v1[k] + v2[k];
+    cross3(e2, s, c); W[i] = dot3(c, D);
+    const float minUVW = sse_min(sse_min(U[i], V[i]), W[i]);
+    const float maxUVW = sse_max(sse_max(U[i], V[i]), W[i]);
+    if (minUVW >= 0.0f || maxUVW <= 0.0f) valid |= 1u << i; /* no backface culling (kernels/config.h) */
+    stable_triangle_normal(e0, e1, e2, Ng[i]);
+    den[i] = dot3(Ng[i], D);
+    den[i] = den[i] + den[i]; /* twice() */
+    T[i] = dot3(v0, Ng[i]);
+    T[i] = T[i] + T[i];
+  }
+  if (!valid) return 0;
+  for (int i = 0; i < 4; i++) {
+    const float absDen = fabsf(den[i]);
+    const float Ts = bitsf(fbits(T[i]) ^ (fbits(den[i]) & 0x80000000u));
+    if (!(absDen * rh->ray.tnear < Ts)) valid &= ~(1u << i);
+    if (!(Ts <= absDen * rh->ray.tfar)) valid &= ~(1u << i);
+    if (!(den[i] != 0.0f)) valid &= ~(1u << i);
+  }
+  if (!valid) return 0;
+  if (any_hit) return 1; /* Occluded1EpilogM without filter functions / ray masks */
+  /* PlueckerHitM::finalize (rcp = rcpps + one Newton step in the reference; IEEE division here) */
+  float vt[4], vu[4], vv[4];
+  for (int i = 0; i < 4; i++) {
+    const float rcpDen = 1.0f / den[i];
+    vt[i] = T[i] * rcpDen;
+    const float UVW = (U[i] + V[i]) + W[i];
+    const float rcpUVW = fabsf(UVW) < 1E-18f ? 0.0f : 1.0f / UVW;
+    vu[i] = U[i] * rcpUVW;
+    vv[i] = V[i] * rcpUVW;
+  }
+  if (col) {
+    for (int i = 0; i < 4; i++)
+      if (valid & (1u << i)) collect(col, vt[i], ldu(blk + TRI_PRIMIDS + 4 * i));
+    return 1;
+  }
+  /* select_min(valid, vt) (common/simd/vfloat4_sse2.h:654-659): lowest lane holding the minimum */
+  float a[4], h[4], m[4];
+  for (int i = 0; i < 4; i++) a[i] = (valid & (1u << i)) ? vt[i] : INFINITY;
+  for (int i = 0; i < 4; i++) h[i] = sse_min(a[i ^ 1], a[i]);
+  for (int i = 0; i < 4; i++) m[i] = sse_min(h[i ^ 2], h[i]);
+  unsigned vmin = 0;
+  for (int i = 0; i < 4; i++)
+    if ((valid & (1u << i)) && a[i] == m[i]) vmin |= 1u << i;
+  const unsigned pick = vmin ? vmin : valid;
+  int i = 0;
+  while (!(pick & (1u << i))) i++;
+  rh->ray.tfar = vt[i];
+  rh->hit.Ng_x = Ng[i][0]; rh->hit.Ng_y = Ng[i][1]; rh->hit.Ng_z = Ng[i][2];
+  rh->hit.u = vu[i]; rh->hit.v = vv[i];
+  rh->hit.primID = ldu(blk + TRI_PRIMIDS + 4 * i);
+  rh->hit.geomID = ldu(blk + TRI_GEOMIDS + 4 * i);
+  rh->hit.instID = instID;
+  return 1;
+}
+
 /* ---- top level: BVHNIntersector1<4,BVH_AN1,robust,...>::intersect (bvh_intersector1.cpp:40-126) ---- */
 typedef struct stack_item { uint64_t ref; uint32_t dist; } stack_item;
 static inline void xchg(stack_item* a, stack_item* b) { stack_item t = *a; *a = *b; *b = t; }
@@ -517,10 +627,12 @@ static void load_aligned_node(const uint8_t* p, node4* n) {
   memcpy(n->b, p + AN_LOWER_X, 96); /* lower_x, upper_x, lower_y, upper_y, lower_z, upper_z */
 }
 
-static void top_intersect(const cbvh_scene* s, cbvh_rayhit* rh, uint32_t instID, cbvh_stats* st, collector* col) {
+/* tri != 0: the same traversal over the scene's Triangle4v BVH4 (leaves = arrays of blocks) */
+static void top_intersect_ex(const cbvh_scene* s, cbvh_rayhit* rh, uint32_t instID, cbvh_stats* st, collector* col, int tri) {
   stack_item stack[256];
   int sp = 1;
-  stack[0].ref = s->root;
+  stack[0].ref = tri ? s->tri_root : s->root;
+  if (stack[0].ref == 0) return; /* no such accel in this scene */
   stack[0].dist = 0xff800000u; /* neg_inf */
   const float org[3] = {rh->ray.org_x, rh->ray.org_y, rh->ray.org_z};
   const float dir[3] = {rh->ray.dir_x, rh->ray.dir_y, rh->ray.dir_z};
@@ -580,10 +692,23 @@ static void top_intersect(const cbvh_scene* s, cbvh_rayhit* rh, uint32_t instID,
     }
     /* leaf: one CompressedBVH block per leaf (encodeTypedLeaf(cbvh,1), bvh_builder_subdiv.cpp:727-728) */
     if (cur == REF_TY_LEAF) continue; /* emptyNode */
-    block_intersect(s, s->base + (cur & ~REF_ALIGN_MASK), rh, instID, st, col);
+    if (tri) { /* ArrayIntersector1 (kernels/geometry/intersector_iterators.h:32-36) */
+      const unsigned num = (unsigned)(cur & REF_ALIGN_MASK) - (unsigned)REF_TY_LEAF;
+      for (unsigned i = 0; i < num; i++)
+        tri4v_intersect(s->base + (cur & ~REF_ALIGN_MASK) + (size_t)TRI_BLOCK_BYTES * i, rh, instID, 0, col);
+    } else {
+      block_intersect(s, s->base + (cur & ~REF_ALIGN_MASK), rh, instID, st, col);
+    }
     tr.tfar = rh->ray.tfar; /* bvh_intersector1.cpp:117 */
   pop:;
   }
+}
+
+/* AccelN::intersect (kernels/common/acceln.cpp:51-56): every accel in creation order on the same ray -- triangle meshes
+ * (Scene::createTriangleAccel) before subdivision surfaces (createSubdivAccel), kernels/common/scene.cpp:650-654 */
+static void top_intersect(const cbvh_scene* s, cbvh_rayhit* rh, uint32_t instID, cbvh_stats* st, collector* col) {
+  if (s->tri_root) top_intersect_ex(s, rh, instID, NULL, col, 1);
+  top_intersect_ex(s, rh, instID, st, col, 0);
 }
 
 void cbvh_intersect1(const cbvh_scene* scene, cbvh_rayhit* rh, uint32_t instID, cbvh_stats* stats) {
@@ -603,11 +728,12 @@ void cbvh_candidates1(const cbvh_scene* scene, const cbvh_rayhit* rh, cbvh_candi
 
 /* BVHNIntersector1::occluded (bvh_intersector1.cpp:128-209) with Prim::occluded == `return true`
  * (compressed.h:754-756): top-level any-hit; the first non-empty leaf reached occludes. */
-void cbvh_occluded1(const cbvh_scene* s, cbvh_ray* ray, cbvh_stats* st) {
+static void occluded_ex(const cbvh_scene* s, cbvh_ray* ray, cbvh_stats* st, int tri) {
   if (ray->tfar < 0.0f) return;
   uint64_t stack[256];
   int sp = 1;
-  stack[0] = s->root;
+  stack[0] = tri ? s->tri_root : s->root;
+  if (stack[0] == 0) return;
   const float org[3] = {ray->org_x, ray->org_y, ray->org_z};
   const float dir[3] = {ray->dir_x, ray->dir_y, ray->dir_z};
   travray tr;
@@ -635,11 +761,32 @@ void cbvh_occluded1(const cbvh_scene* s, cbvh_ray* ray, cbvh_stats* st) {
       cur = ldq(np + AN_CHILDREN + 8 * (unsigned)last);
     }
     if (cur == REF_TY_LEAF) continue;
+    if (tri) {
+      const unsigned num = (unsigned)(cur & REF_ALIGN_MASK) - (unsigned)REF_TY_LEAF;
+      cbvh_rayhit tmp;
+      memset(&tmp, 0, sizeof(tmp));
+      tmp.ray = *ray;
+      int occ = 0;
+      for (unsigned i = 0; i < num && !occ; i++)
+        occ = tri4v_intersect(s->base + (cur & ~REF_ALIGN_MASK) + (size_t)TRI_BLOCK_BYTES * i, &tmp, 0xffffffffu, 1, NULL);
+      if (!occ) continue;
+      ray->tfar = -INFINITY;
+      return;
+    }
     if (st) { st->blocks++; st->hits++; }
     ray->tfar = -INFINITY; /* bvh_intersector1.cpp:199 */
     return;
   pop:;
   }
+}
+
+/* AccelN::occluded (acceln.cpp:86-93): accels in order, stop once the ray is occluded */
+void cbvh_occluded1(const cbvh_scene* s, cbvh_ray* ray, cbvh_stats* st) {
+  if (s->tri_root) {
+    occluded_ex(s, ray, NULL, 1);
+    if (ray->tfar < 0.0f) { if (st) { st->rays++; st->hits++; } return; }
+  }
+  occluded_ex(s, ray, st, 0);
 }
 
 /* ---- instancing: BVHNIntersector1<4,BVH_AN1,robust=false,ArrayIntersector1<ObjectIntersector1>> over instances ----

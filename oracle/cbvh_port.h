@@ -32,6 +32,7 @@ typedef struct cbvh_scene {
   uint64_t root;            /* BVH4 NodeRef (kernels/bvh/bvh.h:150-400) */
   int32_t leaf_kind;        /* CBVH_LEAF_* : which CompressedBVHIntersector1 variant (compressed.h:777-779) */
   int32_t proj_col_major;   /* storage order of Eigen::Matrix3f proj in the block header */
+  uint64_t tri_root;        /* 0, or the root NodeRef of the scene's BVH4 over Triangle4v blocks (mixed scenes) */
 } cbvh_scene;
 
 /* include/embree3/rtcore_ray.h:26-64 */

@@ -88,6 +88,8 @@ def ref_lib():
         L.ref_scene_dump_image.restype = C.c_size_t
         L.ref_scene_dump_image.argtypes = [vp, vp, C.c_size_t]
         L.ref_hardware_threads.restype = C.c_int
+        L.ref_scene_triangle_root.restype = C.c_uint64
+        L.ref_scene_triangle_root.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint)]
         L.ref_scene_instance_info.restype = C.c_int
         L.ref_scene_instance_info.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint, vp, vp, vp]
         _ref = L
@@ -157,6 +159,13 @@ class RefScene:
     def handle(self):
         return self.L.ref_scene_handle(self.h)
 
+    def triangle_root(self):
+        """(root of the BVH4 over Triangle4v blocks or 0, its index and the compressed accel's index in the AccelN list,
+        sizeof(Triangle4v))."""
+        ti, si, sz = C.c_int(), C.c_int(), C.c_uint()
+        r = self.L.ref_scene_triangle_root(self.h, C.byref(ti), C.byref(si), C.byref(sz))
+        return r, ti.value, si.value, sz.value
+
     def intersect(self, rayhits, threads=None):
         assert rayhits.dtype == np.float32 and rayhits.flags.c_contiguous
         return self.L.ref_intersect(self.h, rayhits.ctypes.data, rayhits.shape[0], rayhits.strides[0],
@@ -201,7 +210,8 @@ class RefScene:
 
 # ---------------------------------------------------------------------------------------------- port
 class _PortScene(C.Structure):
-    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("leaf_kind", C.c_int32), ("proj_col_major", C.c_int32)]
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("leaf_kind", C.c_int32), ("proj_col_major", C.c_int32),
+                ("tri_root", C.c_uint64)]
 
 
 class _Stats(C.Structure):
@@ -229,7 +239,7 @@ def port_lib():
 RIMG_HEADER = np.dtype([("magic", "S8"), ("version", "<u4"), ("leaf_kind", "<u4"), ("subdiv_level", "<u4"),
                         ("comp_level", "<u4"), ("proj_col_major", "<u4"), ("n_nodes", "<u4"), ("n_blocks", "<u4"),
                         ("reserved0", "<u4"), ("root", "<u8"), ("total_bytes", "<u8"), ("bounds", "<f4", (6,)),
-                        ("reserved1", "<u4", (4,))])
+                        ("tri_root", "<u8"), ("reserved1", "<u4", (2,))])
 assert RIMG_HEADER.itemsize == 96
 
 
@@ -240,9 +250,9 @@ def rimg_header(image):
 class PortScene:
     """The C restatement bound either to a live reference scene (base=0) or to an RIMG buffer."""
 
-    def __init__(self, base, root, leaf_kind, proj_col_major, keepalive=None):
+    def __init__(self, base, root, leaf_kind, proj_col_major, keepalive=None, tri_root=0):
         self.L = port_lib()
-        self.s = _PortScene(base, root, leaf_kind, proj_col_major)
+        self.s = _PortScene(base, root, leaf_kind, proj_col_major, tri_root)
         self.keepalive = keepalive
         self.last_stats = None
 
@@ -251,13 +261,15 @@ class PortScene:
         root, _ = ref_scene.root()
         if not root:
             raise RuntimeError("no compressed accel")
-        return cls(0, root, LEAF_KINDS[ref_scene.leaf.split(",")[0]], ref_layout()["proj_col_major"], keepalive=ref_scene)
+        return cls(0, root, LEAF_KINDS[ref_scene.leaf.split(",")[0]], ref_layout()["proj_col_major"], keepalive=ref_scene,
+                   tri_root=ref_scene.triangle_root()[0])
 
     @classmethod
     def from_image(cls, image):
         h = rimg_header(image)
         assert h["magic"] == b"ECBRIMG1"
-        return cls(image.ctypes.data, int(h["root"]), int(h["leaf_kind"]), int(h["proj_col_major"]), keepalive=image)
+        return cls(image.ctypes.data, int(h["root"]), int(h["leaf_kind"]), int(h["proj_col_major"]), keepalive=image,
+                   tri_root=int(h["tri_root"]))
 
     def _stats(self, st):
         self.last_stats = {n: getattr(st, n) for n, _ in _Stats._fields_}
@@ -311,7 +323,7 @@ class PortInstancedScene:
         lay = ref_layout()
         for i, o in enumerate(object_scenes):
             r, _ = o.root()
-            self.objects[i] = _PortScene(0, r, LEAF_KINDS[o.leaf.split(",")[0]], lay["proj_col_major"])
+            self.objects[i] = _PortScene(0, r, LEAF_KINDS[o.leaf.split(",")[0]], lay["proj_col_major"], o.triangle_root()[0])
         self.instances = (_PortInstance * len(ids))()
         n_geoms = int(ids.max()) + 1 if len(ids) else 0
         self.g2i = (C.c_uint32 * max(1, n_geoms))(*([INVALID] * max(1, n_geoms)))

@@ -257,6 +257,8 @@ REF_API void ref_scene_bounds(RefScene* s, float* b) {
   b[3] = bb.upper_x; b[4] = bb.upper_y; b[5] = bb.upper_z;
 }
 
+REF_API uint64_t ref_scene_triangle_root(RefScene* s, int* tri_index, int* subdiv_index, unsigned* sizeof_block);
+
 REF_API uint64_t ref_scene_compressed_root(RefScene* s, int* n_accels) {
   using namespace embree;
   // same access pattern as the reference's tutorials/bvh_access/bvh_access.cpp:199-219
@@ -271,7 +273,7 @@ REF_API uint64_t ref_scene_compressed_root(RefScene* s, int* n_accels) {
   }
   if (accel->type == AccelData::TY_ACCELN) {
     AccelN* an = (AccelN*)accel;
-    if (n_accels) *n_accels = (int)an->accels.size();
+    if (n_accels) *n_accels = (int)an->validAccels.size();  // non-empty accels: what AccelN::intersect loops over
     for (size_t i = 0; i < an->accels.size(); i++) {
       AccelData* a = an->accels[i]->intersectors.ptr;
       if (a && a->type == AccelData::TY_BVH4) {
@@ -368,6 +370,7 @@ struct Dumper {
   char* buf;
   size_t cap, pos;
   uint32_t n_nodes = 0, n_blocks = 0;
+  bool tri = false;  // walking the Triangle4v BVH4: a leaf is an array of `num` 176-byte blocks
   std::map<uint64_t, uint64_t> seen;
 
   size_t alloc(size_t bytes) {
@@ -384,6 +387,13 @@ struct Dumper {
     const uint64_t tag = ref & 15, ptr = ref & ~uint64_t(15);
     auto it = seen.find(ptr);
     if (it != seen.end()) return it->second | tag;
+    if ((ref & BVH4::tyLeaf) && tri) {
+      const size_t num = (size_t)tag - BVH4::tyLeaf;
+      const size_t at = alloc(num * sizeof(Triangle4v));
+      seen[ptr] = at;
+      put(at, (const void*)ptr, num * sizeof(Triangle4v));
+      return at | tag;
+    }
     if (ref & BVH4::tyLeaf) {
       typedef isa::compressed::CompressedBVH<isa::compressed::compressedNonUniform> Block;
       const Block* b = (const Block*)ptr;
@@ -426,6 +436,7 @@ REF_API size_t ref_scene_dump_image(RefScene* s, void* buf, size_t cap) {
   int n_accels = 0;
   const uint64_t root = ref_scene_compressed_root(s, &n_accels);
   if (!root || s->leaf_kind < 0) return 0;
+  const uint64_t tri_root = ref_scene_triangle_root(s, nullptr, nullptr, nullptr);
   Dumper d;
   d.s = s;
   d.buf = (char*)buf;
@@ -444,6 +455,10 @@ REF_API size_t ref_scene_dump_image(RefScene* s, void* buf, size_t cap) {
   h.root = d.visit(root);
   h.n_nodes = d.n_nodes;
   h.n_blocks = d.n_blocks;
+  if (tri_root) {  // mixed scene: the triangle accel travels in the same image
+    d.tri = true;
+    h.tri_root = d.visit(tri_root);
+  }
   h.total_bytes = (d.pos + 15) & ~size_t(15);
   ref_scene_bounds(s, h.bounds);
   d.put(0, &h, sizeof(h));
@@ -517,6 +532,17 @@ REF_API int ref_scene_instance_info(RefScene* s, uint64_t* root_out, unsigned ca
     n++;
   }
   return (int)n;
+}
+
+// mixed scenes: third accessor of INTEGRATION.md -- root of the BVH4 over Triangle4v blocks that AccelN visits before the
+// compressed accel (0 if the scene has no triangle meshes); fails if the triangle accel is not a BVH4<Triangle4v>
+REF_API int rtcGetTriangleBVH_b200(RTCScene hscene, uint64_t* root_out) {
+  RefScene tmp;
+  tmp.scene = hscene;
+  int ti = -1, si = -1;
+  *root_out = ref_scene_triangle_root(&tmp, &ti, &si, nullptr);
+  if (*root_out && si >= 0 && ti > si) return -1;  // the device path assumes triangles first (scene.cpp:650-654)
+  return 0;
 }
 
 // instancing scenes: second accessor of INTEGRATION.md (instance-level BVH4 root + per-instance data)

@@ -27,5 +27,7 @@ typedef struct rimg_header {
   uint64_t root;           /* relocated root NodeRef */
   uint64_t total_bytes;
   float bounds[6];         /* scene bounds lower xyz, upper xyz */
-  uint32_t reserved1[4];
+  uint64_t tri_root;       /* 0, or the relocated root NodeRef of the scene's BVH4 over Triangle4v blocks (176 B each,
+                              kernels/geometry/trianglev.h) -- mixed scenes, SURVEY 8f-1 */
+  uint32_t reserved1[2];
 } rimg_header;             /* 96 bytes */

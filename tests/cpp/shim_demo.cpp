@@ -2,7 +2,7 @@
 // (declarations from include/embree3_b200/rtcore_subset.h, which restate the reference's headers) and is linked
 // against libembree3_b200.so instead of libembree3.so.
 //
-//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin> [instanced]
+//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin> [instanced|plane]
 // builds the displaced cube of tutorials/displacement_geometry through rtc* calls (subdivision mesh + displacement
 // callback), commits, and traces the RTCRayHit records of rays.bin four ways, writing one result block per way:
 //   [0] rtcIntersect1M   [1] rtcIntersect16 packets   [2] rtcIntersect1 per ray (first 64 rays)   [3] rtcOccluded1M
@@ -41,7 +41,7 @@ static void on_error(void*, RTCError code, const char* str) { fprintf(stderr, "R
 
 int main(int argc, char** argv) {
   if (argc < 6) { fprintf(stderr, "usage: shim_demo leaf S C rays.bin out.bin\n"); return 2; }
-  const std::string cfg = std::string("subdiv_accel=bvh4.compressed.") + argv[1] + ",object_accel=bvh4.object,set_affinity=0,start_threads=0";
+  const std::string cfg = std::string("subdiv_accel=bvh4.compressed.") + argv[1] + ",object_accel=bvh4.object,tri_accel=bvh4.triangle4v,set_affinity=0,start_threads=0";
   RTCDevice device = rtcNewDevice(cfg.c_str());
   if (!device) { fprintf(stderr, "rtcNewDevice failed (%d)\n", (int)rtcGetDeviceError(nullptr)); return 3; }
   rtcSetDeviceErrorFunction(device, on_error, nullptr);
@@ -58,6 +58,20 @@ int main(int argc, char** argv) {
   rtcCommitGeometry(geom);
   rtcAttachGeometry(scene, geom);
   rtcReleaseGeometry(geom);
+  if (argc > 6 && std::string(argv[6]) == "plane") {
+    // the tutorial's ground plane (tutorials/displacement_geometry/displacement_geometry_device.cpp:156-177): a triangle mesh in
+    // the same scene -> the host builds a second accel and the shim hands both to the device path
+    RTCGeometry plane = rtcNewGeometry(device, RTC_GEOMETRY_TYPE_TRIANGLE);
+    float* v = (float*)rtcSetNewGeometryBuffer(plane, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, 16, 4);
+    const float vv[4][4] = {{-10, -2, -10, 0}, {-10, -2, 10, 0}, {10, -2, -10, 0}, {10, -2, 10, 0}};
+    memcpy(v, vv, sizeof(vv));
+    unsigned* t = (unsigned*)rtcSetNewGeometryBuffer(plane, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, 12, 2);
+    const unsigned tt[6] = {0, 1, 2, 1, 3, 2};
+    memcpy(t, tt, sizeof(tt));
+    rtcCommitGeometry(plane);
+    rtcAttachGeometry(scene, plane);
+    rtcReleaseGeometry(plane);
+  }
   rtcCommitScene(scene);
   if (RTCError e = rtcGetDeviceError(device)) { fprintf(stderr, "commit failed: %d\n", (int)e); return 4; }
   RTCScene object_scene = nullptr;

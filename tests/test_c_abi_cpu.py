@@ -61,6 +61,38 @@ def test_import_image_and_blob_round_trip(ecb, name, tmp_path):
         ecb.Scene.load(bad)
 
 
+def test_mixed_scene_import_and_blob_round_trip(ecb, tmp_path):
+    """the triangle accel (BVH4 over Triangle4v blocks) travels with the image and with the native blob."""
+    from oracle import pyoracle as po
+    image = np.fromfile(os.path.join(GOLDEN, "cubeplane_s4c2_leaf.rimg"), np.uint8)
+    plain = np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8)
+    h = po.rimg_header(image)
+    assert h["tri_root"] != 0 and po.rimg_header(plain)["tri_root"] == 0
+    mixed, alone = ecb.Scene.from_image(image), ecb.Scene.from_image(plain)
+    im, ia = mixed.info(), alone.info()
+    assert im["n_blocks"] == ia["n_blocks"]
+    assert im["device_bytes"] == ia["device_bytes"] + 176, "the ground plane is ONE Triangle4v block (root = leaf, no nodes)"
+    p = str(tmp_path / "m.ecbs")
+    mixed.save(p)
+    again = ecb.Scene.load(p)
+    assert again.info()["device_bytes"] == im["device_bytes"]
+    raw = bytearray(open(p, "rb").read())
+    raw[-176 - 8:-176 - 4] = (0x80000000 | (5 << 3) | 1).to_bytes(4, "little")   # trailer root -> block 5 of 1
+    bad = str(tmp_path / "bad.ecbs")
+    open(bad, "wb").write(raw)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(bad)
+    # attaching twice, or a null root, is refused
+    with pytest.raises(ecb.EcbError):
+        mixed.attach_triangles4v(int(h["tri_root"]), image.ctypes.data)
+    with pytest.raises(ecb.EcbError):
+        alone.attach_triangles4v(0, image.ctypes.data)
+    # attaching by hand gives the same scene as the image import
+    by_hand = ecb.Scene.import_bvh4(int(h["root"]), "leaf", 2, 4, int(h["proj_col_major"]), image.ctypes.data)
+    by_hand.attach_triangles4v(int(h["tri_root"]), image.ctypes.data)
+    assert by_hand.info()["device_bytes"] == im["device_bytes"]
+
+
 def test_importer_rejects_bad_input(ecb):
     image = np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8)
     with pytest.raises(ecb.EcbError):

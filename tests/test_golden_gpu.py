@@ -21,6 +21,8 @@ def test_cuda_matches_golden_vectors(ecb, name):
         got = rays.copy()
         scene.intersect1M(got)
         assert (got[:, COLS].view(np.uint32) == g["port_" + key].view(np.uint32)).all(), "%s %s: CUDA != recorded port output" % (name, key)
+        if "port_%s_ng" % key in g:  # mixed scenes: Ng of triangle hits is the real normal, bit-exact vs the port
+            assert (got[:, 12:15].view(np.uint32) == g["port_%s_ng" % key].view(np.uint32)).all()
         untouched = [c for c in range(20) if c not in COLS and c not in (12, 13, 14)]
         assert (got[:, untouched].view(np.uint32) == rays[:, untouched].view(np.uint32)).all()
         cand = np.zeros((len(rays), 4), np.float32)

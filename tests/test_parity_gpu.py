@@ -229,3 +229,63 @@ def test_full_size_configs(ecb, reference, ref_scene, leaf):
             scene.intersect1M(again)
             assert (again.view(np.uint32) == got.view(np.uint32)).all()
         scene.release()
+
+
+# ---- mixed scenes: BASELINE config 1 as the tutorial builds it, with its ground plane ----------------
+@pytest.mark.parametrize("leaf", LEAVES)
+def test_mixed_scene_cube_with_ground_plane(ecb, reference, leaf):
+    S, C = 5, 3
+    ref = reference.RefScene(leaf, S, C)
+    ref.add_cube(1, 1.0)
+    plane = ref.add_ground_plane()
+    ref.commit()
+    root, n_accels = ref.root()
+    tri_root = ref.triangle_root()[0]
+    assert root and tri_root and n_accels == 2
+    scene = ecb.Scene.import_bvh4(root, leaf, C, S, reference.ref_layout()["proj_col_major"], 0, ref.bounds())
+    scene.attach_triangles4v(tri_root)
+    port = reference.PortScene.from_ref(ref)
+    rays = rg.primary_rays(384, 384, **OFF_AXIS)
+    got, truth, c = _check_intersect(scene, port, ref, rays, "cube+plane %s primary" % leaf)
+    gi = got.view(np.uint32)
+    on_plane = (gi[:, 18] == plane) & (truth.view(np.uint32)[:, 18] == plane)
+    assert on_plane.sum() > 5000 and (gi[:, 18] == 0).sum() > 5000
+    assert np.allclose(got[on_plane, 12:15], truth[on_plane, 12:15], rtol=1e-5)          # real normals on triangle hits
+    assert (got[gi[:, 18] == 0, 12:15] == [1.0, 0.0, 0.0]).all()                         # dummy Ng on compressed hits
+    b = ref.bounds()
+    bounce = rg.diffuse_rays(truth, ref.hit_normals(truth), float(np.linalg.norm(b[3:] - b[:3])))
+    _check_intersect(scene, port, ref, bounce, "cube+plane %s bounce" % leaf)
+    # any-hit: AccelN::occluded = triangles first, then the (conservative) compressed accel
+    o_got, o_port, o_ref = rg.rays_only(bounce), rg.rays_only(bounce), rg.rays_only(bounce)
+    scene.occluded1M(o_got)
+    port.occluded(o_port)
+    ref.occluded(o_ref)
+    assert (o_got.view(np.uint32) == o_port.view(np.uint32)).all()
+    assert (o_got.view(np.uint32) == o_ref.view(np.uint32)).all() and (o_got[:, 8] < 0).any()
+    # device-resident entry point and the image / blob forms of the same scene
+    import torch
+    d = torch.from_numpy(rays).cuda()
+    scene.intersect_device(d.data_ptr(), len(rays))
+    torch.cuda.synchronize()
+    assert (d.cpu().numpy().view(np.uint32) == got.view(np.uint32)).all()
+    from_image = ecb.Scene.from_image(ref.dump_image())
+    again = rays.copy()
+    from_image.intersect1M(again)
+    assert (again.view(np.uint32) == got.view(np.uint32)).all()
+    ref.free()
+
+
+@pytest.mark.slow
+def test_config1_full_frame_with_ground_plane(ecb, reference):
+    """BASELINE config 1 exactly: cube S6/C4 with displacement + ground plane, 1024x1024 primary rays, tutorial camera."""
+    ref = reference.RefScene("leaf", 6, 4)
+    ref.add_cube(1, 1.0)
+    ref.add_ground_plane()
+    ref.commit()
+    scene = ecb.Scene.import_bvh4(ref.root()[0], "leaf", 4, 6, reference.ref_layout()["proj_col_major"], 0, ref.bounds())
+    scene.attach_triangles4v(ref.triangle_root()[0])
+    port = reference.PortScene.from_ref(ref)
+    rays = rg.primary_rays(1024, 1024, **rg.CUBE_CAMERA)
+    _, truth, c = _check_intersect(scene, port, ref, rays, "config 1 with ground plane")
+    assert c["hits_ref"] > 500000
+    ref.free()

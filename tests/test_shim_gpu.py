@@ -78,3 +78,34 @@ def test_instanced_scene_through_the_shim(ecb, reference, tmp_path):
     c = parity.assert_reference_parity(stream, truth, port.candidates(rays), "shim instanced")
     hit = truth.view(np.uint32)[:, 18] != 0xFFFFFFFF
     assert c["hits_ref"] > 500 and set(np.unique(stream.view(np.uint32)[hit, 19])) == {0, 1}
+
+
+def test_mixed_scene_through_the_shim(ecb, reference, tmp_path):
+    """The tutorial scene as the tutorial builds it: subdivision cube + triangle-mesh ground plane in one
+    RTCScene.  The shim receives two accels from the host and must reproduce AccelN::intersect / occluded."""
+    cam = dict(vp=(1.6, 1.45, -1.35), vi=(0.05, -0.02, 0.03), vu=(0.0, 1.0, 0.0), fov=90.0)
+    rays = rg.primary_rays(160, 128, **cam)
+    n = len(rays)
+    rays_path, out_path = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rays_path)
+    env = dict(os.environ, ECB200_HOST_EMBREE=reference.REF_SO)
+    r = subprocess.run([DEMO, "leaf", "5", "3", rays_path, out_path, "plane"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.float32)
+    stream = raw[: n * 20].reshape(n, 20)
+    occ = raw[-n * 16:].reshape(n, 16)
+    ref = reference.RefScene("leaf", 5, 3)
+    ref.add_cube(1, 1.0)
+    plane = ref.add_ground_plane()
+    ref.commit()
+    port = reference.PortScene.from_ref(ref)
+    truth, want = rays.copy(), rays.copy()
+    ref.intersect(truth)
+    port.intersect(want)
+    assert (stream.view(np.uint32) == want.view(np.uint32)).all(), "shim result differs from the oracle port"
+    c = parity.assert_reference_parity(stream, truth, port.candidates(rays), "shim mixed scene")
+    assert (truth.view(np.uint32)[:, 18] == plane).sum() > 1000 and c["hits_ref"] > 5000
+    o_truth = rg.rays_only(rays)
+    ref.occluded(o_truth)
+    assert (occ[:, :12].view(np.uint32) == o_truth.view(np.uint32)).all()
+    ref.free()
