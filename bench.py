@@ -294,9 +294,17 @@ def run_ours(args, rank, world):
     e2e_value = world * rays_per_step / float(t.item()) / 1e6
     e2e_hits = int((hp.view(np.uint32)[:, 18] != 0xFFFFFFFF).sum())
     assert e2e_hits == n_hits, "e2e path found %d hits, device path %d" % (e2e_hits, n_hits)
+    # the host-buffer call must leave exactly the bits the device-buffer call leaves
+    p_dev, b_dev = bufs[W]
+    assert (hp.view(np.uint32) == p_dev.cpu().numpy().view(np.uint32)).all(), "e2e primary results differ from the device path"
+    assert (hb.view(np.uint32) == b_dev.cpu().numpy().view(np.uint32)).all(), "e2e bounce results differ from the device path"
+    full_copy = os.environ.get("ECB200_HOST_PATH") == "copy"
+    d2h = int(prim.nbytes + bounce.nbytes) if full_copy else 20 * (len(prim) + len(bounce))
     e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(prim.nbytes + bounce.nbytes),
-           "d2h_bytes_per_step": int(prim.nbytes + bounce.nbytes), "steps": e2e_steps,
-           "call": "ecbIntersect1M (rtcIntersect1M drop-in), pinned host RTCRayHit arrays"}
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "call": "ecbIntersect1M (rtcIntersect1M drop-in), pinned host RTCRayHit arrays, results written in place; "
+                   + ("full records copied back" if full_copy else
+                      "20-byte compact hit records copied back and scattered into the caller's records by the library's host pool")}
     ecb.host_free(hp_ptr)
     ecb.host_free(hb_ptr)
 

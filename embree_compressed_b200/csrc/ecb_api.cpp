@@ -4,12 +4,16 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <functional>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ecb_kernels.h"
@@ -21,8 +25,10 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
-constexpr int kStages = 4;
-constexpr size_t kChunkRaysMax = 1u << 18;  // capacity of a staging buffer: 256 Ki rays
+constexpr int kStages = 6;
+constexpr size_t kChunkRaysMax = 1u << 17;  // capacity of a staging buffer: 128 Ki rays
+constexpr size_t kCompactBytesMax = kChunkRaysMax * 20 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n]
+constexpr int kScatterParts = 4;            // scatter jobs per chunk
 constexpr uint32_t kQueueRing = 256;
 
 ecbError cuda_fail(cudaError_t e, const char* what) {
@@ -43,16 +49,28 @@ ecbError cuda_fail(cudaError_t e, const char* what) {
 
 void ecb_set_error(const std::string& msg) { g_last_error = msg; }
 
-// Three-stage H2D -> kernel -> D2H pipeline over fixed device buffers; created lazily per scene.
+// Host-buffer pipeline: kStages chunks in flight, each H2D -> kernel(s) -> D2H on its own stream over fixed device
+// buffers; created lazily per scene.
 struct Staging {
   int device = -1;
   cudaStream_t stream[kStages] = {};
+  cudaEvent_t done[kStages] = {};
   void* d_buf[kStages] = {};
   void* h_pin[kStages] = {};  // pinned bounce buffers for pageable caller memory
+  void* d_cmp[kStages] = {};  // compact results of a chunk (device) ...
+  void* h_cmp[kStages] = {};  // ... and their pinned landing zone, scattered into the caller's array by the host pool
+  // scatter jobs of the chunk that currently owns a stage
+  std::mutex mutex;
+  std::condition_variable cv;
+  int pending[kStages] = {};
+  cudaError_t worker_error = cudaSuccess;
   ~Staging() {
     for (int i = 0; i < kStages; i++) {
       if (d_buf[i]) cudaFree(d_buf[i]);
       if (h_pin[i]) cudaFreeHost(h_pin[i]);
+      if (d_cmp[i]) cudaFree(d_cmp[i]);
+      if (h_cmp[i]) cudaFreeHost(h_cmp[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
       if (stream[i]) cudaStreamDestroy(stream[i]);
     }
   }
@@ -170,7 +188,10 @@ ecbError ensure_staging(ecbScene* s) {
   st->device = s->device;
   for (int i = 0; i < kStages; i++) {
     cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRaysMax * kRayHitBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_cmp[i], kCompactBytesMax);
+    if (e == cudaSuccess) e = cudaMallocHost(&st->h_cmp[i], kCompactBytesMax);
     if (e != cudaSuccess) {
       delete st;
       return cuda_fail(e, "staging allocation");
@@ -189,12 +210,53 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Transfer strategy of the host-buffer entry points when the caller's rays are in pinned memory
-// (ECB200_HOST_PATH = "copy" | "zerocopy" | "zerocopy2d"; measured on B200 / PCIe Gen5 x16, 55 GB/s one way, 35+35 both):
-//   copy (default): contiguous DMA of the full records both ways, 3-stage pipeline      -> 456 Mrays/s on the bench step
-//   zerocopy      : contiguous H2D DMA, kernel writes tfar + hit of the rays that hit straight into the caller's array
-//                   through its mapped device address (no D2H copy)                     -> 363 Mrays/s (small PCIe writes)
-//   zerocopy2d    : as above with a 2-D H2D copy of the 48-byte RTCRay part only        ->  35 Mrays/s (row-sized DMAs)
+// ---- host worker pool: scatters compact results into the caller's records while the next chunks are in flight ----
+// (ECB200_HOST_THREADS overrides the size; default min(8, hardware threads / 2).)  Process-wide, never torn down.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* pool = new HostPool;  // leaked on purpose: no destruction-order issues with the CUDA runtime at exit
+    return *pool;
+  }
+  void submit(std::function<void()> job) {
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      jobs_.push_back(std::move(job));
+    }
+    cv_.notify_one();
+  }
+  size_t size() const { return threads_.size(); }
+
+ private:
+  HostPool() {
+    unsigned n = std::thread::hardware_concurrency() / 2;
+    if (n > 8) n = 8;
+    if (const char* e = getenv("ECB200_HOST_THREADS")) n = (unsigned)atoi(e);
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    for (unsigned i = 0; i < n; i++) {
+      threads_.emplace_back([this] { run(); });
+      threads_.back().detach();
+    }
+  }
+  void run() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> lock(mutex_);
+        cv_.wait(lock, [this] { return !jobs_.empty(); });
+        job = std::move(jobs_.front());
+        jobs_.pop_front();
+      }
+      job();
+    }
+  }
+  std::mutex mutex_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> jobs_;
+  std::vector<std::thread> threads_;
+};
+
 // rays per pipeline stage of the host-buffer entry points (ECB200_HOST_CHUNK overrides for experiments)
 size_t pipeline_chunk() {
   static const size_t n = [] {
@@ -207,16 +269,54 @@ size_t pipeline_chunk() {
   return n;
 }
 
-int host_path_mode() {  // 0 copy, 1 zero-copy results + contiguous H2D, 2 zero-copy results + 48-byte 2-D H2D
-  static const int mode = [] {
+// Transfer strategy of the host-buffer entry points (measured on B200 / PCIe Gen5 x16: 55 GB/s one way, 35+35 GB/s both
+// ways at once, so the BYTES moved decide the end-to-end rate):
+//   compact (default): the full records go up, 20 bytes per ray ({tfar,u,v,primID} + geomID) come back into a pinned
+//                      landing zone, and a small host thread pool writes them into the caller's records while the next
+//                      chunks are in flight (a miss writes nothing, as the API demands)
+//   copy             : the full records travel both ways (ECB200_HOST_PATH=copy; also what instancing and mixed scenes
+//                      use, whose hits carry an instID / a real normal)                           -> 456 Mrays/s on the bench step
+// Tried and dropped: results written by the kernel straight into the caller's mapped pinned array 363 Mrays/s (small PCIe
+// writes), the same with a 48-byte 2-D H2D copy 35 Mrays/s (row-sized DMAs).
+bool use_compact_results() {
+  static const bool on = [] {
     const char* e = getenv("ECB200_HOST_PATH");
-    if (e && strcmp(e, "zerocopy") == 0) return 1;
-    if (e && strcmp(e, "zerocopy2d") == 0) return 2;
-    return 0;
+    return !(e && strcmp(e, "copy") == 0);
   }();
-  return mode;
+  return on;
 }
-bool use_zero_copy() { return host_path_mode() != 0; }
+
+// writes the compact results of rays [b, e) of a chunk into the caller's records (hit semantics of rtcIntersect1 /
+// rtcOccluded1: compressed.h:570-591, bvh_intersector1.cpp:199)
+void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n, size_t b, size_t e, bool any_hit, uint32_t instID) {
+  const uint32_t* geom = reinterpret_cast<const uint32_t*>(cmp);
+  const float* rec = reinterpret_cast<const float*>(cmp + ((4 * n + 15) & ~size_t(15)));
+  const float ninf = -__builtin_inff();
+  constexpr size_t kAhead = 16;  // the caller's records are not in cache: fetch the lines of the hits ahead (measured on the B200 host: -25 %)
+  for (size_t i = b; i < e; i++) {
+    if (i + kAhead < e && geom[i + kAhead] != 0xFFFFFFFFu) {
+      __builtin_prefetch(rays + (i + kAhead) * stride + 32, 1);
+      __builtin_prefetch(rays + (i + kAhead) * stride + 79, 1);
+    }
+    const uint32_t g = geom[i];
+    if (g == 0xFFFFFFFFu) continue;
+    uint8_t* r = rays + i * stride;
+    if (any_hit) {
+      memcpy(r + 32, &ninf, 4);
+      continue;
+    }
+    const float* q = rec + 4 * i;
+    const float ngu[4] = {1.f, 0.f, 0.f, q[1]};  // Ng dummy (compressed.h:574), u
+    uint32_t tail[4];
+    memcpy(&tail[0], &q[2], 4);  // v
+    memcpy(&tail[1], &q[3], 4);  // primID
+    tail[2] = g;
+    tail[3] = instID;
+    memcpy(r + 32, &q[0], 4);
+    memcpy(r + 48, ngu, 16);
+    memcpy(r + 64, tail, 16);
+  }
+}
 
 // Shared by intersect (elem = 80) and occluded (elem = 48).
 ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact = false) {
@@ -241,22 +341,21 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   uint8_t* base = static_cast<uint8_t*>(rays);
   const size_t chunk = pipeline_chunk();
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
-
-  void* mapped = nullptr;
   const bool pinned = is_pinned(rays);
-  const bool zero_copy = pinned && use_zero_copy() && !s->has_triangles() && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(rays) & 15) == 0) &&
-                         (stride % 16 == 0) && cudaHostGetDevicePointer(&mapped, rays, 0) == cudaSuccess && mapped;
-  if (!zero_copy) cudaGetLastError();
+  const bool compact = use_compact_results() && !s->instanced && !s->has_triangles();
+  const bool use_pool = compact && M > 8192;  // small calls (rtcIntersect1, packets) scatter inline
 
-  auto launch = [&](int k, size_t n, size_t in_stride, uint8_t* out, size_t out_stride) -> cudaError_t {
+  auto launch = [&](int k, size_t n) -> cudaError_t {
     EcbLaunch L;
     L.in = static_cast<const uint8_t*>(st->d_buf[k]);
-    L.in_stride = in_stride;
-    L.out = out;
-    L.out_stride = out_stride;
+    L.in_stride = elem;
+    L.out = compact ? nullptr : static_cast<uint8_t*>(st->d_buf[k]);
+    L.out_stride = elem;
     L.M = n;
     L.instID = instID;
     L.any_hit_exact = exact ? 1u : 0u;
+    L.hit_geom = compact ? static_cast<uint32_t*>(st->d_cmp[k]) : nullptr;
+    L.hit_rec = compact ? reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15))) : nullptr;
     L.block_out = nullptr;
     L.counters = nullptr;
     L.queue = next_queue(s);
@@ -271,70 +370,88 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
   };
 
-  if (zero_copy) {
-    // H2D: only the RTCRay part (48 B) of every record; results go back through the mapped pointer
-    for (uint64_t c = 0; c < n_chunks; c++) {
-      const int k = (int)(c % kStages);
-      const uint64_t first = c * chunk;
-      const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
-      cudaStream_t q = st->stream[k];
-      size_t in_stride = elem;
-      if (host_path_mode() == 2) {
-        in_stride = kRayBytes;
-        CU(cudaMemcpy2DAsync(st->d_buf[k], kRayBytes, base + first * stride, stride, kRayBytes, n, cudaMemcpyHostToDevice, q));
-      } else if (stride == elem) {
-        CU(cudaMemcpyAsync(st->d_buf[k], base + first * stride, n * elem, cudaMemcpyHostToDevice, q));
-      } else {
-        CU(cudaMemcpy2DAsync(st->d_buf[k], elem, base + first * stride, stride, elem, n, cudaMemcpyHostToDevice, q));
-      }
-      cudaError_t le = launch(k, n, in_stride, static_cast<uint8_t*>(mapped) + first * stride, stride);
-      if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
-    }
-    for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
-    return ECB_SUCCESS;
-  }
-
   if (!pinned) {
     for (int i = 0; i < kStages; i++)
       if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRaysMax * kRayHitBytes));
   }
-  auto unpack = [&](uint64_t c, int k) {  // bounce buffer -> caller's array
-    const uint64_t first = c * chunk;
-    const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
-    uint8_t* dst = base + first * stride;
+  auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
+  auto unpack = [&](uint64_t c, int k) {  // full-record mode, pageable caller memory: bounce buffer -> caller's array
+    const size_t n = chunk_size(c);
+    uint8_t* dst = base + c * chunk * stride;
     const uint8_t* hb = static_cast<const uint8_t*>(st->h_pin[k]);
     if (stride == elem) memcpy(dst, hb, n * elem);
     else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, hb + i * elem, elem);
   };
+  auto wait_stage = [&](int k) {  // the scatter jobs of the chunk that last used stage k are done
+    std::unique_lock<std::mutex> wl(st->mutex);
+    st->cv.wait(wl, [&] { return st->pending[k] == 0; });
+  };
+  st->worker_error = cudaSuccess;
+  const bool any_hit = occluded;  // exact any-hit runs through the occluded entry points as well
+
   for (uint64_t c = 0; c < n_chunks; c++) {
     const int k = (int)(c % kStages);
-    const uint64_t first = c * chunk;
-    const size_t n = (size_t)((M - first) < chunk ? (M - first) : chunk);
-    uint8_t* src = base + first * stride;
+    const size_t n = chunk_size(c);
+    uint8_t* src = base + c * chunk * stride;
     cudaStream_t q = st->stream[k];
+    if (use_pool) wait_stage(k);
     if (pinned) {
       if (stride == elem) CU(cudaMemcpyAsync(st->d_buf[k], src, n * elem, cudaMemcpyHostToDevice, q));
       else CU(cudaMemcpy2DAsync(st->d_buf[k], elem, src, stride, elem, n, cudaMemcpyHostToDevice, q));
     } else {
       // pageable caller memory: bounce through pinned buffers; first drain this stage's previous round trip
       CU(cudaStreamSynchronize(q));
-      if (c >= (uint64_t)kStages) unpack(c - kStages, k);
+      if (!compact && c >= (uint64_t)kStages) unpack(c - kStages, k);
       uint8_t* hb = static_cast<uint8_t*>(st->h_pin[k]);
       if (stride == elem) memcpy(hb, src, n * elem);
       else for (size_t i = 0; i < n; i++) memcpy(hb + i * elem, src + i * stride, elem);
       CU(cudaMemcpyAsync(st->d_buf[k], hb, n * elem, cudaMemcpyHostToDevice, q));
     }
-    cudaError_t le = launch(k, n, elem, static_cast<uint8_t*>(st->d_buf[k]), elem);
+    cudaError_t le = launch(k, n);
     if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
-    if (pinned) {
+    if (compact) {
+      const size_t bytes = ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n);
+      CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], bytes, cudaMemcpyDeviceToHost, q));
+      if (use_pool) {
+        CU(cudaEventRecord(st->done[k], q));
+        {
+          std::lock_guard<std::mutex> wl(st->mutex);
+          st->pending[k] = kScatterParts;
+        }
+        for (int part = 0; part < kScatterParts; part++) {
+          const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
+          const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
+          const int device = s->device;
+          cudaEvent_t ev = st->done[k];
+          HostPool::get().submit([=] {
+            cudaError_t ce = cudaSetDevice(device);
+            if (ce == cudaSuccess) ce = cudaEventSynchronize(ev);
+            if (ce == cudaSuccess) scatter_results(src, stride, cmp, n, b, e, any_hit, instID);
+            std::lock_guard<std::mutex> wl(st->mutex);
+            if (ce != cudaSuccess && st->worker_error == cudaSuccess) st->worker_error = ce;
+            if (--st->pending[k] == 0) st->cv.notify_all();
+          });
+        }
+      }
+    } else if (pinned) {
       if (stride == elem) CU(cudaMemcpyAsync(src, st->d_buf[k], n * elem, cudaMemcpyDeviceToHost, q));
       else CU(cudaMemcpy2DAsync(src, stride, st->d_buf[k], elem, elem, n, cudaMemcpyDeviceToHost, q));
     } else {
       CU(cudaMemcpyAsync(st->h_pin[k], st->d_buf[k], n * elem, cudaMemcpyDeviceToHost, q));
     }
   }
+  if (use_pool) {
+    for (int k = 0; k < kStages; k++) wait_stage(k);
+    if (st->worker_error != cudaSuccess) return cuda_fail(st->worker_error, "result scatter");
+    return ECB_SUCCESS;
+  }
   for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
-  if (!pinned) {
+  if (compact) {  // small call: scatter inline
+    for (uint64_t c = 0; c < n_chunks; c++) {
+      const size_t n = chunk_size(c);
+      scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID);
+    }
+  } else if (!pinned) {
     const uint64_t tail0 = n_chunks > (uint64_t)kStages ? n_chunks - kStages : 0;
     for (uint64_t c = tail0; c < n_chunks; c++) unpack(c, (int)(c % kStages));
   }
@@ -361,6 +478,8 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
   L.M = M;
   L.instID = instID;
   L.any_hit_exact = exact ? 1u : 0u;
+  L.hit_rec = nullptr;
+  L.hit_geom = nullptr;
   L.block_out = d_block_out;
   L.counters = d_counters;
   L.queue = next_queue(s);

@@ -660,6 +660,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
           const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
+          if (L.hit_geom) L.hit_geom[index] = 0xFFFFFFFFu;
           if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
             org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
             dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
@@ -688,11 +689,16 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
         busy = false;
         if (hit.block != 0xFFFFFFFFu && !L.any_hit_exact) {
-          uint8_t* op = L.out + index * L.out_stride;
-          *reinterpret_cast<float*>(op + 32) = hit.tfar;
-          *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
-          *reinterpret_cast<float4*>(op + 64) =
-              make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(L.instID));
+          if (L.hit_geom) {  // compact result: the host layer scatters it into the caller's record
+            L.hit_rec[index] = make_float4(hit.tfar, hit.u, hit.v, __uint_as_float(hit.primID));
+            L.hit_geom[index] = hit.geomID;
+          } else {
+            uint8_t* op = L.out + index * L.out_stride;
+            *reinterpret_cast<float*>(op + 32) = hit.tfar;
+            *reinterpret_cast<float4*>(op + 48) = make_float4(1.f, 0.f, 0.f, hit.u);  // Ng = (1,0,0) dummy (compressed.h:574), u
+            *reinterpret_cast<float4*>(op + 64) =
+                make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(L.instID));
+          }
           if (L.block_out) L.block_out[index] = hit.block;
           if (STATS) n_hits++;
         }
@@ -710,7 +716,8 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         if (L.any_hit_exact && hit.block != 0xFFFFFFFFu) {
           // opt-in exact shadow query (NOT the reference's behaviour, which stops at the block's bounding box): any
           // accepted leaf hit inside [tnear, tfar] occludes
-          *reinterpret_cast<float*>(L.out + index * L.out_stride + 32) = __int_as_float(0xff800000);
+          if (L.hit_geom) L.hit_geom[index] = 0u;
+          else *reinterpret_cast<float*>(L.out + index * L.out_stride + 32) = __int_as_float(0xff800000);
           busy = false;
           if (STATS) n_hits++;
         }
@@ -1131,12 +1138,14 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScen
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
     const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
     const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
-    if (r0.w > tfar_in) continue;
-    if (tfar_in < 0.0f) continue;  // bvh_intersector1.cpp:133
-    const float org[3] = {r0.x, r0.y, r0.z};
-    const float dir[3] = {r1.x, r1.y, r1.z};
-    if (sc.root != ECB_REF_EMPTY && trace_any(sc, org, dir, r0.w, tfar_in))
-      *reinterpret_cast<float*>(L.out + i * L.out_stride + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
+    bool occluded = false;
+    if (!(r0.w > tfar_in) && !(tfar_in < 0.0f)) {  // inactive stream ray; already occluded (bvh_intersector1.cpp:133)
+      const float org[3] = {r0.x, r0.y, r0.z};
+      const float dir[3] = {r1.x, r1.y, r1.z};
+      occluded = sc.root != ECB_REF_EMPTY && trace_any(sc, org, dir, r0.w, tfar_in);
+    }
+    if (L.hit_geom) L.hit_geom[i] = occluded ? 0u : 0xFFFFFFFFu;
+    else if (occluded) *reinterpret_cast<float*>(L.out + i * L.out_stride + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
   }
 }
 

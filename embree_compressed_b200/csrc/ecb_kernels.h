@@ -34,6 +34,11 @@ struct EcbLaunch {
   uint64_t M;
   uint32_t instID;
   uint32_t any_hit_exact;         // 1: shadow-ray mode (first accepted leaf hit terminates the ray, only tfar = -inf is written)
+  // compact result mode (host-buffer entry points): when hit_geom != NULL the kernels never touch `out`; per ray they write
+  // hit_geom[i] = geomID of the hit (0xFFFFFFFF: miss / inactive; any-hit queries: 0 = occluded) and, for a hit,
+  // hit_rec[i] = {tfar, u, v, primID}.  20 bytes per ray go back over PCIe instead of the 80-byte record.
+  float4* hit_rec;
+  uint32_t* hit_geom;
   uint32_t* block_out;            // optional: index of the block of the final hit per ray
   unsigned long long* counters;   // optional: instrumented variant (6 counters)
   unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)
