@@ -40,15 +40,22 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+SUBDIV_LEVEL, COMP_LEVEL = 6, 3   # BASELINE.json configs[1] (build/bomberman.ecs); --levels S,C selects another tessellation
+
+
 def scene_path(leaf):
-    return os.path.join(ROOT, "scenes", "_built", "bomberman_s6c3_%s.rimg" % leaf)
+    return os.path.join(ROOT, "scenes", "_built", "bomberman_s%dc%d_%s.rimg" % (SUBDIV_LEVEL, COMP_LEVEL, leaf))
 
 
-def workload_config(leaf, n_primary, n_bounce):
-    return {"workload": "bomberman.obj subdiv S=6 C=3 compress.%s, %dx%d primary + 1 cosine-diffuse bounce" % (leaf, WIDTH, HEIGHT),
-            "rays_primary": int(n_primary), "rays_bounce_active": int(n_bounce),
-            "l2": "ray buffers (2 x 166 MB per step, a fresh copy every step) exceed the 126 MB L2; the 18.8 MB scene is "
-                  "L2-resident by construction of the workload"}
+def workload_config(leaf, n_primary, n_bounce, scene_bytes=None):
+    if scene_bytes is None or scene_bytes < 100e6:
+        l2 = "ray buffers (2 x 166 MB per step, a fresh copy every step) exceed the 126 MB L2; the %s scene is L2-resident by " \
+             "construction of the workload" % ("18.8 MB" if scene_bytes is None else "%.1f MB" % (scene_bytes / 1e6))
+    else:
+        l2 = "ray buffers (2 x 166 MB per step, a fresh copy every step) and the %.0f MB scene both exceed the 126 MB L2" % (scene_bytes / 1e6)
+    return {"workload": "bomberman.obj subdiv S=%d C=%d compress.%s, %dx%d primary + 1 cosine-diffuse bounce"
+                        % (SUBDIV_LEVEL, COMP_LEVEL, leaf, WIDTH, HEIGHT),
+            "rays_primary": int(n_primary), "rays_bounce_active": int(n_bounce), "l2": l2}
 
 
 class ClockSampler:
@@ -262,7 +269,7 @@ def run_ours(args, rank, world):
     peak, peak_src = measured_peak()
     achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": recorded_traffic(args.leaf), "peak_source": peak_src, "kernel": "ecb_intersect_kernel<%s> (%s pass)" % (args.leaf, dom),
+                "traffic": recorded_traffic(args.leaf) if (SUBDIV_LEVEL, COMP_LEVEL) == (6, 3) else None, "peak_source": peak_src, "kernel": "ecb_intersect_kernel<%s> (%s pass)" % (args.leaf, dom),
                 "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
                 "algorithmic_bytes_per_ray": {"primary": round(bytes_prim / n_prim, 1), "bounce": round(bytes_bounce / max(1, n_bounce), 1)},
                 "work_per_ray": {"primary": {"top_nodes": round(c_prim[1] / c_prim[0], 3), "blocks": round(c_prim[2] / c_prim[0], 3),
@@ -333,7 +340,7 @@ def run_ours(args, rank, world):
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": workload_config(args.leaf, n_prim, n_bounce),
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args.leaf, n_prim, n_bounce, info["device_bytes"]),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                "bytes_per_micro_triangle": {"device_format": round(info["bytes_per_micro_triangle"], 3),
                                             "reference_layout": round(info["reference_bytes_per_micro_triangle"], 3)},
@@ -361,7 +368,7 @@ def build_reference_scene(leaf):
     from oracle import pyoracle as po
     if not po.have_reference():
         return None, po
-    ref = po.RefScene(leaf, 6, 3)
+    ref = po.RefScene(leaf, SUBDIV_LEVEL, COMP_LEVEL)
     ref.add_obj()
     ref.commit()
     return ref, po
@@ -446,7 +453,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--leaf", default="leaf", choices=["leaf", "grid", "box"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--levels", default="6,3", help="S,C of the scene image (default: BASELINE configs[1]); other images come "
+                                                    "from `python __graft_entry__.py --scene bomberman_s8c3_leaf`")
     args = ap.parse_args()
+    global SUBDIV_LEVEL, COMP_LEVEL
+    SUBDIV_LEVEL, COMP_LEVEL = (int(v) for v in args.levels.split(","))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

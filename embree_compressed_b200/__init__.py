@@ -44,6 +44,12 @@ class TriangleDesc(C.Structure):
     _fields_ = [("base", C.c_void_p), ("root", C.c_uint64)]
 
 
+class BuildDesc(C.Structure):
+    _fields_ = [("leaf_kind", C.c_uint32), ("comp_level", C.c_uint32), ("n_blocks", C.c_uint32), ("reserved", C.c_uint32),
+                ("grids", C.c_void_p), ("space", C.c_void_p), ("world", C.c_void_p), ("uv", C.c_void_p),
+                ("geomIDs", C.c_void_p), ("primIDs", C.c_void_p)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("leaf_kind", C.c_uint32), ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32),
                 ("n_top_nodes", C.c_uint32), ("n_blocks", C.c_uint32), ("top_depth", C.c_uint32),
@@ -58,6 +64,10 @@ SYMBOLS = {
     "ecbSceneImportBVH4": (C.c_int, [C.POINTER(ImportDesc), C.POINTER(_vp)]),
     "ecbSceneImportInstances": (C.c_int, [C.POINTER(InstanceDesc), C.POINTER(_vp)]),
     "ecbSceneAttachTriangles4v": (C.c_int, [_vp, C.POINTER(TriangleDesc)]),
+    "ecbBlockStride": (_u32, [_u32, _u32]),
+    "ecbBuildBlocks": (C.c_int, [C.POINTER(BuildDesc), _vp, _vp, _vp]),
+    "ecbSceneCopyBlocks": (C.c_int, [_vp, _vp, _sz]),
+    "ecbSceneSetBlocks": (C.c_int, [_vp, _vp, _sz]),
     "ecbSceneImportImage": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "ecbSceneImportImageFile": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "ecbSceneSave": (C.c_int, [_vp, C.c_char_p]),
@@ -121,6 +131,25 @@ def host_alloc(n_bytes):
 
 def host_free(ptr):
     _lib().ecbHostFree(ptr)
+
+
+def build_blocks(leaf_kind, comp_level, grids, space, world, uv, geom_ids, prim_ids):
+    """ecbBuildBlocks: compressed blocks from displaced vertex grids and frames, built on the GPU.
+    Returns (blocks uint8 (n, stride), bounds float32 (n, 6), patch_ok uint32 (n,))."""
+    kind = LEAF_KINDS.get(leaf_kind, leaf_kind)
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (grids, space, world, uv)]
+    ids = [np.ascontiguousarray(a, np.uint32) for a in (geom_ids, prim_ids)]
+    n = len(ids[0])
+    stride = int(_lib().ecbBlockStride(kind, comp_level))
+    d = BuildDesc()
+    d.leaf_kind, d.comp_level, d.n_blocks = kind, comp_level, n
+    d.grids, d.space, d.world, d.uv = (a.ctypes.data for a in arrs)
+    d.geomIDs, d.primIDs = (a.ctypes.data for a in ids)
+    blocks = np.zeros((n, max(stride, 1)), np.uint8)
+    bounds = np.zeros((n, 6), np.float32)
+    ok = np.zeros(n, np.uint32)
+    _check(_lib().ecbBuildBlocks(C.byref(d), blocks.ctypes.data, bounds.ctypes.data, ok.ctypes.data), "ecbBuildBlocks")
+    return blocks, bounds, ok
 
 
 class Scene:
@@ -220,6 +249,18 @@ class Scene:
         d["bytes_per_micro_triangle"] = d["device_bytes"] / max(1, d["micro_triangles"])
         d["reference_bytes_per_micro_triangle"] = d["reference_bytes"] / max(1, d["micro_triangles"])
         return d
+
+    def copy_blocks(self):
+        """Host copy of the converted blocks: uint8 (n_blocks, block_stride)."""
+        i = self.info()
+        out = np.zeros((i["n_blocks"], i["block_stride"]), np.uint8)
+        _check(_lib().ecbSceneCopyBlocks(self._h, out.ctypes.data, out.nbytes), "ecbSceneCopyBlocks")
+        return out
+
+    def set_blocks(self, blocks):
+        b = np.ascontiguousarray(blocks, np.uint8)
+        _check(_lib().ecbSceneSetBlocks(self._h, b.ctypes.data, b.nbytes), "ecbSceneSetBlocks")
+        return self
 
     def block_normals(self):
         n = self.info()["n_blocks"]

@@ -36,7 +36,7 @@ def _stale(target, sources):
 def build_variant(name, defines):
     """Developer helper: build libecb200_<name>.so with extra -D flags (kernel A/B experiments, tools/kbench.py)."""
     out = os.path.join(HERE, "libecb200_%s.so" % name)
-    srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_api.cpp", "ecb_import.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_build.cu", "ecb_api.cpp", "ecb_import.cpp")]
     cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-shared", "-o", out] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -46,7 +46,7 @@ def build_variant(name, defines):
 
 
 def build(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_api.cpp", "ecb_import.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_build.cu", "ecb_api.cpp", "ecb_import.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + \
         [os.path.join(HERE, "..", "include", "ecb200.h"), __file__]
     if force or _stale(LIB, deps):

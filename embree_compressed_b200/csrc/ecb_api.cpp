@@ -805,6 +805,94 @@ ecbError ecbSceneBlockNormals(const ecbScene* s, float* out, size_t cap) {
   return ECB_SUCCESS;
 }
 
+uint32_t ecbBlockStride(uint32_t leaf_kind, uint32_t comp_level) {
+  if (leaf_kind > ECB_LEAF_BOX || comp_level < 1 || comp_level > ECB_MAX_C) return 0;
+  uint32_t leaf_offset, stride;
+  ecb_block_layout(comp_level, leaf_kind, &leaf_offset, &stride);
+  return stride;
+}
+
+ecbError ecbBuildBlocks(const ecbBuildDesc* d, void* blocks_out, float* bounds_out, uint32_t* patch_ok_out) {
+  if (!d || !blocks_out || !bounds_out) return ECB_ERROR_INVALID_ARGUMENT;
+  if (d->leaf_kind > ECB_LEAF_BOX || d->comp_level < 1 || d->comp_level > ECB_MAX_C) {
+    g_last_error = "leaf kind / compression level out of range";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  if (d->n_blocks == 0) return ECB_SUCCESS;
+  if (!d->grids || !d->space || !d->world || !d->uv || !d->geomIDs || !d->primIDs) return ECB_ERROR_INVALID_ARGUMENT;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0) {
+    g_last_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    return ECB_ERROR_NO_DEVICE;
+  }
+  int device = 0;
+  CU(cudaGetDevice(&device));
+  const uint32_t n = d->n_blocks, W = (1u << d->comp_level) + 1;
+  EcbBuildLaunch b{};
+  ecb_block_layout(d->comp_level, d->leaf_kind, &b.leaf_offset, &b.stride);
+  b.n = n;
+  b.comp_level = d->comp_level;
+  b.leaf_kind = d->leaf_kind;
+  const size_t grid_bytes = (size_t)n * W * W * 12, out_bytes = (size_t)n * b.stride;
+  void* dev[9] = {};
+  auto release = [&] { for (void* p : dev) if (p) cudaFree(p); };
+  auto up = [&](int slot, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(&dev[slot], bytes);
+    if (e == cudaSuccess && src) e = cudaMemcpy(dev[slot], src, bytes, cudaMemcpyHostToDevice);
+    return e;
+  };
+  ce = up(0, d->grids, grid_bytes);
+  if (ce == cudaSuccess) ce = up(1, d->space, (size_t)n * 36);
+  if (ce == cudaSuccess) ce = up(2, d->world, (size_t)n * 36);
+  if (ce == cudaSuccess) ce = up(3, d->uv, (size_t)n * 16);
+  if (ce == cudaSuccess) ce = up(4, d->geomIDs, (size_t)n * 4);
+  if (ce == cudaSuccess) ce = up(5, d->primIDs, (size_t)n * 4);
+  if (ce == cudaSuccess) ce = up(6, nullptr, out_bytes);
+  if (ce == cudaSuccess) ce = up(7, nullptr, (size_t)n * 24);
+  if (ce == cudaSuccess) ce = up(8, nullptr, (size_t)n * 4);
+  if (ce == cudaSuccess) ce = cudaMemset(dev[6], 0, out_bytes);
+  if (ce == cudaSuccess) {
+    b.grids = static_cast<const float*>(dev[0]);
+    b.space = static_cast<const float*>(dev[1]);
+    b.world = static_cast<const float*>(dev[2]);
+    b.uv = static_cast<const float*>(dev[3]);
+    b.geomIDs = static_cast<const uint32_t*>(dev[4]);
+    b.primIDs = static_cast<const uint32_t*>(dev[5]);
+    b.blocks = static_cast<uint8_t*>(dev[6]);
+    b.bounds = static_cast<float*>(dev[7]);
+    b.patch_ok = static_cast<uint32_t*>(dev[8]);
+    ce = ecb_launch_build(b, device, nullptr);
+    g_launches.fetch_add(1);
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(blocks_out, dev[6], out_bytes, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = cudaMemcpy(bounds_out, dev[7], (size_t)n * 24, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && patch_ok_out) ce = cudaMemcpy(patch_ok_out, dev[8], (size_t)n * 4, cudaMemcpyDeviceToHost);
+  release();
+  if (ce != cudaSuccess) return cuda_fail(ce, "ecbBuildBlocks");
+  return ECB_SUCCESS;
+}
+
+ecbError ecbSceneCopyBlocks(const ecbScene* s, void* out, size_t capacity) {
+  if (!s || !out || s->instanced) return ECB_ERROR_INVALID_ARGUMENT;
+  if (capacity < s->blocks.size()) {
+    g_last_error = "buffer smaller than n_blocks x block_stride";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  memcpy(out, s->blocks.data(), s->blocks.size());
+  return ECB_SUCCESS;
+}
+
+ecbError ecbSceneSetBlocks(ecbScene* s, const void* blocks, size_t bytes) {
+  if (!s || !blocks || s->instanced) return ECB_ERROR_INVALID_ARGUMENT;
+  if (s->device >= 0 || bytes != s->blocks.size()) {
+    g_last_error = "blocks can be replaced before the scene is resident, by the same number of bytes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
+  memcpy(s->blocks.data(), blocks, bytes);
+  return ECB_SUCCESS;
+}
+
 ecbError ecbHostAlloc(void** ptr, size_t bytes) {
   if (!ptr) return ECB_ERROR_INVALID_ARGUMENT;
   CU(cudaMallocHost(ptr, bytes));

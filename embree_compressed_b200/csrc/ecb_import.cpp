@@ -132,12 +132,7 @@ ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out) {
   s->elems = (cells - 1) / 3;
   s->grid_width = (1u << C) + 1;
   s->rcp_edges = 1.0f / (float)(1u << C);
-  size_t off = ECB_BLOCK_NODES_OFFSET + 4 * (size_t)(s->elems - 1);
-  off = (off + 15) & ~size_t(15);
-  s->leaf_offset = (uint32_t)off;
-  if (desc->leaf_kind == ECB_LEAF_LEAF) off += 2 * (size_t)cells;
-  if (desc->leaf_kind == ECB_LEAF_GRID) off += 12 * (size_t)s->grid_width * s->grid_width;
-  s->block_stride = (uint32_t)((off + 15) & ~size_t(15));
+  ecb_block_layout(C, desc->leaf_kind, &s->leaf_offset, &s->block_stride);
 
   Importer imp(*desc, *s);
   try {

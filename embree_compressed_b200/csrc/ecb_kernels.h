@@ -49,3 +49,18 @@ cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbL
 cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);
 // mixed scenes: the triangle accel is traversed first, in place (L.in == L.out), then the compressed accel on the same rays
 cudaError_t ecb_launch_triangles(const EcbDeviceTriScene& ts, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);
+
+// block construction (csrc/ecb_build.cu): all pointers are device pointers
+struct EcbBuildLaunch {
+  const float* grids;        // n x (2^C+1)^2 x 3 displaced vertices, row-major
+  const float* space;        // n x 9 block frames (world -> local)
+  const float* world;        // n x 9 their inverses [vx vy vz]
+  const float* uv;           // n x 4 uv of vertex (0,0) and uv extent
+  const uint32_t* geomIDs;
+  const uint32_t* primIDs;
+  uint8_t* blocks;           // n x stride, zero-initialised by the caller; receives blocks in the device format
+  float* bounds;             // n x 6 conservative world bounds
+  uint32_t* patch_ok;        // optional, n
+  uint32_t n, comp_level, leaf_kind, stride, leaf_offset;
+};
+cudaError_t ecb_launch_build(const EcbBuildLaunch& b, int device, cudaStream_t stream);

@@ -54,6 +54,17 @@ struct ecbScene {
   struct Staging* staging = nullptr;
 };
 
+// byte layout of one block in the device format for compression level C and leaf kind (ecb_format.h)
+inline void ecb_block_layout(uint32_t C, uint32_t leaf_kind, uint32_t* leaf_offset, uint32_t* stride) {
+  const uint32_t cells = 1u << (2 * C), elems = (cells - 1) / 3, width = (1u << C) + 1;
+  size_t off = ECB_BLOCK_NODES_OFFSET + 4 * (size_t)(elems - 1);
+  off = (off + 15) & ~size_t(15);
+  *leaf_offset = (uint32_t)off;
+  if (leaf_kind == ECB_LEAF_LEAF) off += 2 * (size_t)cells;
+  if (leaf_kind == ECB_LEAF_GRID) off += 12 * (size_t)width * width;
+  *stride = (uint32_t)((off + 15) & ~size_t(15));
+}
+
 void ecb_set_error(const std::string& msg);
 ecbError ecb_import_bvh4(const ecbImportDesc* desc, ecbScene** out);
 ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out);

@@ -123,6 +123,34 @@ ECB_API ecbError ecbSceneUpload(ecbScene* scene, int device);
 ECB_API ecbError ecbSceneGetInfo(const ecbScene* scene, ecbSceneInfo* info);
 ECB_API void ecbSceneRelease(ecbScene* scene);
 
+/* ---- block construction on the GPU (the step in front of the path) -------------------------------
+ * Builds n compressed blocks from their displaced vertex grids and frames, exactly as CompressedBVH::CompressedBVH does
+ * (kernels/geometry/compressed.h:128-337: homography, box hierarchy, Node::setAABB quantization against re-expanded
+ * parents, frustum box, conservative world bounds, pizza-box leaves), in the device format.  What stays on the host is
+ * what needs the application: subdivision + displacement callbacks (evalGrid) and the 3x3 block frame (compressed.h:91-126).
+ * All pointers are HOST pointers; the work runs on the GPU (no CPU fallback). */
+typedef struct ecbBuildDesc {
+  uint32_t leaf_kind;        /* ecbLeafKind */
+  uint32_t comp_level;       /* C: blocks of 2^C x 2^C cells, (2^C+1)^2 vertices */
+  uint32_t n_blocks;
+  uint32_t reserved;
+  const float* grids;        /* n x (2^C+1)^2 x 3: displaced vertices of each block, row-major y*width+x */
+  const float* space;        /* n x 9: LinearSpace3f world->local of each block (vx,vy,vz columns), compressed.h:125-126 */
+  const float* world;        /* n x 9: LinearSpace3f(vx,vy,vz) it was inverted from */
+  const float* uv;           /* n x 4: patch uv of vertex (0,0) and uv extent of the block (compressed.h:84-86) */
+  const uint32_t* geomIDs;   /* n */
+  const uint32_t* primIDs;   /* n */
+} ecbBuildDesc;
+/* bytes per block of the device format for a leaf kind / compression level (what blocks_out must hold per block) */
+ECB_API uint32_t ecbBlockStride(uint32_t leaf_kind, uint32_t comp_level);
+/* blocks_out: n x ecbBlockStride bytes; bounds_out: n x 6 floats (lower xyz, upper xyz: the PrimRef bounds the host's
+ * top-level BVH4 builder needs, compressed.h:252-264); patch_ok_out: optional, n flags (homography applicable). */
+ECB_API ecbError ecbBuildBlocks(const ecbBuildDesc* desc, void* blocks_out, float* bounds_out, uint32_t* patch_ok_out);
+/* Host copy of a scene's converted blocks (n_blocks x block_stride bytes, ecbSceneGetInfo), and the reverse: install
+ * blocks built by ecbBuildBlocks into a scene that is not yet resident (same count, kind and level). */
+ECB_API ecbError ecbSceneCopyBlocks(const ecbScene* scene, void* blocks_out, size_t capacity_bytes);
+ECB_API ecbError ecbSceneSetBlocks(ecbScene* scene, const void* blocks, size_t bytes);
+
 /* ---- traversal, host buffers (drop-in semantics of the rtc* calls named above) ---------------------
  * rayhit / ray point to RTCRayHit (80 B) / RTCRay (48 B) structs, include/embree3/rtcore_ray.h:26-64, mutated in
  * place exactly like the reference does: on a hit tfar,Ng,u,v,primID,geomID,instID are overwritten, on a miss

@@ -100,6 +100,30 @@ void cbvh_inst_candidates1(const cbvh_inst_scene* scene, const cbvh_rayhit* rh, 
 void cbvh_inst_candidatesN(const cbvh_inst_scene* scene, const void* rayhits, size_t n, size_t stride, int nthreads, cbvh_candidates* out);
 double cbvh_inst_occludedN(const cbvh_inst_scene* scene, void* rays, size_t n, size_t stride, int nthreads, cbvh_stats* stats);
 
+/* ---- block construction, oracle/cbvh_build_port.c ---------------------------------------------------
+ * One compressed block from its displaced vertex grid and its frame; restates CompressedBVH::CompressedBVH
+ * (kernels/geometry/compressed.h:128-337).  comp_level <= 5. */
+typedef struct cbvh_build_in {
+  const float* grid;     /* (2^C+1)^2 x 3 floats, row-major y*width+x (compressed.h:69-77) */
+  float space[9];        /* LinearSpace3f world->local: vx, vy, vz columns (compressed.h:125-126) */
+  float world[9];        /* LinearSpace3f(vx,vy,vz) it was inverted from (only the world bounds need it) */
+  int32_t leaf_kind;     /* CBVH_LEAF_* */
+  int32_t comp_level;    /* C */
+} cbvh_build_in;
+
+typedef struct cbvh_build_out {
+  float proj[9];         /* homography, row-major */
+  float box[10];         /* frustum box */
+  float extent;          /* cLeaf only */
+  float bounds[6];       /* conservative world bounds: lower xyz, upper xyz */
+  int32_t patch_ok;      /* the projective mapping was applicable */
+  uint8_t nodes[4 * 341];   /* xz, x, yz, y per inner node (low two bits of x and y are zero here, unspecified in the reference) */
+  uint8_t leaves[2 * 1024]; /* z12, z34 per cell (cLeaf only) */
+} cbvh_build_out;
+
+void cbvh_build_block(const cbvh_build_in* in, cbvh_build_out* out);
+void cbvh_build_blocks(const cbvh_build_in* in, cbvh_build_out* out, size_t n, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,13 +29,13 @@ LEAF_KINDS = {"grid": 0, "leaf": 1, "box": 2}
 
 def build_port(force=False):
     """gcc the C restatement (no contraction: see cbvh_port.h)."""
-    src = os.path.join(HERE, "cbvh_port.c")
+    srcs = [os.path.join(HERE, "cbvh_port.c"), os.path.join(HERE, "cbvh_build_port.c")]
     os.makedirs(REF_DIR, exist_ok=True)
-    if (not force and os.path.exists(PORT_SO) and os.path.getmtime(PORT_SO) >= os.path.getmtime(src)
-            and os.path.getmtime(PORT_SO) >= os.path.getmtime(os.path.join(HERE, "cbvh_port.h"))):
+    deps = srcs + [os.path.join(HERE, "cbvh_port.h")]
+    if not force and os.path.exists(PORT_SO) and all(os.path.getmtime(PORT_SO) >= os.path.getmtime(d) for d in deps):
         return PORT_SO
-    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wall", "-o", PORT_SO, src,
-                    "-lm"], check=True)
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wall", "-o", PORT_SO] + srcs +
+                   ["-lm"], check=True)
     return PORT_SO
 
 

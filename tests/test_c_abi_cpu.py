@@ -138,3 +138,26 @@ def test_argument_checks(ecb):
     with pytest.raises(ValueError):
         scene.intersect1M(np.zeros((4, 20), np.float64))
     scene.intersect1M(np.zeros((0, 20), np.float32))  # M == 0 is a no-op on any machine
+
+
+def test_block_layout_and_block_exchange(ecb):
+    """ecbBlockStride / ecbSceneCopyBlocks / ecbSceneSetBlocks are host logic (the builder kernel itself needs the GPU)."""
+    lib = ecb._lib()
+    assert lib.ecbBlockStride(ecb.LEAF_LEAF, 3) == 352 and lib.ecbBlockStride(ecb.LEAF_BOX, 3) == 224
+    assert lib.ecbBlockStride(ecb.LEAF_GRID, 3) == 224 + 976 and lib.ecbBlockStride(3, 3) == 0 and lib.ecbBlockStride(1, 0) == 0
+    scene = ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8))
+    info = scene.info()
+    blocks = scene.copy_blocks()
+    assert blocks.shape == (info["n_blocks"], info["block_stride"]) and info["block_stride"] == lib.ecbBlockStride(1, 2)
+    scene.set_blocks(blocks)
+    with pytest.raises(ecb.EcbError):
+        scene.set_blocks(blocks[:-1])
+    with pytest.raises(ecb.EcbError) as e:   # the builder has no CPU fallback either
+        try:
+            import torch
+            if torch.cuda.is_available():
+                raise ecb.EcbError(ecb.ERROR_NO_DEVICE, "skip", "")
+        except ImportError:
+            pass
+        ecb.build_blocks("leaf", 2, np.zeros((1, 75)), np.zeros((1, 9)), np.zeros((1, 9)), np.zeros((1, 4)), [0], [0])
+    assert e.value.code == ecb.ERROR_NO_DEVICE
