@@ -835,40 +835,34 @@ ecbError ecbBuildBlocks(const ecbBuildDesc* d, void* blocks_out, float* bounds_o
   b.comp_level = d->comp_level;
   b.leaf_kind = d->leaf_kind;
   const size_t grid_bytes = (size_t)n * W * W * 12, out_bytes = (size_t)n * b.stride;
-  void* dev[9] = {};
-  auto release = [&] { for (void* p : dev) if (p) cudaFree(p); };
-  auto up = [&](int slot, const void* src, size_t bytes) -> cudaError_t {
-    cudaError_t e = cudaMalloc(&dev[slot], bytes);
-    if (e == cudaSuccess && src) e = cudaMemcpy(dev[slot], src, bytes, cudaMemcpyHostToDevice);
-    return e;
-  };
-  ce = up(0, d->grids, grid_bytes);
-  if (ce == cudaSuccess) ce = up(1, d->space, (size_t)n * 36);
-  if (ce == cudaSuccess) ce = up(2, d->world, (size_t)n * 36);
-  if (ce == cudaSuccess) ce = up(3, d->uv, (size_t)n * 16);
-  if (ce == cudaSuccess) ce = up(4, d->geomIDs, (size_t)n * 4);
-  if (ce == cudaSuccess) ce = up(5, d->primIDs, (size_t)n * 4);
-  if (ce == cudaSuccess) ce = up(6, nullptr, out_bytes);
-  if (ce == cudaSuccess) ce = up(7, nullptr, (size_t)n * 24);
-  if (ce == cudaSuccess) ce = up(8, nullptr, (size_t)n * 4);
-  if (ce == cudaSuccess) ce = cudaMemset(dev[6], 0, out_bytes);
+  // one device allocation, carved into the ten arrays (256-byte aligned)
+  const size_t sizes[10] = {grid_bytes, (size_t)n * 36, (size_t)n * 36, (size_t)n * 16, (size_t)n * 4, (size_t)n * 4,
+                            out_bytes, (size_t)n * 24, (size_t)n * 4, ecb_build_tmp_bytes(n)};
+  size_t offs[10], total = 0;
+  for (int i = 0; i < 10; i++) { offs[i] = total; total += (sizes[i] + 255) & ~size_t(255); }
+  uint8_t* base = nullptr;
+  ce = cudaMalloc(reinterpret_cast<void**>(&base), total);
+  const void* srcs[6] = {d->grids, d->space, d->world, d->uv, d->geomIDs, d->primIDs};
+  for (int i = 0; i < 6 && ce == cudaSuccess; i++) ce = cudaMemcpyAsync(base + offs[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, nullptr);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(base + offs[6], 0, out_bytes, nullptr);
   if (ce == cudaSuccess) {
-    b.grids = static_cast<const float*>(dev[0]);
-    b.space = static_cast<const float*>(dev[1]);
-    b.world = static_cast<const float*>(dev[2]);
-    b.uv = static_cast<const float*>(dev[3]);
-    b.geomIDs = static_cast<const uint32_t*>(dev[4]);
-    b.primIDs = static_cast<const uint32_t*>(dev[5]);
-    b.blocks = static_cast<uint8_t*>(dev[6]);
-    b.bounds = static_cast<float*>(dev[7]);
-    b.patch_ok = static_cast<uint32_t*>(dev[8]);
+    b.grids = reinterpret_cast<const float*>(base + offs[0]);
+    b.space = reinterpret_cast<const float*>(base + offs[1]);
+    b.world = reinterpret_cast<const float*>(base + offs[2]);
+    b.uv = reinterpret_cast<const float*>(base + offs[3]);
+    b.geomIDs = reinterpret_cast<const uint32_t*>(base + offs[4]);
+    b.primIDs = reinterpret_cast<const uint32_t*>(base + offs[5]);
+    b.blocks = base + offs[6];
+    b.bounds = reinterpret_cast<float*>(base + offs[7]);
+    b.patch_ok = reinterpret_cast<uint32_t*>(base + offs[8]);
+    b.tmp = base + offs[9];
     ce = ecb_launch_build(b, device, nullptr);
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(d->leaf_kind == ECB_LEAF_GRID ? 3 : 5);
   }
-  if (ce == cudaSuccess) ce = cudaMemcpy(blocks_out, dev[6], out_bytes, cudaMemcpyDeviceToHost);
-  if (ce == cudaSuccess) ce = cudaMemcpy(bounds_out, dev[7], (size_t)n * 24, cudaMemcpyDeviceToHost);
-  if (ce == cudaSuccess && patch_ok_out) ce = cudaMemcpy(patch_ok_out, dev[8], (size_t)n * 4, cudaMemcpyDeviceToHost);
-  release();
+  if (ce == cudaSuccess) ce = cudaMemcpy(blocks_out, base + offs[6], out_bytes, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = cudaMemcpy(bounds_out, base + offs[7], (size_t)n * 24, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && patch_ok_out) ce = cudaMemcpy(patch_ok_out, base + offs[8], (size_t)n * 4, cudaMemcpyDeviceToHost);
+  if (base) cudaFree(base);
   if (ce != cudaSuccess) return cuda_fail(ce, "ecbBuildBlocks");
   return ECB_SUCCESS;
 }

@@ -1,7 +1,7 @@
 // ecb_build.cu -- construction of compressed blocks on the GPU (the step in front of the traversal path).
 //
-// One CTA builds one block from its displaced vertex grid and its frame, directly in the device format of
-// ecb_format.h.  Restates what CompressedBVH::CompressedBVH (kernels/geometry/compressed.h:128-337) does once the grid
+// Builds blocks from their displaced vertex grids and frames, directly in the device format of ecb_format.h
+// (one CTA per block for the per-vertex / per-cell / per-node work, one thread per block for the two 8x8 solves).  Restates what CompressedBVH::CompressedBVH (kernels/geometry/compressed.h:128-337) does once the grid
 // has been evaluated and the frame chosen:
 //   homography            ComputeLinearEstimate / project             kernels/geometry/compressed_help.h:54-90
 //   monotonicity test, fall-back scaling                              compressed.h:147-210
@@ -261,6 +261,16 @@ __device__ void reduce_box(Box3& b, float* scratch /* 6 x warps */) {
   __syncthreads();
 }
 
+// Per-block scratch that carries the (tiny) serial part between the phases.
+struct BuildTmp {
+  float lBox[6];      // bounds of the local vertices
+  float pBox[6];      // bounds of the vertices under the first homography estimate
+  float corners[8];   // local xy of the four corner vertices
+  float proj[9];      // first estimate, later the final homography (row-major)
+  float iproj[9];
+  int ok;             // the projective mapping is (still) applicable
+};
+
 struct BuildArgs {
   const float* grids;      // n x W*W x 3
   const float* space;      // n x 9
@@ -271,38 +281,43 @@ struct BuildArgs {
   uint8_t* blocks;         // n x stride, device format
   float* bounds;           // n x 6
   uint32_t* patch_ok;      // n (optional)
+  BuildTmp* tmp;           // n
   uint32_t n, C, leaf_kind, stride, leaf_offset;
 };
 
-__global__ void __launch_bounds__(kBuildThreads) ecb_build_blocks_kernel(BuildArgs a) {
-  extern __shared__ float smem[];
-  const unsigned C = a.C, W = (1u << C) + 1u, nv = W * W, cells = 1u << (2 * C), elems = (cells - 1) / 3;
-  float* pv = smem;                                   // nv x 3: local, later projected vertices
-  Box3* heap = reinterpret_cast<Box3*>(smem + 3 * nv);  // elems + cells boxes, heap order (children of n: 4n+1..4n+4)
-  float* scratch = reinterpret_cast<float*>(heap + elems + cells);  // 6 x warps
-  __shared__ float s_space[9], s_world[9], s_proj[9], s_iproj[9];
-  __shared__ int s_flag;
-  __shared__ float s_extent;
-  const unsigned tid = threadIdx.x, T = blockDim.x;
+// The construction runs in five launches so that the two 8x8 solves per block -- serial, double precision, ~90 % of the
+// instructions when one thread of a CTA does them while the others wait -- run ONE THREAD PER BLOCK across the whole
+// grid instead (phases B and D); the vertex / cell / node parallel work is phases A, C and E (one CTA per block).
 
+// local coordinates of every vertex of block `blk` into pv (nv x 3)
+__device__ __forceinline__ void local_vertices(const BuildArgs& a, unsigned blk, unsigned nv, const float* s_space, float* pv) {
+  const float* v = a.grids + (size_t)blk * nv * 3;
+  for (unsigned i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float p[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+    float l[3];
+    xfm_point(s_space, p, l);
+    pv[3 * i] = l[0]; pv[3 * i + 1] = l[1]; pv[3 * i + 2] = l[2];
+  }
+}
+
+// Phase A: monotonicity test per cell and bounds of the local vertices (compressed.h:148-166)
+__global__ void __launch_bounds__(kBuildThreads) ecb_build_phase_a(BuildArgs a) {
+  extern __shared__ float smem[];
+  const unsigned C = a.C, W = (1u << C) + 1u, nv = W * W, cells = 1u << (2 * C);
+  float* pv = smem;
+  float* scratch = smem + 3 * nv;
+  __shared__ float s_space[9];
+  __shared__ int s_flag;
+  const unsigned tid = threadIdx.x, T = blockDim.x;
   for (unsigned blk = blockIdx.x; blk < a.n; blk += gridDim.x) {
-    const float* v = a.grids + (size_t)blk * nv * 3;
-    uint8_t* out = a.blocks + (size_t)blk * a.stride;
-    if (tid < 9) { s_space[tid] = a.space[(size_t)blk * 9 + tid]; s_world[tid] = a.world[(size_t)blk * 9 + tid]; }
+    if (tid < 9) s_space[tid] = a.space[(size_t)blk * 9 + tid];
     if (tid == 0) s_flag = 0;
     __syncthreads();
-
-    // local coordinates of every vertex, their bounds, and the monotonicity test per cell (compressed.h:148-166)
+    local_vertices(a, blk, nv, s_space, pv);
+    __syncthreads();
     Box3 lBox;
     box_empty(lBox);
-    for (unsigned i = tid; i < nv; i += T) {
-      const float p[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
-      float l[3];
-      xfm_point(s_space, p, l);
-      pv[3 * i] = l[0]; pv[3 * i + 1] = l[1]; pv[3 * i + 2] = l[2];
-      box_extend_p(lBox, l);
-    }
-    __syncthreads();
+    for (unsigned i = tid; i < nv; i += T) box_extend_p(lBox, pv + 3 * i);
     bool bad = false;
     for (unsigned i = tid; i < cells; i += T) {
       const unsigned x = i % (W - 1), y = i / (W - 1);
@@ -313,49 +328,112 @@ __global__ void __launch_bounds__(kBuildThreads) ecb_build_blocks_kernel(BuildAr
       if (v00[0] > v10[0] || v01[0] > v11[0] || v00[1] > v01[1] || v10[1] > v11[1]) bad = true;
     }
     if (bad) s_flag = 1;
-    reduce_box(lBox, scratch);  // contains the barriers that publish s_flag
-    bool patch_ok = a.leaf_kind != 0 /* `!use_grid && true` (:148) */ && s_flag == 0;
+    reduce_box(lBox, scratch);  // its barriers publish s_flag
+    if (tid == 0) {
+      BuildTmp& t = a.tmp[blk];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { t.lBox[k] = lBox.lo[k]; t.lBox[3 + k] = lBox.hi[k]; }
+      const unsigned idx[4] = {0, W - 1, W * (W - 1), W * W - 1};
+      for (int c = 0; c < 4; c++) { t.corners[2 * c] = pv[3 * idx[c]]; t.corners[2 * c + 1] = pv[3 * idx[c] + 1]; }
+      t.ok = (a.leaf_kind != 0 /* `!use_grid && true` (:148) */ && s_flag == 0) ? 1 : 0;
+    }
     __syncthreads();
+  }
+}
 
-    // first estimate from the four corners, test it on every vertex (compressed.h:171-187)
-    if (patch_ok) {
-      if (tid == 0) {
-        const unsigned i00 = 0, i10 = W - 1, i01 = W * (W - 1), i11 = W * W - 1;
-        const float src[4][2] = {{pv[3 * i00], pv[3 * i00 + 1]}, {pv[3 * i10], pv[3 * i10 + 1]},
-                                 {pv[3 * i01], pv[3 * i01 + 1]}, {pv[3 * i11], pv[3 * i11 + 1]}};
-        linear_estimate(src, s_proj);
-        s_flag = 0;
-      }
-      __syncthreads();
-      Box3 pBox;
-      box_empty(pBox);
-      bool broke = false;
-      for (unsigned i = tid; i < nv; i += T) {
-        float p[3];
-        project_p(s_proj, pv + 3 * i, p);
-        if (!isfinite(p[0]) || !isfinite(p[1]) || p[0] < -1.5f || p[0] > 1.5f || p[1] < -1.5f || p[1] > 1.5f) broke = true;
-        box_extend_p(pBox, p);
-      }
-      if (broke) s_flag = 1;
-      reduce_box(pBox, scratch);
-      patch_ok = s_flag == 0;
-      __syncthreads();
-      if (tid == 0) {
-        if (patch_ok) {  // :189-199
-          const float s2[4][2] = {{pBox.lo[0], pBox.lo[1]}, {pBox.hi[0], pBox.lo[1]}, {pBox.lo[0], pBox.hi[1]}, {pBox.hi[0], pBox.hi[1]}};
-          float scale[9], tmp[9];
-          linear_estimate(s2, scale);
-          for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) tmp[3 * i + j] = (scale[3 * i] * s_proj[j] + scale[3 * i + 1] * s_proj[3 + j]) + scale[3 * i + 2] * s_proj[6 + j];
-          for (int i = 0; i < 9; i++) s_proj[i] = tmp[i];
-        }
-      }
+// Phase B: first homography estimate from the four corners, one thread per block (compressed.h:171)
+__global__ void __launch_bounds__(128) ecb_build_phase_b(BuildArgs a) {
+  const unsigned blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= a.n) return;
+  BuildTmp& t = a.tmp[blk];
+  if (!t.ok) return;
+  const float src[4][2] = {{t.corners[0], t.corners[1]}, {t.corners[2], t.corners[3]}, {t.corners[4], t.corners[5]}, {t.corners[6], t.corners[7]}};
+  float M[9];
+  linear_estimate(src, M);
+  for (int i = 0; i < 9; i++) t.proj[i] = M[i];
+}
+
+// Phase C: the first estimate applied to every vertex: range test and projected bounds (compressed.h:173-186)
+__global__ void __launch_bounds__(kBuildThreads) ecb_build_phase_c(BuildArgs a) {
+  extern __shared__ float smem[];
+  const unsigned C = a.C, W = (1u << C) + 1u, nv = W * W;
+  float* pv = smem;
+  float* scratch = smem + 3 * nv;
+  __shared__ float s_space[9], s_proj[9];
+  __shared__ int s_flag;
+  const unsigned tid = threadIdx.x, T = blockDim.x;
+  for (unsigned blk = blockIdx.x; blk < a.n; blk += gridDim.x) {
+    if (!a.tmp[blk].ok) continue;  // uniform per CTA
+    if (tid < 9) { s_space[tid] = a.space[(size_t)blk * 9 + tid]; s_proj[tid] = a.tmp[blk].proj[tid]; }
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    local_vertices(a, blk, nv, s_space, pv);
+    __syncthreads();
+    Box3 pBox;
+    box_empty(pBox);
+    bool broke = false;
+    for (unsigned i = tid; i < nv; i += T) {
+      float p[3];
+      project_p(s_proj, pv + 3 * i, p);
+      if (!isfinite(p[0]) || !isfinite(p[1]) || p[0] < -1.5f || p[0] > 1.5f || p[1] < -1.5f || p[1] > 1.5f) broke = true;
+      box_extend_p(pBox, p);
     }
-    if (!patch_ok && tid == 0) {  // :200-210
-      const float s2[4][2] = {{lBox.lo[0], lBox.lo[1]}, {lBox.hi[0], lBox.lo[1]}, {lBox.lo[0], lBox.hi[1]}, {lBox.hi[0], lBox.hi[1]}};
-      linear_estimate(s2, s_proj);
+    if (broke) s_flag = 1;
+    reduce_box(pBox, scratch);
+    if (tid == 0) {
+      BuildTmp& t = a.tmp[blk];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { t.pBox[k] = pBox.lo[k]; t.pBox[3 + k] = pBox.hi[k]; }
+      if (s_flag) t.ok = 0;
     }
-    if (tid == 0) mat3_inverse(s_proj, s_iproj);
+    __syncthreads();
+  }
+}
+
+// Phase D: final homography and its inverse, one thread per block (compressed.h:189-214)
+__global__ void __launch_bounds__(128) ecb_build_phase_d(BuildArgs a) {
+  const unsigned blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= a.n) return;
+  BuildTmp& t = a.tmp[blk];
+  float proj[9];
+  if (t.ok) {
+    const float s2[4][2] = {{t.pBox[0], t.pBox[1]}, {t.pBox[3], t.pBox[1]}, {t.pBox[0], t.pBox[4]}, {t.pBox[3], t.pBox[4]}};
+    float scale[9];
+    linear_estimate(s2, scale);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) proj[3 * i + j] = (scale[3 * i] * t.proj[j] + scale[3 * i + 1] * t.proj[3 + j]) + scale[3 * i + 2] * t.proj[6 + j];
+  } else {
+    const float s2[4][2] = {{t.lBox[0], t.lBox[1]}, {t.lBox[3], t.lBox[1]}, {t.lBox[0], t.lBox[4]}, {t.lBox[3], t.lBox[4]}};
+    linear_estimate(s2, proj);
+  }
+  float iproj[9];
+  mat3_inverse(proj, iproj);
+  for (int i = 0; i < 9; i++) { t.proj[i] = proj[i]; t.iproj[i] = iproj[i]; }
+  if (a.patch_ok) a.patch_ok[blk] = t.ok ? 1u : 0u;
+}
+
+// Phase E: projected vertices, box hierarchy, quantization, bounds, frustum box, leaves -> the block in the device format
+__global__ void __launch_bounds__(kBuildThreads) ecb_build_phase_e(BuildArgs a) {
+  extern __shared__ float smem[];
+  const unsigned C = a.C, W = (1u << C) + 1u, nv = W * W, cells = 1u << (2 * C), elems = (cells - 1) / 3;
+  float* pv = smem;                                   // nv x 3: local, then projected vertices
+  Box3* heap = reinterpret_cast<Box3*>(smem + 3 * nv);  // elems + cells boxes, heap order (children of n: 4n+1..4n+4)
+  float* scratch = reinterpret_cast<float*>(heap + elems + cells);  // 6 x warps
+  __shared__ float s_space[9], s_world[9], s_proj[9], s_iproj[9];
+  __shared__ float s_extent;
+  const unsigned tid = threadIdx.x, T = blockDim.x;
+
+  for (unsigned blk = blockIdx.x; blk < a.n; blk += gridDim.x) {
+    const float* v = a.grids + (size_t)blk * nv * 3;
+    uint8_t* out = a.blocks + (size_t)blk * a.stride;
+    if (tid < 9) {
+      s_space[tid] = a.space[(size_t)blk * 9 + tid];
+      s_world[tid] = a.world[(size_t)blk * 9 + tid];
+      s_proj[tid] = a.tmp[blk].proj[tid];
+      s_iproj[tid] = a.tmp[blk].iproj[tid];
+    }
+    __syncthreads();
+    local_vertices(a, blk, nv, s_space, pv);
     __syncthreads();
 
     // projected vertices, leaf boxes in Morton order, bottom-up merge (build_box_hierarchy, :381-405)
@@ -450,7 +528,6 @@ __global__ void __launch_bounds__(kBuildThreads) ecb_build_blocks_kernel(BuildAr
       if (a.leaf_kind != 1) hdr->extent = 0.f;
 #pragma unroll
       for (int k = 0; k < 3; k++) { a.bounds[(size_t)blk * 6 + k] = bounds.lo[k]; a.bounds[(size_t)blk * 6 + 3 + k] = bounds.hi[k]; }
-      if (a.patch_ok) a.patch_ok[blk] = patch_ok ? 1u : 0u;
     }
 
     if (a.leaf_kind == 1) {  // pizza-box leaves (:296-326)
@@ -513,16 +590,29 @@ __global__ void __launch_bounds__(kBuildThreads) ecb_build_blocks_kernel(BuildAr
 cudaError_t ecb_launch_build(const EcbBuildLaunch& b, int device, cudaStream_t stream) {
   if (b.n == 0) return cudaSuccess;
   const unsigned W = (1u << b.comp_level) + 1u, cells = 1u << (2 * b.comp_level), elems = (cells - 1) / 3;
-  const size_t smem = (size_t)3 * W * W * 4 + (size_t)(elems + cells) * sizeof(Box3) + 6 * (kBuildThreads / 32) * 4;
-  cudaError_t e = cudaFuncSetAttribute(ecb_build_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem_v = (size_t)3 * W * W * 4 + 6 * (kBuildThreads / 32) * 4;
+  const size_t smem_e = (size_t)3 * W * W * 4 + (size_t)(elems + cells) * sizeof(Box3) + 6 * (kBuildThreads / 32) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ecb_build_phase_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
   if (e != cudaSuccess) return e;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const unsigned grid = b.n < (unsigned)sms * 8u ? b.n : (unsigned)sms * 8u;
+  // a block of 2^C x 2^C cells has (2^C+1)^2 vertices: 81 / 289 / 1089 for C = 3 / 4 / 5
+  const unsigned threads = b.comp_level <= 3 ? 64u : (unsigned)kBuildThreads;
+  const unsigned per_sm = 2048u / threads < 16u ? 2048u / threads : 16u;
+  const unsigned grid = b.n < (unsigned)sms * per_sm ? b.n : (unsigned)sms * per_sm;
+  const unsigned grid_t = (b.n + 127u) / 128u;
   BuildArgs a;
   a.grids = b.grids; a.space = b.space; a.world = b.world; a.uv = b.uv; a.geomIDs = b.geomIDs; a.primIDs = b.primIDs;
-  a.blocks = b.blocks; a.bounds = b.bounds; a.patch_ok = b.patch_ok;
+  a.blocks = b.blocks; a.bounds = b.bounds; a.patch_ok = b.patch_ok; a.tmp = static_cast<BuildTmp*>(b.tmp);
   a.n = b.n; a.C = b.comp_level; a.leaf_kind = b.leaf_kind; a.stride = b.stride; a.leaf_offset = b.leaf_offset;
-  ecb_build_blocks_kernel<<<grid, kBuildThreads, smem, stream>>>(a);
+  ecb_build_phase_a<<<grid, threads, smem_v, stream>>>(a);
+  if (b.leaf_kind != 0) {  // cGrid never uses the projective mapping: no first estimate to compute or test
+    ecb_build_phase_b<<<grid_t, 128, 0, stream>>>(a);
+    ecb_build_phase_c<<<grid, threads, smem_v, stream>>>(a);
+  }
+  ecb_build_phase_d<<<grid_t, 128, 0, stream>>>(a);
+  ecb_build_phase_e<<<grid, threads, smem_e, stream>>>(a);
   return cudaGetLastError();
 }
+
+size_t ecb_build_tmp_bytes(uint32_t n) { return (size_t)n * sizeof(BuildTmp); }

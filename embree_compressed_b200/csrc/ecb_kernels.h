@@ -61,6 +61,8 @@ struct EcbBuildLaunch {
   uint8_t* blocks;           // n x stride, zero-initialised by the caller; receives blocks in the device format
   float* bounds;             // n x 6 conservative world bounds
   uint32_t* patch_ok;        // optional, n
+  void* tmp;                 // ecb_build_tmp_bytes(n) bytes of scratch
   uint32_t n, comp_level, leaf_kind, stride, leaf_offset;
 };
+size_t ecb_build_tmp_bytes(uint32_t n);
 cudaError_t ecb_launch_build(const EcbBuildLaunch& b, int device, cudaStream_t stream);
