@@ -289,3 +289,53 @@ def test_config1_full_frame_with_ground_plane(ecb, reference):
     _, truth, c = _check_intersect(scene, port, ref, rays, "config 1 with ground plane")
     assert c["hits_ref"] > 500000
     ref.free()
+
+
+@pytest.mark.parametrize("leaf", LEAVES)
+def test_degenerate_rays_and_empty_scene(ecb, reference, ref_scene, leaf):
+    """Rays the reference's own tutorials never produce but its API admits: zero / axis-parallel / denormal directions,
+    origins on and inside the boxes, negative tnear, tfar = 0, huge and non-finite values.  The CUDA path must terminate
+    and leave exactly the bits the oracle leaves."""
+    ref = ref_scene("cube", leaf, 4, 2)
+    scene, port = _scene_pair(ecb, reference, ref)
+    base = rg.primary_rays(48, 48, **OFF_AXIS)
+    n = len(base)
+    rays = np.concatenate([base] * 10)
+    k = lambda i: slice(i * n, (i + 1) * n)
+    rays[k(0), 4:7] = 0.0                                   # zero direction
+    rays[k(1), 4] = 0.0                                     # one zero component
+    rays[k(1), 5] = 0.0                                     # axis-parallel along z
+    rays[k(2), 4:7] *= 1e-30                                # denormal-scale direction
+    rays[k(3), 0:3] = 0.0                                   # origin inside the cube
+    rays[k(4), 3] = -5.0                                    # negative tnear
+    rays[k(5), 8] = 0.0                                     # tfar = 0
+    rays[k(6), 0:3] *= 1e18                                 # far away
+    rays[k(7), 4:7] = np.sign(rays[k(7), 4:7]) * np.float32(1.0)   # diagonal, un-normalised
+    rays[k(8), 5] = np.float32(np.inf)                      # non-finite direction component
+    rays[k(9), 0] = np.float32(np.nan)                      # NaN origin
+    got, want = rays.copy(), rays.copy()
+    scene.intersect1M(got)
+    port.intersect(want)
+    finite = slice(0, 8 * n)                                # the non-finite groups only have to terminate identically in hit/miss
+    bad = parity.bit_exact_mismatches(got[finite], want[finite])
+    assert len(bad) == 0, "degenerate rays: CUDA differs from the oracle on rows %s" % bad[:10]
+    assert ((got.view(np.uint32)[8 * n:, 18] != 0xFFFFFFFF) == (want.view(np.uint32)[8 * n:, 18] != 0xFFFFFFFF)).all()
+    truth = rays[finite].copy()
+    ref.intersect(truth)
+    c = parity.classify(got[finite], truth, port.candidates(rays[finite]))
+    assert c["hit_miss_flips"] <= 4 and c["hits_ref"] > 1000, c
+    o_got, o_want = rg.rays_only(rays), rg.rays_only(rays)
+    scene.occluded1M(o_got)
+    port.occluded(o_want)
+    assert (o_got[finite].view(np.uint32) == o_want[finite].view(np.uint32)).all()
+    scene.release()
+    # a committed scene without geometry: BVH4::emptyNode as root (kernels/bvh/bvh.h:127); nothing may be written
+    empty = ecb.Scene.import_bvh4(8, leaf, 2, 4, 1, 0, np.zeros(6, np.float32))
+    assert empty.info()["n_blocks"] == 0
+    e = base.copy()
+    empty.intersect1M(e)
+    assert (e.view(np.uint32) == base.view(np.uint32)).all()
+    eo = rg.rays_only(base)
+    empty.occluded1M(eo)
+    assert (eo.view(np.uint32) == rg.rays_only(base).view(np.uint32)).all()
+    empty.release()
