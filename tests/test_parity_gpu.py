@@ -339,3 +339,57 @@ def test_degenerate_rays_and_empty_scene(ecb, reference, ref_scene, leaf):
     empty.occluded1M(eo)
     assert (eo.view(np.uint32) == rg.rays_only(base).view(np.uint32)).all()
     empty.release()
+
+
+def test_concurrent_callers_on_one_scene(ecb, reference, ref_scene):
+    """rtcIntersect* / rtcOccluded* are re-entrant in the reference (kernels/common/rtcore.cpp:287-304: no locks, state
+    only in the ray): several user threads trace different ray sets through the same committed scene at once, host
+    buffers (compact-result pipeline + scatter pool) and device buffers mixed."""
+    import threading
+    import torch
+    ref = ref_scene("bomberman", "leaf", 6, 3)
+    scene, port = _scene_pair(ecb, reference, ref)
+    sets = [rg.primary_rays(640, 360, **rg.BOMBERMAN_CAMERA),
+            rg.incoherent_rays(200_000, ref.bounds(), seed=21),
+            rg.primary_rays(320, 200, **rg.BOMBERMAN_CAMERA)[::-1].copy(),
+            rg.incoherent_rays(50_000, ref.bounds(), seed=22)]
+    want = []
+    for r in sets:
+        w = r.copy()
+        port.intersect(w)
+        want.append(w)
+    got = [None] * len(sets)
+    errors = []
+
+    def host_worker(i):
+        try:
+            for _ in range(3):
+                g = sets[i].copy()
+                scene.intersect1M(g)
+                o = rg.rays_only(sets[i])
+                scene.occluded1M(o)
+            got[i] = g
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def device_worker(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    d = torch.from_numpy(sets[i]).cuda()
+                    scene.intersect_device(d.data_ptr(), len(sets[i]), 80, st.cuda_stream)
+                    st.synchronize()
+                got[i] = d.cpu().numpy()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=host_worker if i % 2 == 0 else device_worker, args=(i,)) for i in range(len(sets))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    for i in range(len(sets)):
+        assert got[i] is not None and (got[i].view(np.uint32) == want[i].view(np.uint32)).all(), "caller %d got wrong results" % i
+    scene.release()
