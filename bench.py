@@ -137,12 +137,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(leaf):
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if one exists."""
+def recorded_traffic(leaf, key=None):
+    """dram bytes per launch of the dominant kernel (or another recorded field) from the committed ncu summary."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(leaf)
+            return json.load(open(p)).get(key or leaf)
         except Exception:
             return None
     return None
@@ -277,6 +277,14 @@ def run_ours(args, rank, world):
                                  "bounce": {"top_nodes": round(c_bounce[1] / max(1, c_bounce[0]), 3), "blocks": round(c_bounce[2] / max(1, c_bounce[0]), 3),
                                             "cnodes": round(c_bounce[3] / max(1, c_bounce[0]), 3), "cells": round(c_bounce[4] / max(1, c_bounce[0]), 3)}},
                 "mrays_per_s": {"primary": round(n_prim / kernel_ms["primary"] / 1e3, 1), "bounce": round(n_bounce / kernel_ms["bounce"] / 1e3, 1)}}
+    # the memory roofline is not what limits this path (the scene is L2 resident); the informative figures are
+    # rays per SM-cycle (live, at the SM clock sampled during the timed region) and the issue / L2 counters of the ncu capture
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    roofline["rays_per_sm_cycle_live"] = {k: round((n_prim if k == "primary" else n_bounce) / (kernel_ms[k] * 1e-3 * sm_mhz * 1e6 * sm_count), 5)
+                                          for k in kernel_ms}
+    if args.leaf == "leaf" and (SUBDIV_LEVEL, COMP_LEVEL) == (6, 3):
+        roofline["ncu"] = recorded_traffic(args.leaf, "ncu_primary_pass")
 
     # ---- e2e: the reference-facing call with pinned host buffers, copies inside the timed region ----
     hp, hp_ptr = ecb.host_alloc(prim.nbytes)
