@@ -388,6 +388,18 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   };
   st->worker_error = cudaSuccess;
   const bool any_hit = occluded;  // exact any-hit runs through the occluded entry points as well
+  // whatever way this call ends (CUDA errors included), no scatter job may outlive it: they write into the caller's array
+  struct Drain {
+    Staging* st;
+    ~Drain() {
+      std::unique_lock<std::mutex> wl(st->mutex);
+      st->cv.wait(wl, [&] {
+        for (int k = 0; k < kStages; k++)
+          if (st->pending[k]) return false;
+        return true;
+      });
+    }
+  } drain{st};
 
   for (uint64_t c = 0; c < n_chunks; c++) {
     const int k = (int)(c % kStages);
