@@ -228,6 +228,51 @@ void packet_intersect(const int* valid, ShimScene* s, RTCIntersectContext* ctx, 
   }
 }
 
+// The remaining stream layouts of the API (rtcore_scene.h:112-142) are gathered into one AoS batch, traced with the
+// stream entry point and scattered back: pointer streams (1Mp), streams of N-wide SoA packets (NM) and pointer-SoA (Np).
+// `word(i, f)` returns the address of field f (0..19, RTCRayHit word order) of ray i.
+template <typename WordAt>
+void stream_any_layout(ShimScene* s, RTCIntersectContext* ctx, size_t n, bool occluded, WordAt word, const char* what) {
+  if (n == 0) return;
+  const int fields = occluded ? 12 : 20;
+  void* pinned = nullptr;
+  const size_t bytes = n * (size_t)fields * 4;
+  std::vector<uint32_t> pageable;
+  uint32_t* aos = nullptr;
+  if (bytes >= (1u << 20) && ecbHostAlloc(&pinned, bytes) == ECB_SUCCESS) aos = static_cast<uint32_t*>(pinned);
+  else { pageable.resize(n * (size_t)fields); aos = pageable.data(); }
+  for (size_t i = 0; i < n; i++)
+    for (int f = 0; f < fields; f++) aos[i * fields + f] = *word(i, f);
+  // gathered in chunks: the C ABI counts rays in 32 bits
+  ecbError e = ECB_SUCCESS;
+  for (size_t first = 0; first < n && e == ECB_SUCCESS; first += (1u << 30)) {
+    const uint32_t m = (uint32_t)((n - first) < (1u << 30) ? (n - first) : (1u << 30));
+    e = occluded ? ecbOccluded1M(s->gpu, ctx_inst(ctx), aos + first * fields, m, 48)
+                 : ecbIntersect1M(s->gpu, ctx_inst(ctx), aos + first * fields, m, 80);
+  }
+  check(s, e, what);
+  if (e == ECB_SUCCESS)
+    for (size_t i = 0; i < n; i++) {
+      *word(i, 8) = aos[i * fields + 8];  // tfar
+      if (!occluded)
+        for (int f = 12; f < 20; f++) *word(i, f) = aos[i * fields + f];
+    }
+  if (pinned) ecbHostFree(pinned);
+}
+
+uint32_t* np_word(const RTCRayNp& r, const RTCHitNp* h, size_t i, int f) {
+  float* const rf[9] = {r.org_x, r.org_y, r.org_z, r.tnear, r.dir_x, r.dir_y, r.dir_z, r.time, r.tfar};
+  if (f < 9) return reinterpret_cast<uint32_t*>(rf[f] + i);
+  if (f == 9) return r.mask + i;
+  if (f == 10) return r.id + i;
+  if (f == 11) return r.flags + i;
+  float* const hf[5] = {h->Ng_x, h->Ng_y, h->Ng_z, h->u, h->v};
+  if (f < 17) return reinterpret_cast<uint32_t*>(hf[f - 12] + i);
+  if (f == 17) return h->primID + i;
+  if (f == 18) return h->geomID + i;
+  return h->instID[0] + i;
+}
+
 }  // namespace
 
 extern "C" {
@@ -477,6 +522,42 @@ RTC_API void rtcOccluded8(const int* valid, RTCScene scene, RTCIntersectContext*
 }
 RTC_API void rtcOccluded16(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay16* r) {
   if (ready(S(scene), "rtcOccluded16")) packet_intersect<16>(valid, S(scene), ctx, r, true);
+}
+
+RTC_API void rtcIntersect1Mp(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit** rayhit, unsigned M) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcIntersect1Mp")) return;
+  stream_any_layout(s, ctx, M, false, [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(rayhit[i]) + f; }, "rtcIntersect1Mp");
+}
+RTC_API void rtcOccluded1Mp(RTCScene scene, RTCIntersectContext* ctx, RTCRay** ray, unsigned M) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcOccluded1Mp")) return;
+  stream_any_layout(s, ctx, M, true, [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(ray[i]) + f; }, "rtcOccluded1Mp");
+}
+// M packets of N rays in SoA layout, byteStride between packets (rtcore_scene.h:115,139)
+RTC_API void rtcIntersectNM(RTCScene scene, RTCIntersectContext* ctx, RTCRayHitN* rayhit, unsigned N, unsigned M, size_t byteStride) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcIntersectNM")) return;
+  uint8_t* base = reinterpret_cast<uint8_t*>(rayhit);
+  stream_any_layout(s, ctx, (size_t)N * M, false,
+                    [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(base + (i / N) * byteStride) + (size_t)f * N + (i % N); }, "rtcIntersectNM");
+}
+RTC_API void rtcOccludedNM(RTCScene scene, RTCIntersectContext* ctx, RTCRayN* ray, unsigned N, unsigned M, size_t byteStride) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcOccludedNM")) return;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ray);
+  stream_any_layout(s, ctx, (size_t)N * M, true,
+                    [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(base + (i / N) * byteStride) + (size_t)f * N + (i % N); }, "rtcOccludedNM");
+}
+RTC_API void rtcIntersectNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayHitNp* rayhit, unsigned N) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcIntersectNp")) return;
+  stream_any_layout(s, ctx, N, false, [&](size_t i, int f) { return np_word(rayhit->ray, &rayhit->hit, i, f); }, "rtcIntersectNp");
+}
+RTC_API void rtcOccludedNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayNp* ray, unsigned N) {
+  ShimScene* s = S(scene);
+  if (!ready(s, "rtcOccludedNp")) return;
+  stream_any_layout(s, ctx, N, true, [&](size_t i, int f) { return np_word(*ray, nullptr, i, f); }, "rtcOccludedNp");
 }
 
 RTC_API void* rtcAllocRays_b200(size_t bytes) {

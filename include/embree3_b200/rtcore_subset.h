@@ -60,6 +60,13 @@ RTC_B200_PACKET(4)
 RTC_B200_PACKET(8)
 RTC_B200_PACKET(16)
 
+/* streams of N-wide SoA packets (opaque: 12 / 20 arrays of N words, rtcore_ray.h:189-191) and pointer-SoA streams (:192-228) */
+struct RTCRayN;
+struct RTCRayHitN;
+struct RTCRayNp { float *org_x, *org_y, *org_z, *tnear, *dir_x, *dir_y, *dir_z, *time, *tfar; unsigned int *mask, *id, *flags; };
+struct RTCHitNp { float *Ng_x, *Ng_y, *Ng_z, *u, *v; unsigned int *primID, *geomID, *instID[RTC_MAX_INSTANCE_LEVEL_COUNT]; };
+struct RTCRayHitNp { struct RTCRayNp ray; struct RTCHitNp hit; };
+
 struct __attribute__((aligned(16))) RTCBounds { float lower_x, lower_y, lower_z, align0, upper_x, upper_y, upper_z, align1; };
 struct RTCFilterFunctionNArguments;
 typedef void (*RTCFilterFunctionN)(const struct RTCFilterFunctionNArguments* args);
@@ -126,11 +133,17 @@ RTC_API void rtcIntersect4(const int* valid, RTCScene scene, struct RTCIntersect
 RTC_API void rtcIntersect8(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit8* rayhit);
 RTC_API void rtcIntersect16(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit16* rayhit);
 RTC_API void rtcIntersect1M(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit* rayhit, unsigned int M, size_t byteStride);
+RTC_API void rtcIntersect1Mp(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit** rayhit, unsigned int M);
+RTC_API void rtcIntersectNM(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHitN* rayhit, unsigned int N, unsigned int M, size_t byteStride);
+RTC_API void rtcIntersectNp(RTCScene scene, struct RTCIntersectContext* context, const struct RTCRayHitNp* rayhit, unsigned int N);
 RTC_API void rtcOccluded1(RTCScene scene, struct RTCIntersectContext* context, struct RTCRay* ray);
 RTC_API void rtcOccluded4(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay4* ray);
 RTC_API void rtcOccluded8(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay8* ray);
 RTC_API void rtcOccluded16(const int* valid, RTCScene scene, struct RTCIntersectContext* context, struct RTCRay16* ray);
 RTC_API void rtcOccluded1M(RTCScene scene, struct RTCIntersectContext* context, struct RTCRay* ray, unsigned int M, size_t byteStride);
+RTC_API void rtcOccluded1Mp(RTCScene scene, struct RTCIntersectContext* context, struct RTCRay** ray, unsigned int M);
+RTC_API void rtcOccludedNM(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayN* ray, unsigned int N, unsigned int M, size_t byteStride);
+RTC_API void rtcOccludedNp(RTCScene scene, struct RTCIntersectContext* context, const struct RTCRayNp* ray, unsigned int N);
 
 /* ---- additions of this repo ----------------------------------------------------------------------------------- */
 /* What the host Embree must export so that rtcCommitScene can hand the committed compressed accel to the plugin

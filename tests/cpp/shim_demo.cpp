@@ -2,7 +2,7 @@
 // (declarations from include/embree3_b200/rtcore_subset.h, which restate the reference's headers) and is linked
 // against libembree3_b200.so instead of libembree3.so.
 //
-//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin> [instanced|plane]
+//   shim_demo <leaf> <S> <C> <rays.bin> <out.bin> [instanced|plane|streams]
 // builds the displaced cube of tutorials/displacement_geometry through rtc* calls (subdivision mesh + displacement
 // callback), commits, and traces the RTCRayHit records of rays.bin four ways, writing one result block per way:
 //   [0] rtcIntersect1M   [1] rtcIntersect16 packets   [2] rtcIntersect1 per ray (first 64 rays)   [3] rtcOccluded1M
@@ -144,6 +144,68 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < n; i++) { r[i].ray = rays[i].ray; for (int k = 0; k < 4; k++) r[i].pad[k] = 7.f; }
     rtcOccluded1M(scene, &ctx, &r[0].ray, (unsigned)n, sizeof(Padded));
     for (size_t i = 0; i < n; i++) fwrite(&r[i], sizeof(Padded), 1, out);
+  }
+  if (argc > 6 && std::string(argv[6]) == "streams") {
+    // the other stream layouts of the API: each must give what rtcIntersect1M gave
+    {  // [4] rtcIntersect1Mp: array of pointers, here in reverse order
+      std::vector<RTCRayHit> r(rays);
+      std::vector<RTCRayHit*> ptr(n);
+      for (size_t i = 0; i < n; i++) ptr[i] = &r[n - 1 - i];
+      rtcIntersect1Mp(scene, &ctx, ptr.data(), (unsigned)n);
+      fwrite(r.data(), sizeof(RTCRayHit), n, out);
+    }
+    {  // [5] rtcIntersectNM: packets of N = 8 rays in SoA layout, 64 bytes of padding between packets
+      const unsigned N = 8;
+      const size_t M = n / N, stride = 20 * N * 4 + 64;
+      std::vector<unsigned char> buf(M * stride, 0x5a);
+      for (size_t i = 0; i < M * N; i++)
+        for (int fld = 0; fld < 20; fld++)
+          ((unsigned*)(buf.data() + (i / N) * stride))[fld * N + i % N] = ((const unsigned*)&rays[i])[fld];
+      rtcIntersectNM(scene, &ctx, (RTCRayHitN*)buf.data(), N, (unsigned)M, stride);
+      std::vector<RTCRayHit> r(M * N);
+      for (size_t i = 0; i < M * N; i++)
+        for (int fld = 0; fld < 20; fld++)
+          ((unsigned*)&r[i])[fld] = ((const unsigned*)(buf.data() + (i / N) * stride))[fld * N + i % N];
+      fwrite(r.data(), sizeof(RTCRayHit), M * N, out);
+      for (size_t p = 0; p < M; p++)
+        for (size_t b = 20 * N * 4; b < stride; b++)
+          if (buf[p * stride + b] != 0x5a) { fprintf(stderr, "rtcIntersectNM touched the padding\n"); return 7; }
+    }
+    {  // [6] rtcIntersectNp: one array per field
+      std::vector<std::vector<unsigned>> f(20, std::vector<unsigned>(n));
+      for (size_t i = 0; i < n; i++)
+        for (int fld = 0; fld < 20; fld++) f[fld][i] = ((const unsigned*)&rays[i])[fld];
+      RTCRayHitNp np;
+      np.ray.org_x = (float*)f[0].data(); np.ray.org_y = (float*)f[1].data(); np.ray.org_z = (float*)f[2].data();
+      np.ray.tnear = (float*)f[3].data(); np.ray.dir_x = (float*)f[4].data(); np.ray.dir_y = (float*)f[5].data();
+      np.ray.dir_z = (float*)f[6].data(); np.ray.time = (float*)f[7].data(); np.ray.tfar = (float*)f[8].data();
+      np.ray.mask = f[9].data(); np.ray.id = f[10].data(); np.ray.flags = f[11].data();
+      np.hit.Ng_x = (float*)f[12].data(); np.hit.Ng_y = (float*)f[13].data(); np.hit.Ng_z = (float*)f[14].data();
+      np.hit.u = (float*)f[15].data(); np.hit.v = (float*)f[16].data();
+      np.hit.primID = f[17].data(); np.hit.geomID = f[18].data(); np.hit.instID[0] = f[19].data();
+      rtcIntersectNp(scene, &ctx, &np, (unsigned)n);
+      std::vector<RTCRayHit> r(n);
+      for (size_t i = 0; i < n; i++)
+        for (int fld = 0; fld < 20; fld++) ((unsigned*)&r[i])[fld] = f[fld][i];
+      fwrite(r.data(), sizeof(RTCRayHit), n, out);
+      // [7] rtcOccludedNp on the same arrays restored to the input rays: tfar only
+      for (size_t i = 0; i < n; i++)
+        for (int fld = 0; fld < 12; fld++) f[fld][i] = ((const unsigned*)&rays[i])[fld];
+      rtcOccludedNp(scene, &ctx, &np.ray, (unsigned)n);
+      fwrite(f[8].data(), 4, n, out);
+      // [8] rtcOccluded1Mp / rtcOccludedNM (N = 4): tfar only
+      std::vector<RTCRay> o(n);
+      std::vector<RTCRay*> optr(n);
+      for (size_t i = 0; i < n; i++) { o[i] = rays[i].ray; optr[i] = &o[i]; }
+      rtcOccluded1Mp(scene, &ctx, optr.data(), (unsigned)n);
+      for (size_t i = 0; i < n; i++) fwrite(&o[i].tfar, 4, 1, out);
+      const unsigned N4 = 4;
+      std::vector<unsigned> soa(12 * n);
+      for (size_t i = 0; i < n / N4 * N4; i++)
+        for (int fld = 0; fld < 12; fld++) soa[(i / N4) * 12 * N4 + fld * N4 + i % N4] = ((const unsigned*)&rays[i])[fld];
+      rtcOccludedNM(scene, &ctx, (RTCRayN*)soa.data(), N4, (unsigned)(n / N4), 12 * N4 * 4);
+      for (size_t i = 0; i < n / N4 * N4; i++) fwrite(&soa[(i / N4) * 12 * N4 + 8 * N4 + i % N4], 4, 1, out);
+    }
   }
   fclose(out);
   const RTCError e = rtcGetDeviceError(device);

@@ -109,3 +109,29 @@ def test_mixed_scene_through_the_shim(ecb, reference, tmp_path):
     ref.occluded(o_truth)
     assert (occ[:, :12].view(np.uint32) == o_truth.view(np.uint32)).all()
     ref.free()
+
+
+def test_all_stream_layouts_through_the_shim(ecb, reference, ref_scene, tmp_path):
+    """rtcIntersect1Mp / NM / Np and rtcOccluded1Mp / NM / Np (include/embree3/rtcore_scene.h:112-142): every layout of
+    the stream API must give what rtcIntersect1M / rtcOccluded1M give on the same rays."""
+    cam = dict(vp=(1.6, 1.45, -1.35), vi=(0.05, -0.02, 0.03), vu=(0.0, 1.0, 0.0), fov=90.0)
+    rays = rg.primary_rays(160, 128, **cam)
+    n = len(rays)
+    rays_path, out_path = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rays_path)
+    env = dict(os.environ, ECB200_HOST_EMBREE=reference.REF_SO)
+    r = subprocess.run([DEMO, "leaf", "5", "3", rays_path, out_path, "streams"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.float32)
+    n_pk, n_one = min(n // 16, 32) * 16, min(n, 64)
+    sizes = [n * 20, n_pk * 20, n_one * 20, n * 16, n * 20, (n // 8) * 8 * 20, n * 20, n, n, (n // 4) * 4]
+    assert raw.size == sum(sizes), (raw.size, sum(sizes))
+    parts = np.split(raw, np.cumsum(sizes)[:-1])
+    stream = parts[0].reshape(n, 20)
+    occ = parts[3].reshape(n, 16)[:, 8]
+    assert (stream.view(np.uint32)[:, 18] != 0xFFFFFFFF).sum() > 5000
+    for name, part, m in (("1Mp", parts[4], n), ("NM", parts[5], (n // 8) * 8), ("Np", parts[6], n)):
+        got = part.reshape(m, 20)
+        assert (got.view(np.uint32) == stream[:m].view(np.uint32)).all(), "rtcIntersect%s differs from rtcIntersect1M" % name
+    for name, part in (("Np", parts[7]), ("1Mp", parts[8]), ("NM", parts[9])):
+        assert (part.view(np.uint32) == occ[:len(part)].view(np.uint32)).all(), "rtcOccluded%s differs from rtcOccluded1M" % name
