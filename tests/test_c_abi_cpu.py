@@ -161,3 +161,26 @@ def test_block_layout_and_block_exchange(ecb):
             pass
         ecb.build_blocks("leaf", 2, np.zeros((1, 75)), np.zeros((1, 9)), np.zeros((1, 9)), np.zeros((1, 4)), [0], [0])
     assert e.value.code == ecb.ERROR_NO_DEVICE
+
+
+def test_shim_exports_every_declared_embree3_symbol(ecb):
+    """include/embree3_b200/rtcore_subset.h declares the embree3 entry points of this path (signatures of the reference's
+    include/embree3/*.h); libembree3_b200.so must export each of them -- loading needs neither a GPU nor a host Embree."""
+    text = open(os.path.join(ROOT, "include", "embree3_b200", "rtcore_subset.h")).read()
+    declared = sorted(set(re.findall(r"RTC_API\s+[\w\s\*]+?\b(rtc\w+)\s*\(", text)))
+    assert len(declared) >= 55, declared
+    for must in ("rtcNewScene", "rtcSetSceneLevels", "rtcCommitScene", "rtcIntersect1", "rtcIntersect16", "rtcIntersect1M",
+                 "rtcIntersect1Mp", "rtcIntersectNM", "rtcIntersectNp", "rtcOccluded1", "rtcOccluded1M", "rtcOccludedNp"):
+        assert must in declared
+    shim = C.CDLL(os.path.join(os.path.dirname(ecb.LIB_PATH), "libembree3_b200.so"))
+    missing = [n for n in declared if not hasattr(shim, n)]
+    assert not missing, "libembree3_b200.so does not export %s" % missing
+    # without a host Embree the device cannot be created, and that is reported, not papered over
+    shim.rtcNewDevice.restype = C.c_void_p
+    shim.rtcNewDevice.argtypes = [C.c_char_p]
+    env_before = os.environ.pop("ECB200_HOST_EMBREE", None)
+    try:
+        assert shim.rtcNewDevice(b"subdiv_accel=bvh4.compressed.leaf") is None
+    finally:
+        if env_before is not None:
+            os.environ["ECB200_HOST_EMBREE"] = env_before
