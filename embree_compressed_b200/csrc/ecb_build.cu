@@ -29,6 +29,9 @@
 namespace {
 
 constexpr int kBuildThreads = 128;
+#ifndef ECB_BUILD_THREADS_C3
+#define ECB_BUILD_THREADS_C3 32u  // CTA size for C <= 3 (81 vertices, 64 cells per block): one warp, barriers cost nothing (measured 629 -> 385 us vs 64)
+#endif
 
 __device__ __forceinline__ float min_e(float a, float b) { return a < b ? a : b; }  // embree min/max (common/math/math.h:177,194)
 __device__ __forceinline__ float max_e(float a, float b) { return a < b ? b : a; }
@@ -37,13 +40,14 @@ __constant__ float c_border[8] = {0.000f, 0.005f, 0.010f, 0.050f, 0.100f, 0.200f
 __constant__ float c_mid[8] = {0.00f, 0.40f, 0.48f, 0.49f, 0.50f, 0.51f, 0.52f, 0.60f};
 __constant__ float c_z[4] = {0.f, 0.25f, 0.5f, 0.75f};
 
-__device__ __forceinline__ unsigned look_up_idx(const float* table, unsigned n, float val) {  // compressed_node.h:47-55
-  unsigned ret = 0;
-  for (unsigned i = 0; i < n; i++) {
-    if (table[i] <= val) ret = i;
-    else break;
-  }
-  return ret;
+// lookUpIdx (compressed_node.h:47-55): index of the last entry of the leading run with table[i] <= val, 0 if there is none.
+// The tables are increasing, so that run is everything <= val and a branch-free count gives the same index (NaN: 0).
+template <unsigned N>
+__device__ __forceinline__ unsigned look_up_idx(const float* table, float val) {
+  unsigned count = 0;
+#pragma unroll
+  for (unsigned i = 0; i < N; i++) count += table[i] <= val ? 1u : 0u;
+  return count ? count - 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t compact(uint32_t x) {
@@ -167,16 +171,16 @@ __device__ uint32_t set_aabb(const Box3& parent, const Box3& b00, const Box3& b1
   const float y3 = fmaxf(b00.hi[1], b10.hi[1]), y4 = fmaxf(b01.hi[1], b11.hi[1]);
   const float z1 = fminf(fminf(b00.lo[2], b10.lo[2]), fminf(b01.lo[2], b11.lo[2]));
   const float z2 = fmaxf(fmaxf(b00.hi[2], b10.hi[2]), fmaxf(b01.hi[2], b11.hi[2]));
-  const unsigned X1 = look_up_idx(c_border, 8, (float)((double)(x1 - parent.lo[0]) * xF));
-  const unsigned X2 = look_up_idx(c_mid, 8, (float)((double)(x2 - parent.lo[0]) * xF));
-  const unsigned X3 = look_up_idx(c_mid, 8, (float)((double)(parent.hi[0] - x3) * xF));
-  const unsigned X4 = look_up_idx(c_border, 8, (float)((double)(parent.hi[0] - x4) * xF));
-  const unsigned Y1 = look_up_idx(c_border, 8, (float)((double)(y1 - parent.lo[1]) * yF));
-  const unsigned Y2 = look_up_idx(c_mid, 8, (float)((double)(y2 - parent.lo[1]) * yF));
-  const unsigned Y3 = look_up_idx(c_mid, 8, (float)((double)(parent.hi[1] - y3) * yF));
-  const unsigned Y4 = look_up_idx(c_border, 8, (float)((double)(parent.hi[1] - y4) * yF));
-  const unsigned Zmin = look_up_idx(c_z, 4, (float)((double)(z1 - parent.lo[2]) * zF));
-  const unsigned Zmax = look_up_idx(c_z, 4, (float)((double)(parent.hi[2] - z2) * zF));
+  const unsigned X1 = look_up_idx<8>(c_border, (float)((double)(x1 - parent.lo[0]) * xF));
+  const unsigned X2 = look_up_idx<8>(c_mid, (float)((double)(x2 - parent.lo[0]) * xF));
+  const unsigned X3 = look_up_idx<8>(c_mid, (float)((double)(parent.hi[0] - x3) * xF));
+  const unsigned X4 = look_up_idx<8>(c_border, (float)((double)(parent.hi[0] - x4) * xF));
+  const unsigned Y1 = look_up_idx<8>(c_border, (float)((double)(y1 - parent.lo[1]) * yF));
+  const unsigned Y2 = look_up_idx<8>(c_mid, (float)((double)(y2 - parent.lo[1]) * yF));
+  const unsigned Y3 = look_up_idx<8>(c_mid, (float)((double)(parent.hi[1] - y3) * yF));
+  const unsigned Y4 = look_up_idx<8>(c_border, (float)((double)(parent.hi[1] - y4) * yF));
+  const unsigned Zmin = look_up_idx<4>(c_z, (float)((double)(z1 - parent.lo[2]) * zF));
+  const unsigned Zmax = look_up_idx<4>(c_z, (float)((double)(parent.hi[2] - z2) * zF));
   const uint32_t xz = X1 << 5 | X2 << 2 | Zmin, xb = X3 << 5 | X4 << 2, yz = Y1 << 5 | Y2 << 2 | Zmax, yb = Y3 << 5 | Y4 << 2;
   return xz | xb << 8 | yz << 16 | yb << 24;
 }
@@ -597,7 +601,7 @@ cudaError_t ecb_launch_build(const EcbBuildLaunch& b, int device, cudaStream_t s
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   // a block of 2^C x 2^C cells has (2^C+1)^2 vertices: 81 / 289 / 1089 for C = 3 / 4 / 5
-  const unsigned threads = b.comp_level <= 3 ? 64u : (unsigned)kBuildThreads;
+  const unsigned threads = b.comp_level <= 3 ? ECB_BUILD_THREADS_C3 : (unsigned)kBuildThreads;
   const unsigned per_sm = 2048u / threads < 16u ? 2048u / threads : 16u;
   const unsigned grid = b.n < (unsigned)sms * per_sm ? b.n : (unsigned)sms * per_sm;
   const unsigned grid_t = (b.n + 127u) / 128u;
