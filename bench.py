@@ -372,11 +372,11 @@ def reference_pass(ref, prim, bounce, threads):
     return time.perf_counter() - t0
 
 
-def build_reference_scene(leaf):
+def build_reference_scene(leaf, lib_path=None):
     from oracle import pyoracle as po
     if not po.have_reference():
         return None, po
-    ref = po.RefScene(leaf, SUBDIV_LEVEL, COMP_LEVEL)
+    ref = po.RefScene(leaf, SUBDIV_LEVEL, COMP_LEVEL, lib_path=lib_path)
     ref.add_obj()
     ref.commit()
     return ref, po
@@ -400,9 +400,27 @@ def cpu_baseline(args, prim, bounce, n_prim, n_bounce):
         ts = [reference_pass(ref, prim, bounce, threads) for _ in range(4)][1:]
         kind = "reference"
     best = min(ts)
-    return {"value": round((n_prim + n_bounce) / best / 1e6, 2), "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": "the full step (%d primary + %d active bounce rays), best of %d passes, rtcIntersect1 per ray on %d std::threads, AVX2 build"
-                      % (n_prim, n_bounce, len(ts), threads)}
+    out = {"value": round((n_prim + n_bounce) / best / 1e6, 2), "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": "the full step (%d primary + %d active bounce rays), best of %d passes, rtcIntersect1 per ray on %d std::threads, AVX2 build"
+                     % (n_prim, n_bounce, len(ts), threads)}
+    if ref is not None:
+        # also one core, and the AVX512SKX build of the reference where the host can run it
+        k = max(1, len(prim) // 16)
+        a, b = prim[::16].copy(), bounce[::16].copy()
+        t0 = time.perf_counter()
+        ref.intersect(a, 1)
+        ref.intersect(b, 1)
+        dt = time.perf_counter() - t0
+        act = int(k + (bounce[::16, 3] <= bounce[::16, 8]).sum())
+        out["single_core"] = {"value": round(act / dt / 1e6, 2), "cores": 1, "sample": "every 16th ray of the step, AVX2 build"}
+        ref.free()
+        if po.have_avx512_reference():
+            ref512, _ = build_reference_scene(args.leaf, po.REF_SO_AVX512)
+            t512 = min(reference_pass(ref512, prim, bounce, threads) for _ in range(3))
+            out["avx512"] = {"value": round((n_prim + n_bounce) / t512 / 1e6, 2), "cores": threads,
+                             "sample": "the full step, best of 3 passes, AVX512SKX build of the reference (its own BVH4 commit)"}
+            ref512.free()
+    return out
 
 
 def run_reference(args, rank, world):

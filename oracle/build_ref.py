@@ -30,18 +30,29 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("ECB_REFERENCE_DIR", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-OBJ = os.path.join(OUT, "obj")
 
 FLAGS_ISA = {
     "sse2": "-msse2",
     "sse42": "-msse4.2",
     "avx": "-mavx",
     "avx2": "-mf16c -mavx2 -mfma -mlzcnt -mbmi -mbmi2",
+    # common/cmake/gcc.cmake:22 (EMBREE_MAX_ISA=AVX512SKX; only the second library below is built with it)
+    "avx512skx": "-mavx512f -mavx512dq -mavx512cd -mavx512bw -mavx512vl -mf16c -mavx2 -mfma -mlzcnt -mbmi -mbmi2",
 }
 # common/cmake/gcc.cmake:26-40 + Release (:52-54); -Wall dropped (noise only), -fPIE dropped (we link a .so)
 COMMON = ("-fPIC -std=c++11 -fvisibility=hidden -fvisibility-inlines-hidden -fno-strict-aliasing "
           "-fno-tree-vectorize -DNDEBUG -O3 -w")
 DEFS = "-DEMBREE_TARGET_SSE2 -DEMBREE_TARGET_SSE42 -DEMBREE_TARGET_AVX -DEMBREE_TARGET_AVX2 -DTASKING_INTERNAL"
+
+# Two libraries are built from the same sources:
+#   libembree3_ref.so         EMBREE_MAX_ISA=AVX2       the parity oracle and the default CPU baseline (pinned ISA set, so
+#                                                       that the reference's numerics do not depend on the box's CPU)
+#   libembree3_ref_avx512.so  EMBREE_MAX_ISA=AVX512SKX  timing baseline only ("AVX2 and AVX512SKX builds")
+VARIANTS = {
+    "avx2": dict(so="libembree3_ref.so", obj="obj", defs=DEFS, isas=("sse42", "avx", "avx2")),
+    "avx512": dict(so="libembree3_ref_avx512.so", obj="obj512", defs=DEFS + " -DEMBREE_TARGET_AVX512SKX",
+                   isas=("sse42", "avx", "avx2", "avx512skx")),
+}
 
 COMMON_LIBS = [
     "common/sys/sysinfo.cpp", "common/sys/alloc.cpp", "common/sys/filename.cpp", "common/sys/library.cpp",
@@ -81,8 +92,8 @@ BASE = [
 
 
 def isa_files(isa):
-    """kernels/CMakeLists.txt:100-172 (macro embree_files) for ISA in {sse42, avx, avx2}."""
-    order = {"sse2": 0, "sse42": 1, "avx": 2, "avx2": 3}[isa]
+    """kernels/CMakeLists.txt:100-172 (macro embree_files) for ISA in {sse42, avx, avx2, avx512skx}."""
+    order = {"sse2": 0, "sse42": 1, "avx": 2, "avx2": 3, "avx512skx": 5}[isa]
     f = ["geometry/instance_intersector.cpp", "bvh/bvh_intersector1_bvh4.cpp"]
     if isa in ("sse2", "avx"):
         f += ["common/scene_triangle_mesh.cpp", "common/scene_quad_mesh.cpp", "common/scene_bezier_curves.cpp",
@@ -102,6 +113,8 @@ def isa_files(isa):
     if order > 1:
         f += ["bvh/bvh_intersector_hybrid8_bvh4.cpp", "bvh/bvh_intersector_hybrid4_bvh8.cpp",
               "bvh/bvh_intersector_hybrid8_bvh8.cpp", "bvh/bvh_intersector_stream_bvh8.cpp"]
+    if order > 3:
+        f += ["bvh/bvh_intersector_hybrid16_bvh8.cpp", "bvh/bvh_intersector_hybrid16_bvh4.cpp"]
     return f
 
 
@@ -116,14 +129,14 @@ def include_flags():
     ])
 
 
-def jobs():
+def jobs(variant="avx2"):
     js = []
     for s in COMMON_LIBS:
         js.append((os.path.join(REF, s), "c_" + s.replace("/", "_")[:-4] + ".o", FLAGS_ISA["sse2"]))
     for s in BASE:
         js.append((os.path.join(REF, "kernels", s), "k_sse2_" + s.replace("/", "_")[:-4] + ".o",
                    FLAGS_ISA["sse2"] + " -DEMBREE_LOWEST_ISA"))
-    for isa in ("sse42", "avx", "avx2"):
+    for isa in VARIANTS[variant]["isas"]:
         for s in isa_files(isa):
             js.append((os.path.join(REF, "kernels", s), "k_%s_" % isa + s.replace("/", "_")[:-4] + ".o",
                        FLAGS_ISA[isa]))
@@ -138,12 +151,13 @@ def run(cmd):
     return r
 
 
-def compile_one(job):
+def compile_one(job, variant="avx2"):
     src, obj, flags = job
-    out = os.path.join(OBJ, obj)
+    v = VARIANTS[variant]
+    out = os.path.join(OUT, v["obj"], obj)
     if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
         return out
-    run("g++ %s %s %s %s -c %s -o %s" % (COMMON, DEFS, flags, include_flags(), src, out))
+    run("g++ %s %s %s %s -c %s -o %s" % (COMMON, v["defs"], flags, include_flags(), src, out))
     return out
 
 
@@ -156,37 +170,56 @@ def source_digest():
     return h.hexdigest()
 
 
-def build(force=False):
-    if not os.path.isdir(REF):
-        if os.path.exists(os.path.join(OUT, "libembree3_ref.so")):
-            print("[build_ref] %s absent; using prebuilt oracle/_ref" % REF)
-            return True
-        print("[build_ref] %s absent and nothing prebuilt" % REF)
+def cpu_has_avx512():
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return all(f in flags for f in ("avx512f", "avx512dq", "avx512cd", "avx512bw", "avx512vl"))
+    except Exception:
         return False
-    so = os.path.join(OUT, "libembree3_ref.so")
-    info_path = os.path.join(OUT, "BUILD_INFO.json")
+
+
+def build(force=False, variants=None):
+    """Builds the AVX2 library (always) and the AVX512SKX timing library (ECB_REF_AVX512=0 skips it)."""
+    if variants is None:
+        variants = ["avx2"] + (["avx512"] if os.environ.get("ECB_REF_AVX512", "1") != "0" else [])
+    ok = True
+    for v in variants:
+        ok = build_variant(v, force) and ok if v == "avx2" else (build_variant(v, force) or True) and ok
+    return ok
+
+
+def build_variant(variant, force=False):
+    v = VARIANTS[variant]
+    so = os.path.join(OUT, v["so"])
+    if not os.path.isdir(REF):
+        if os.path.exists(so):
+            print("[build_ref] %s absent; using prebuilt %s" % (REF, v["so"]))
+            return True
+        print("[build_ref] %s absent and no prebuilt %s" % (REF, v["so"]))
+        return False
+    info_path = os.path.join(OUT, "BUILD_INFO.json" if variant == "avx2" else "BUILD_INFO_%s.json" % variant)
     digest = source_digest()
     if not force and os.path.exists(so) and os.path.exists(info_path):
         try:
             if json.load(open(info_path)).get("digest") == digest:
-                print("[build_ref] up to date")
+                print("[build_ref] %s up to date" % v["so"])
                 return True
         except Exception:
             pass
-    os.makedirs(OBJ, exist_ok=True)
+    obj_dir = os.path.join(OUT, v["obj"])
+    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(os.path.join(HERE, "gen", "kernels"), exist_ok=True)
     hash_h = os.path.join(HERE, "gen", "kernels", "hash.h")
     if not os.path.exists(hash_h):
         open(hash_h, "w").write('#define RTC_HASH "oracle-build"\n')
     t0 = time.time()
-    js = jobs()
+    js = jobs(variant)
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
-        objs = list(ex.map(compile_one, js))
-    print("[build_ref] compiled %d reference translation units in %.0f s" % (len(objs), time.time() - t0))
-    # the harness is compiled against the reference's internal headers (AVX2 flags so that it may use
-    # the same inline helpers; it only *reads* the committed BVH and drives rtc* calls)
-    host_o = os.path.join(OBJ, "refhost.o")
-    run("g++ %s %s %s %s -I%s -c %s -o %s" % (COMMON.replace("-fvisibility=hidden", ""), DEFS,
+        objs = list(ex.map(lambda j: compile_one(j, variant), js))
+    print("[build_ref] %s: compiled %d reference translation units in %.0f s" % (variant, len(objs), time.time() - t0))
+    # the harness is compiled against the reference's internal headers (it only *reads* the committed BVH and drives rtc* calls)
+    host_o = os.path.join(obj_dir, "refhost.o")
+    run("g++ %s %s %s %s -I%s -c %s -o %s" % (COMMON.replace("-fvisibility=hidden", ""), v["defs"],
                                                 FLAGS_ISA["sse2"] + " -DEMBREE_LOWEST_ISA", include_flags(), HERE,
                                                 os.path.join(HERE, "refhost.cpp"), host_o))
     # -Bsymbolic: the library's own references to rtc* bind locally, so that it can be dlopen'ed by a process that
@@ -194,7 +227,7 @@ def build(force=False):
     run("g++ -shared -Wl,-Bsymbolic -o %s %s %s -lpthread -ldl -Wl,-z,noexecstack" % (so, " ".join(objs), host_o))
     os.makedirs(os.path.join(OUT, "assets"), exist_ok=True)
     shutil.copyfile(os.path.join(REF, "build", "bomberman.obj"), os.path.join(OUT, "assets", "bomberman.obj"))
-    json.dump({"digest": digest, "units": len(objs), "isas": ["sse2", "sse42", "avx", "avx2"],
+    json.dump({"digest": digest, "units": len(objs), "isas": ["sse2"] + list(v["isas"]),
                "tasking": "internal", "eigen": "oracle/eigen_shim stand-in",
                "compiler": subprocess.run("g++ --version", shell=True, capture_output=True, text=True).stdout.splitlines()[0],
                "seconds": round(time.time() - t0, 1)}, open(info_path, "w"), indent=1)

@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_SO = os.path.join(REF_DIR, "libembree3_ref.so")
+REF_SO_AVX512 = os.path.join(REF_DIR, "libembree3_ref_avx512.so")   # timing baseline only (EMBREE_MAX_ISA=AVX512SKX)
 PORT_SO = os.path.join(REF_DIR, "libcbvh_port.so")
 BOMBERMAN_OBJ = os.path.join(REF_DIR, "assets", "bomberman.obj")
 
@@ -50,13 +51,22 @@ class _Layout(C.Structure):
         "sizeof_aligned_node sizeof_rayhit off_an_children off_an_lower_x").split()]
 
 
-_ref = None
+_ref = {}
 
 
-def ref_lib():
-    global _ref
-    if _ref is None:
-        L = C.CDLL(REF_SO)
+def have_avx512_reference():
+    """The AVX512SKX build exists and this CPU can run it."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except Exception:
+        return False
+    return os.path.exists(REF_SO_AVX512) and all(f in flags for f in ("avx512f", "avx512dq", "avx512cd", "avx512bw", "avx512vl"))
+
+
+def ref_lib(path=None):
+    path = path or REF_SO
+    if path not in _ref:
+        L = C.CDLL(path)
         vp = C.c_void_p
         L.ref_layout.argtypes = [C.POINTER(_Layout)]
         L.ref_scene_new.restype = vp
@@ -92,8 +102,8 @@ def ref_lib():
         L.ref_scene_triangle_root.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint)]
         L.ref_scene_instance_info.restype = C.c_int
         L.ref_scene_instance_info.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint, vp, vp, vp]
-        _ref = L
-    return _ref
+        _ref[path] = L
+    return _ref[path]
 
 
 def ref_layout():
@@ -109,8 +119,8 @@ def hardware_threads():
 class RefScene:
     """A scene built and traced by the compiled reference."""
 
-    def __init__(self, leaf, S, C_, build_threads=0):
-        self.L = ref_lib()
+    def __init__(self, leaf, S, C_, build_threads=0, lib_path=None):
+        self.L = ref_lib(lib_path)
         self.leaf, self.S, self.C = leaf, S, C_
         self.h = self.L.ref_scene_new(leaf.encode(), S, C_, build_threads)
         self._children = []
