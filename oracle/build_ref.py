@@ -208,7 +208,8 @@ def build_variant(variant, force=False):
             pass
     obj_dir = os.path.join(OUT, v["obj"])
     os.makedirs(obj_dir, exist_ok=True)
-    os.makedirs(os.path.join(HERE, "gen", "kernels"), exist_ok=True)
+    # the include path -I gen/kernels/common must exist for "../config.h" to resolve (git keeps no empty directories)
+    os.makedirs(os.path.join(HERE, "gen", "kernels", "common"), exist_ok=True)
     hash_h = os.path.join(HERE, "gen", "kernels", "hash.h")
     if not os.path.exists(hash_h):
         open(hash_h, "w").write('#define RTC_HASH "oracle-build"\n')
