@@ -287,10 +287,13 @@ def run_ours(args, rank, world):
         roofline["ncu"] = recorded_traffic(args.leaf, "ncu_primary_pass")
 
     # ---- e2e: the reference-facing call with pinned host buffers, copies inside the timed region ----
-    hp, hp_ptr = ecb.host_alloc(prim.nbytes)
-    hb, hb_ptr = ecb.host_alloc(bounce.nbytes)
-    hp = hp.view(np.float32).reshape(prim.shape)
-    hb = hb.view(np.float32).reshape(bounce.shape)
+    if args.e2e_memory == "pinned":
+        hp, hp_ptr = ecb.host_alloc(prim.nbytes)
+        hb, hb_ptr = ecb.host_alloc(bounce.nbytes)
+        hp = hp.view(np.float32).reshape(prim.shape)
+        hb = hb.view(np.float32).reshape(bounce.shape)
+    else:  # what an unmodified embree application hands over: plain malloc'ed ray arrays
+        hp, hb, hp_ptr, hb_ptr = np.empty_like(prim), np.empty_like(bounce), None, None
     e2e_steps = max(3, min(K, 10))
     e2e_t = []
     for i in range(2 + e2e_steps):
@@ -313,15 +316,21 @@ def run_ours(args, rank, world):
     p_dev, b_dev = bufs[W]
     assert (hp.view(np.uint32) == p_dev.cpu().numpy().view(np.uint32)).all(), "e2e primary results differ from the device path"
     assert (hb.view(np.uint32) == b_dev.cpu().numpy().view(np.uint32)).all(), "e2e bounce results differ from the device path"
-    full_copy = os.environ.get("ECB200_HOST_PATH") == "copy"
-    d2h = int(prim.nbytes + bounce.nbytes) if full_copy else 20 * (len(prim) + len(bounce))
-    e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(prim.nbytes + bounce.nbytes),
-           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "call": "ecbIntersect1M (rtcIntersect1M drop-in), pinned host RTCRayHit arrays, results written in place; "
-                   + ("full records copied back" if full_copy else
-                      "20-byte compact hit records copied back and scattered into the caller's records by the library's host pool")}
-    ecb.host_free(hp_ptr)
-    ecb.host_free(hb_ptr)
+    host_path = os.environ.get("ECB200_HOST_PATH") or "packed"
+    n_rec = len(prim) + len(bounce)
+    h2d = 32 * n_rec if host_path == "packed" else int(prim.nbytes + bounce.nbytes)
+    d2h = int(prim.nbytes + bounce.nbytes) if host_path == "copy" else 20 * n_rec
+    how = {"packed": "the library's host pool packs the 32 bytes per ray the path reads into pinned staging, 32-byte records go up, "
+                     "20-byte compact hit records come back and are scattered into the caller's records by the same pool",
+           "compact": "full records go up, 20-byte compact hit records come back and are scattered into the caller's records by the library's host pool",
+           "copy": "full records copied both ways"}[host_path]
+    e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "ms_per_step": round(float(t.item()) * 1e3, 3), "host_path": host_path, "caller_memory": args.e2e_memory,
+           "call": "ecbIntersect1M (rtcIntersect1M drop-in), %s host RTCRayHit arrays (%d bytes), results written in place; %s"
+                   % (args.e2e_memory, int(prim.nbytes + bounce.nbytes), how)}
+    if hp_ptr is not None:
+        ecb.host_free(hp_ptr)
+        ecb.host_free(hb_ptr)
 
     # ---- multi-GPU: the one exchange step of the path, hit records gathered to rank 0 over NCCL (timed apart) ----
     gather = None
@@ -479,6 +488,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--leaf", default="leaf", choices=["leaf", "grid", "box"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-memory", default="pinned", choices=["pinned", "pageable"],
+                    help="caller memory of the e2e leg (the contract asks for pinned; pageable is what an embree application has)")
     ap.add_argument("--levels", default="6,3", help="S,C of the scene image (default: BASELINE configs[1]); other images come "
                                                     "from `python __graft_entry__.py --scene bomberman_s8c3_leaf`")
     args = ap.parse_args()

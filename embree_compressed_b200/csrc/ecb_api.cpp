@@ -2,6 +2,9 @@
 // pipeline, device-buffer launches, serialisation.  No traversal arithmetic lives here and there is no CPU
 // fallback: without a usable CUDA device every traversal entry point fails with ECB_ERROR_NO_DEVICE.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -25,7 +28,10 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
-constexpr int kStages = 6;
+constexpr int kStages = 8;
+constexpr size_t kPackedBytes = 32;         // packed input record of the host-buffer path: {org.xyz,tnear},{dir.xyz,tfar}
+constexpr int kPackPartsDefault = 8;        // pack jobs per chunk (ECB200_PACK_PARTS overrides for experiments)
+constexpr int kPackAheadDefault = 3;        // chunks packed ahead of the one being issued to the GPU (ECB200_PACK_AHEAD)
 constexpr size_t kChunkRaysMax = 1u << 17;  // capacity of a staging buffer: 128 Ki rays
 constexpr size_t kCompactBytesMax = kChunkRaysMax * 20 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n]
 constexpr int kScatterParts = 4;            // scatter jobs per chunk
@@ -59,6 +65,11 @@ struct Staging {
   void* h_pin[kStages] = {};  // pinned bounce buffers for pageable caller memory
   void* d_cmp[kStages] = {};  // compact results of a chunk (device) ...
   void* h_cmp[kStages] = {};  // ... and their pinned landing zone, scattered into the caller's array by the host pool
+  void* h_pk[kStages] = {};   // packed input records of a chunk (pinned), written by the host pool, read by the H2D copy
+  int pack_pending[kStages] = {};
+  uint64_t gpu_issued = 0;      // packed path: chunks whose device work and `done` event have been issued ...
+  uint64_t scat_submitted = 0;  // ... and chunks whose scatter jobs the completion thread has handed to the pool
+  bool stop = false;
   // scatter jobs of the chunk that currently owns a stage
   std::mutex mutex;
   std::condition_variable cv;
@@ -70,6 +81,7 @@ struct Staging {
       if (h_pin[i]) cudaFreeHost(h_pin[i]);
       if (d_cmp[i]) cudaFree(d_cmp[i]);
       if (h_cmp[i]) cudaFreeHost(h_cmp[i]);
+      if (h_pk[i]) cudaFreeHost(h_pk[i]);
       if (done[i]) cudaEventDestroy(done[i]);
       if (stream[i]) cudaStreamDestroy(stream[i]);
     }
@@ -192,6 +204,7 @@ ecbError ensure_staging(ecbScene* s) {
     if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRaysMax * kRayHitBytes);
     if (e == cudaSuccess) e = cudaMalloc(&st->d_cmp[i], kCompactBytesMax);
     if (e == cudaSuccess) e = cudaMallocHost(&st->h_cmp[i], kCompactBytesMax);
+    if (e == cudaSuccess) e = cudaMallocHost(&st->h_pk[i], kChunkRaysMax * kPackedBytes);
     if (e != cudaSuccess) {
       delete st;
       return cuda_fail(e, "staging allocation");
@@ -211,7 +224,9 @@ bool is_pinned(const void* p) {
 }
 
 // ---- host worker pool: scatters compact results into the caller's records while the next chunks are in flight ----
-// (ECB200_HOST_THREADS overrides the size; default min(8, hardware threads / 2).)  Process-wide, never torn down.
+// and, with the packed strategy, packs the rays of the chunks ahead.  (ECB200_HOST_THREADS overrides the size; default
+// min(12, 3/4 of the hardware threads): measured 8 / 10 / 12 / 14 / 16 threads on the 16-core host = 530 / 660 / 680 / 690 /
+// 550 Mrays/s.)  Process-wide, never torn down.
 class HostPool {
  public:
   static HostPool& get() {
@@ -229,8 +244,8 @@ class HostPool {
 
  private:
   HostPool() {
-    unsigned n = std::thread::hardware_concurrency() / 2;
-    if (n > 8) n = 8;
+    unsigned n = std::thread::hardware_concurrency() * 3 / 4;
+    if (n > 12) n = 12;
     if (const char* e = getenv("ECB200_HOST_THREADS")) n = (unsigned)atoi(e);
     if (n < 1) n = 1;
     if (n > 64) n = 64;
@@ -270,20 +285,60 @@ size_t pipeline_chunk() {
 }
 
 // Transfer strategy of the host-buffer entry points (measured on B200 / PCIe Gen5 x16: 55 GB/s one way, 35+35 GB/s both
-// ways at once, so the BYTES moved decide the end-to-end rate):
-//   compact (default): the full records go up, 20 bytes per ray ({tfar,u,v,primID} + geomID) come back into a pinned
-//                      landing zone, and a small host thread pool writes them into the caller's records while the next
-//                      chunks are in flight (a miss writes nothing, as the API demands)
+// ways at once; the host is a 16-core VM whose cores stream 5-9 GB/s each -- bytes over the link AND bytes through the host
+// cores decide the end-to-end rate; bench step = 3.8 M rays, 332 MB of records):
+//   packed (default) : the host pool packs the 32 bytes per ray this path reads ({org,tnear},{dir,tfar}) into pinned
+//                      staging buffers (prefetch + streaming stores) three chunks ahead of the upload, 32 bytes per ray
+//                      go up, 20 bytes per ray ({tfar,u,v,primID} + geomID) come back into a pinned landing zone and
+//                      the pool writes them into the caller's records while the next chunks are in flight (a miss
+//                      writes nothing, as the API demands).  Pinned and pageable caller memory alike
+//                                                                        -> 650-710 Mrays/s (12 pool threads; 8: 530)
+//   compact          : the full records go up (DMA straight from pinned caller memory; pageable memory is copied into
+//                      bounce buffers by the caller's thread), compact results come back as above
+//                      (ECB200_HOST_PATH=compact)                          -> 504-521 Mrays/s pinned, 96 pageable
 //   copy             : the full records travel both ways (ECB200_HOST_PATH=copy; also what instancing and mixed scenes
-//                      use, whose hits carry an instID / a real normal)                           -> 456 Mrays/s on the bench step
+//                      use, whose hits carry an instID / a real normal)   -> 452-462 Mrays/s pinned, 53 pageable
 // Tried and dropped: results written by the kernel straight into the caller's mapped pinned array 363 Mrays/s (small PCIe
-// writes), the same with a 48-byte 2-D H2D copy 35 Mrays/s (row-sized DMAs).
-bool use_compact_results() {
-  static const bool on = [] {
+// writes), the same with a 48-byte 2-D H2D copy 35 Mrays/s (row-sized DMAs); packing with plain stores and 2 x 4 pack
+// jobs in flight 210-310 Mrays/s (one core's streaming rate bounds a pack job: the look-ahead has to cover it).
+enum HostPath { kPathPacked, kPathCompact, kPathCopy };
+HostPath host_path() {
+  static const HostPath path = [] {
     const char* e = getenv("ECB200_HOST_PATH");
-    return !(e && strcmp(e, "copy") == 0);
+    if (e && strcmp(e, "copy") == 0) return kPathCopy;
+    if (e && strcmp(e, "compact") == 0) return kPathCompact;
+    return kPathPacked;
   }();
-  return on;
+  return path;
+}
+bool use_compact_results() { return host_path() != kPathCopy; }
+
+// copies the fields this path reads of rays [b, e) of a chunk into 32-byte packed records: {org.xyz, tnear}, {dir.xyz, tfar}
+// (RTCRay layout, rtcore_ray.h:26-44: org 0, tnear 12, dir 16, time 28, tfar 32; time/mask/id/flags are not read by the
+// compressed-accel intersectors)
+void pack_rays(const uint8_t* rays, size_t stride, uint8_t* dst, size_t b, size_t e) {
+#if defined(__SSE2__)
+  // the source is read once and the staging buffer is read next by the DMA engine: prefetch ahead, streaming stores
+  for (size_t i = b; i < e; i++) {
+    const uint8_t* r = rays + i * stride;
+    __builtin_prefetch(r + 1024);
+    const __m128 o = _mm_loadu_ps(reinterpret_cast<const float*>(r));
+    const __m128 d = _mm_loadu_ps(reinterpret_cast<const float*>(r + 16));
+    const __m128 t = _mm_load_ss(reinterpret_cast<const float*>(r + 32));
+    const __m128 zt = _mm_shuffle_ps(d, t, _MM_SHUFFLE(0, 0, 2, 2));                        // dir.z, dir.z, tfar, tfar
+    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes), o);
+    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes + 16), _mm_shuffle_ps(d, zt, _MM_SHUFFLE(2, 0, 1, 0)));  // dir.xyz, tfar
+  }
+  _mm_sfence();
+#else
+  for (size_t i = b; i < e; i++) {
+    const uint8_t* r = rays + i * stride;
+    uint32_t w[8];
+    memcpy(w, r, 28);
+    memcpy(w + 7, r + 32, 4);
+    memcpy(dst + i * kPackedBytes, w, 32);
+  }
+#endif
 }
 
 // writes the compact results of rays [b, e) of a chunk into the caller's records (hit semantics of rtcIntersect1 /
@@ -318,6 +373,184 @@ void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n,
   }
 }
 
+// Host-buffer entry points on a compressed-accel scene, packed strategy (see host_path()).  Per chunk of rays:
+//   pool: pack -> caller's thread: H2D (32 B/ray), kernel, D2H (20 B/ray, 4 for any-hit), event -> completion thread: waits
+//   for the event, hands the scatter jobs to the pool -> pool: scatter into the caller's records.
+// Pool threads never wait on the GPU; the caller's thread stays kPackAhead chunks ahead with the pack jobs.
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  int v = e ? atoi(e) : dflt;
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride) {
+  static const int kPackParts = env_int("ECB200_PACK_PARTS", kPackPartsDefault, 1, 64);
+  static const int kPackAhead = env_int("ECB200_PACK_AHEAD", kPackAheadDefault, 1, kStages - 2);
+  const size_t chunk = pipeline_chunk();
+  const uint64_t n_chunks = (M + chunk - 1) / chunk;
+  const bool any_hit = occluded;
+  auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
+  auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n); };
+  auto issue = [&](uint64_t c) -> ecbError {  // H2D of the packed records, kernel, D2H of the compact results
+    const int k = (int)(c % kStages);
+    const size_t n = chunk_size(c);
+    cudaStream_t q = st->stream[k];
+    CU(cudaMemcpyAsync(st->d_buf[k], st->h_pk[k], n * kPackedBytes, cudaMemcpyHostToDevice, q));
+    EcbLaunch L;
+    L.in = static_cast<const uint8_t*>(st->d_buf[k]);
+    L.in_stride = kPackedBytes;
+    L.tfar_offset = 28;
+    L.out = nullptr;
+    L.out_stride = 0;
+    L.M = n;
+    L.instID = instID;
+    L.any_hit_exact = exact ? 1u : 0u;
+    L.hit_geom = static_cast<uint32_t*>(st->d_cmp[k]);
+    L.hit_rec = reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15)));
+    L.block_out = nullptr;
+    L.counters = nullptr;
+    L.queue = next_queue(s);
+    g_launches.fetch_add(1);
+    cudaError_t le = (occluded && !exact) ? ecb_launch_occluded(s->dev, s->device, L, q) : ecb_launch_intersect(s->dev, s->device, L, q);
+    if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+    CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], cmp_bytes(n), cudaMemcpyDeviceToHost, q));
+    return ECB_SUCCESS;
+  };
+
+  if (M <= 8192) {  // small calls (rtcIntersect1, packets, short streams): everything inline on the caller's thread
+    for (uint64_t c0 = 0; c0 < n_chunks; c0 += kStages) {
+      const uint64_t c1 = c0 + kStages < n_chunks ? c0 + kStages : n_chunks;
+      for (uint64_t c = c0; c < c1; c++) {
+        pack_rays(base + c * chunk * stride, stride, static_cast<uint8_t*>(st->h_pk[c % kStages]), 0, chunk_size(c));
+        ecbError e = issue(c);
+        if (e != ECB_SUCCESS) return e;
+      }
+      for (uint64_t c = c0; c < c1; c++) {
+        CU(cudaStreamSynchronize(st->stream[c % kStages]));
+        const size_t n = chunk_size(c);
+        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID);
+      }
+    }
+    return ECB_SUCCESS;
+  }
+
+  {
+    std::lock_guard<std::mutex> wl(st->mutex);
+    st->worker_error = cudaSuccess;
+    st->gpu_issued = 0;
+    st->scat_submitted = 0;
+    st->stop = false;
+  }
+  const int device = s->device;
+  // completion thread: chunk by chunk, waits (blocking, not spinning) for the chunk's results and hands the scatter jobs
+  // to the pool
+  std::thread completion([=] {
+    cudaError_t se = cudaSetDevice(device);
+    for (uint64_t c = 0; c < n_chunks; c++) {
+      const int k = (int)(c % kStages);
+      {
+        std::unique_lock<std::mutex> wl(st->mutex);
+        st->cv.wait(wl, [&] { return st->gpu_issued > c || st->stop; });
+        if (st->gpu_issued <= c) break;  // the call ended early
+      }
+      cudaError_t ce = se != cudaSuccess ? se : cudaEventSynchronize(st->done[k]);
+      const size_t n = (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk);
+      uint8_t* src = base + c * chunk * stride;
+      const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
+      {
+        std::lock_guard<std::mutex> wl(st->mutex);
+        if (ce != cudaSuccess && st->worker_error == cudaSuccess) st->worker_error = ce;
+        st->pending[k] = ce == cudaSuccess ? kScatterParts : 0;
+      }
+      if (ce == cudaSuccess) {
+        for (int part = 0; part < kScatterParts; part++) {
+          const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
+          HostPool::get().submit([=] {
+            scatter_results(src, stride, cmp, n, b, e, any_hit, instID);
+            std::lock_guard<std::mutex> wl(st->mutex);
+            if (--st->pending[k] == 0) st->cv.notify_all();
+          });
+        }
+      }
+      {
+        std::lock_guard<std::mutex> wl(st->mutex);
+        st->scat_submitted = c + 1;
+      }
+      st->cv.notify_all();
+    }
+  });
+  // whatever way this call ends (CUDA errors included), no pool job and no completion thread may outlive it: they read and
+  // write the caller's array
+  struct Drain {
+    Staging* st;
+    std::thread* completion;
+    ~Drain() {
+      {
+        std::lock_guard<std::mutex> wl(st->mutex);
+        st->stop = true;
+      }
+      st->cv.notify_all();
+      completion->join();
+      std::unique_lock<std::mutex> wl(st->mutex);
+      st->cv.wait(wl, [&] {
+        for (int k = 0; k < kStages; k++)
+          if (st->pending[k] || st->pack_pending[k]) return false;
+        return true;
+      });
+    }
+  } drain{st, &completion};
+
+  for (uint64_t c = 0; c < n_chunks + kPackAhead; c++) {
+    if (c < n_chunks) {
+      const int k = (int)(c % kStages);
+      const size_t n = chunk_size(c);
+      {
+        std::unique_lock<std::mutex> wl(st->mutex);
+        if (c >= (uint64_t)kStages)  // the stage's previous chunk is done down to its last scatter job
+          st->cv.wait(wl, [&] { return st->scat_submitted > c - kStages && st->pending[k] == 0; });
+        st->pack_pending[k] = kPackParts;
+      }
+      const uint8_t* src = base + c * chunk * stride;
+      uint8_t* dst = static_cast<uint8_t*>(st->h_pk[k]);
+      for (int part = 0; part < kPackParts; part++) {
+        const size_t b = n * part / kPackParts, e = n * (part + 1) / kPackParts;
+        HostPool::get().submit([=] {
+          pack_rays(src, stride, dst, b, e);
+          std::lock_guard<std::mutex> wl(st->mutex);
+          if (--st->pack_pending[k] == 0) st->cv.notify_all();
+        });
+      }
+    }
+    if (c >= (uint64_t)kPackAhead) {
+      const uint64_t d = c - kPackAhead;
+      const int k = (int)(d % kStages);
+      {
+        std::unique_lock<std::mutex> wl(st->mutex);
+        st->cv.wait(wl, [&] { return st->pack_pending[k] == 0; });
+      }
+      ecbError e = issue(d);
+      if (e != ECB_SUCCESS) return e;
+      CU(cudaEventRecord(st->done[k], st->stream[k]));
+      {
+        std::lock_guard<std::mutex> wl(st->mutex);
+        st->gpu_issued = d + 1;
+      }
+      st->cv.notify_all();
+    }
+  }
+  {
+    std::unique_lock<std::mutex> wl(st->mutex);
+    st->cv.wait(wl, [&] {
+      if (st->scat_submitted < n_chunks) return false;
+      for (int k = 0; k < kStages; k++)
+        if (st->pending[k]) return false;
+      return true;
+    });
+    if (st->worker_error != cudaSuccess) return cuda_fail(st->worker_error, "result scatter");
+  }
+  return ECB_SUCCESS;
+}
+
 // Shared by intersect (elem = 80) and occluded (elem = 48).
 ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact = false) {
   if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
@@ -343,6 +576,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
   const bool pinned = is_pinned(rays);
   const bool compact = use_compact_results() && !s->instanced && !s->has_triangles();
+  if (compact && host_path() == kPathPacked) return run_host_packed(s, st, occluded, exact, instID, base, M, stride);
   const bool use_pool = compact && M > 8192;  // small calls (rtcIntersect1, packets) scatter inline
 
   auto launch = [&](int k, size_t n) -> cudaError_t {

@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
           const uint8_t* rp = L.in + index * L.in_stride;
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));       // org.xyz, tnear
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
-          const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+          const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));  // 32, or 28 in packed records
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
           if (L.hit_geom) L.hit_geom[index] = 0xFFFFFFFFu;
           if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
@@ -1137,7 +1137,7 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScen
     const uint8_t* rp = L.in + i * L.in_stride;
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
     const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
     bool occluded = false;
     if (!(r0.w > tfar_in) && !(tfar_in < 0.0f)) {  // inactive stream ray; already occluded (bvh_intersector1.cpp:133)
       const float org[3] = {r0.x, r0.y, r0.z};

@@ -29,6 +29,10 @@
 struct EcbLaunch {
   const uint8_t* in;              // RTCRayHit / RTCRay records (org,tnear,dir,time,tfar in the first 36 bytes)
   size_t in_stride;
+  // byte offset of tfar inside an input record: 32 (RTCRay), or 28 for the 32-byte PACKED records the host-buffer entry
+  // points upload ({org.xyz, tnear}, {dir.xyz, tfar}: the fields this path reads; `time` is not one of them).  Only the
+  // compressed-accel kernels (intersect / occluded) honour it.
+  uint32_t tfar_offset = 32;
   uint8_t* out;                   // RTCRayHit / RTCRay records that receive tfar + hit
   size_t out_stride;
   uint64_t M;

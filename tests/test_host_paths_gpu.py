@@ -1,0 +1,22 @@
+"""-m gpu: the three transfer strategies of the host-buffer entry points (csrc/ecb_api.cpp host_path(): packed /
+compact / copy) give the same bits, for pinned and pageable caller memory, contiguous and padded records, with many more
+chunks in flight than pipeline stages.  Needs only the committed fixtures."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("path", ["packed", "compact", "copy"])
+@pytest.mark.parametrize("chunk,threads", [("1024", "3"), ("65536", "8")])
+def test_host_transfer_strategies(ecb, path, chunk, threads):
+    env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK=chunk, ECB200_HOST_THREADS=threads)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "host_paths_case.py"), "cube_s4c2_leaf", "5"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host paths ok" in r.stdout

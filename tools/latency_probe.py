@@ -8,7 +8,8 @@ from embree_compressed_b200 import raygen as rg
 import bench
 scene = ecb.Scene.from_image_file(bench.scene_path("leaf")).upload(0)
 rays = rg.primary_rays(64, 64, **rg.BOMBERMAN_CAMERA)
-for n in (1, 16, 256, 4096):
+rays = np.concatenate([rays] * 64)
+for n in (1, 16, 256, 4096, 8192, 16384, 65536, 262144):
     r = rays[:n].copy()
     scene.intersect1M(r)
     t0 = time.perf_counter()
