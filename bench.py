@@ -316,7 +316,7 @@ def run_ours(args, rank, world):
     p_dev, b_dev = bufs[W]
     assert (hp.view(np.uint32) == p_dev.cpu().numpy().view(np.uint32)).all(), "e2e primary results differ from the device path"
     assert (hb.view(np.uint32) == b_dev.cpu().numpy().view(np.uint32)).all(), "e2e bounce results differ from the device path"
-    host_path = os.environ.get("ECB200_HOST_PATH") or "packed"
+    host_path = os.environ.get("ECB200_HOST_PATH") or ecb.host_path_for(args.e2e_memory == "pinned")
     n_rec = len(prim) + len(bounce)
     h2d = 32 * n_rec if host_path == "packed" else int(prim.nbytes + bounce.nbytes)
     d2h = int(prim.nbytes + bounce.nbytes) if host_path == "copy" else 20 * n_rec

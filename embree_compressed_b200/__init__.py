@@ -89,6 +89,7 @@ SYMBOLS = {
     "ecbSceneBlockNormals": (C.c_int, [_vp, _vp, _sz]),
     "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbHostFree": (None, [_vp]),
+    "ecbHostPathName": (C.c_char_p, [C.c_int]),
     "ecbLaunchCount": (_u64, []),
     "ecbErrorString": (C.c_char_p, [C.c_int]),
     "ecbLastErrorMessage": (C.c_char_p, []),
@@ -119,6 +120,11 @@ def _check(code, what):
 
 def launch_count():
     return int(_lib().ecbLaunchCount())
+
+
+def host_path_for(pinned):
+    """Name of the transfer strategy the host-buffer entry points pick for this kind of caller memory."""
+    return _lib().ecbHostPathName(1 if pinned else 0).decode()
 
 
 def host_alloc(n_bytes):

@@ -225,7 +225,7 @@ bool is_pinned(const void* p) {
 
 // ---- host worker pool: scatters compact results into the caller's records while the next chunks are in flight ----
 // and, with the packed strategy, packs the rays of the chunks ahead.  (ECB200_HOST_THREADS overrides the size; default
-// min(12, 3/4 of the hardware threads): measured 8 / 10 / 12 / 14 / 16 threads on the 16-core host = 530 / 660 / 680 / 690 /
+// min(12, 3/4 of the hardware threads / LOCAL_WORLD_SIZE): measured 8 / 10 / 12 / 14 / 16 threads on the 16-core host = 530 / 660 / 680 / 690 /
 // 550 Mrays/s.)  Process-wide, never torn down.
 class HostPool {
  public:
@@ -245,6 +245,12 @@ class HostPool {
  private:
   HostPool() {
     unsigned n = std::thread::hardware_concurrency() * 3 / 4;
+    // one process per GPU on a shared host (torchrun exports LOCAL_WORLD_SIZE): the processes split the host's cores
+    if (const char* w = getenv("LOCAL_WORLD_SIZE")) {
+      const int lw = atoi(w);
+      if (lw > 1) n /= (unsigned)lw;
+    }
+    if (n < 2) n = 2;
     if (n > 12) n = 12;
     if (const char* e = getenv("ECB200_HOST_THREADS")) n = (unsigned)atoi(e);
     if (n < 1) n = 1;
@@ -287,7 +293,7 @@ size_t pipeline_chunk() {
 // Transfer strategy of the host-buffer entry points (measured on B200 / PCIe Gen5 x16: 55 GB/s one way, 35+35 GB/s both
 // ways at once; the host is a 16-core VM whose cores stream 5-9 GB/s each -- bytes over the link AND bytes through the host
 // cores decide the end-to-end rate; bench step = 3.8 M rays, 332 MB of records):
-//   packed (default) : the host pool packs the 32 bytes per ray this path reads ({org,tnear},{dir,tfar}) into pinned
+//   packed           : the host pool packs the 32 bytes per ray this path reads ({org,tnear},{dir,tfar}) into pinned
 //                      staging buffers (prefetch + streaming stores) three chunks ahead of the upload, 32 bytes per ray
 //                      go up, 20 bytes per ray ({tfar,u,v,primID} + geomID) come back into a pinned landing zone and
 //                      the pool writes them into the caller's records while the next chunks are in flight (a miss
@@ -298,16 +304,19 @@ size_t pipeline_chunk() {
 //                      (ECB200_HOST_PATH=compact)                          -> 504-521 Mrays/s pinned, 96 pageable
 //   copy             : the full records travel both ways (ECB200_HOST_PATH=copy; also what instancing and mixed scenes
 //                      use, whose hits carry an instID / a real normal)   -> 452-462 Mrays/s pinned, 53 pageable
+// Default (no ECB200_HOST_PATH): packed for pageable caller memory and whenever the process has a full pool of 12 threads,
+// compact for pinned caller memory on a host whose cores are shared between ranks (see run_host).
 // Tried and dropped: results written by the kernel straight into the caller's mapped pinned array 363 Mrays/s (small PCIe
 // writes), the same with a 48-byte 2-D H2D copy 35 Mrays/s (row-sized DMAs); packing with plain stores and 2 x 4 pack
 // jobs in flight 210-310 Mrays/s (one core's streaming rate bounds a pack job: the look-ahead has to cover it).
-enum HostPath { kPathPacked, kPathCompact, kPathCopy };
+enum HostPath { kPathAuto, kPathPacked, kPathCompact, kPathCopy };
 HostPath host_path() {
   static const HostPath path = [] {
     const char* e = getenv("ECB200_HOST_PATH");
     if (e && strcmp(e, "copy") == 0) return kPathCopy;
     if (e && strcmp(e, "compact") == 0) return kPathCompact;
-    return kPathPacked;
+    if (e && strcmp(e, "packed") == 0) return kPathPacked;
+    return kPathAuto;
   }();
   return path;
 }
@@ -576,7 +585,11 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
   const bool pinned = is_pinned(rays);
   const bool compact = use_compact_results() && !s->instanced && !s->has_triangles();
-  if (compact && host_path() == kPathPacked) return run_host_packed(s, st, occluded, exact, instID, base, M, stride);
+  // auto: pageable caller memory has to go through host threads anyway -> packed.  Pinned caller memory can be DMA'd as it
+  // is, which costs no host cycles: packed wins when the process has a full pool (12 threads: 650 vs 510 Mrays/s on the
+  // 16-core single-GPU host), compact when the host's cores are shared between ranks (2 ranks on 24 cores, 9 threads each:
+  // 743 packed vs 855 compact)
+  if (compact && (host_path() == kPathPacked || (host_path() == kPathAuto && (!pinned || HostPool::get().size() >= 12)))) return run_host_packed(s, st, occluded, exact, instID, base, M, stride);
   const bool use_pool = compact && M > 8192;  // small calls (rtcIntersect1, packets) scatter inline
 
   auto launch = [&](int k, size_t n) -> cudaError_t {
@@ -1140,6 +1153,15 @@ ecbError ecbHostAlloc(void** ptr, size_t bytes) {
 }
 void ecbHostFree(void* ptr) {
   if (ptr) cudaFreeHost(ptr);
+}
+
+const char* ecbHostPathName(int caller_memory_is_pinned) {
+  switch (host_path()) {
+    case kPathCopy: return "copy";
+    case kPathCompact: return "compact";
+    case kPathPacked: return "packed";
+    default: return (!caller_memory_is_pinned || HostPool::get().size() >= 12) ? "packed" : "compact";
+  }
 }
 
 uint64_t ecbLaunchCount(void) { return g_launches.load(); }

@@ -190,6 +190,12 @@ ECB_API ecbError ecbSceneBlockNormals(const ecbScene* scene, float* normals_out,
 ECB_API ecbError ecbHostAlloc(void** ptr, size_t bytes);
 ECB_API void ecbHostFree(void* ptr);
 
+/* Transfer strategy the host-buffer entry points use for a large call on a compressed-accel scene, given the kind of
+ * caller memory: "packed" (32 B per ray up, 20 B back), "compact" (full records up by DMA, 20 B back) or "copy" (full
+ * records both ways).  Chosen from ECB200_HOST_PATH, else from the host cores this process can use (csrc/ecb_api.cpp).
+ * Diagnostic only (bench.py reports it with its byte counts); the returned string is static. */
+ECB_API const char* ecbHostPathName(int caller_memory_is_pinned);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 ECB_API uint64_t ecbLaunchCount(void);
 ECB_API const char* ecbErrorString(ecbError e);
