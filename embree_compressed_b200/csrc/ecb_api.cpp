@@ -328,17 +328,31 @@ bool use_compact_results() { return host_path() != kPathCopy; }
 void pack_rays(const uint8_t* rays, size_t stride, uint8_t* dst, size_t b, size_t e) {
 #if defined(__SSE2__)
   // the source is read once and the staging buffer is read next by the DMA engine: prefetch ahead, streaming stores
+  static const bool nt = !(getenv("ECB200_PACK_NT") && atoi(getenv("ECB200_PACK_NT")) == 0);
+  if (nt) {
+    for (size_t i = b; i < e; i++) {
+      const uint8_t* r = rays + i * stride;
+      __builtin_prefetch(r + 1024);
+      const __m128 o = _mm_loadu_ps(reinterpret_cast<const float*>(r));
+      const __m128 d = _mm_loadu_ps(reinterpret_cast<const float*>(r + 16));
+      const __m128 t = _mm_load_ss(reinterpret_cast<const float*>(r + 32));
+      const __m128 zt = _mm_shuffle_ps(d, t, _MM_SHUFFLE(0, 0, 2, 2));                        // dir.z, dir.z, tfar, tfar
+      _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes), o);
+      _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes + 16), _mm_shuffle_ps(d, zt, _MM_SHUFFLE(2, 0, 1, 0)));  // dir.xyz, tfar
+    }
+    _mm_sfence();
+    return;
+  }
   for (size_t i = b; i < e; i++) {
     const uint8_t* r = rays + i * stride;
     __builtin_prefetch(r + 1024);
     const __m128 o = _mm_loadu_ps(reinterpret_cast<const float*>(r));
     const __m128 d = _mm_loadu_ps(reinterpret_cast<const float*>(r + 16));
     const __m128 t = _mm_load_ss(reinterpret_cast<const float*>(r + 32));
-    const __m128 zt = _mm_shuffle_ps(d, t, _MM_SHUFFLE(0, 0, 2, 2));                        // dir.z, dir.z, tfar, tfar
-    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes), o);
-    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes + 16), _mm_shuffle_ps(d, zt, _MM_SHUFFLE(2, 0, 1, 0)));  // dir.xyz, tfar
+    const __m128 zt = _mm_shuffle_ps(d, t, _MM_SHUFFLE(0, 0, 2, 2));
+    _mm_store_ps(reinterpret_cast<float*>(dst + i * kPackedBytes), o);
+    _mm_store_ps(reinterpret_cast<float*>(dst + i * kPackedBytes + 16), _mm_shuffle_ps(d, zt, _MM_SHUFFLE(2, 0, 1, 0)));
   }
-  _mm_sfence();
 #else
   for (size_t i = b; i < e; i++) {
     const uint8_t* r = rays + i * stride;
