@@ -73,6 +73,31 @@ struct HostApi {
   HOST_FN(void, rtcSetGeometryTransform, (RTCGeometry, unsigned, RTCFormat, const void*))
   HOST_FN(int, rtcGetInstanceBVH_b200, (RTCScene, RTCInstanceBVHInfo_b200*, unsigned, unsigned*, float*, RTCScene*))
   HOST_FN(int, rtcGetTriangleBVH_b200, (RTCScene, uint64_t*))
+  // object plumbing that never touches a ray (resolved lazily: a host without one of them only loses that call)
+  HOST_FN(ssize_t, rtcGetDeviceProperty, (RTCDevice, RTCDeviceProperty))
+  HOST_FN(void, rtcSetDeviceMemoryMonitorFunction, (RTCDevice, RTCMemoryMonitorFunction, void*))
+  HOST_FN(RTCBuffer, rtcNewBuffer, (RTCDevice, size_t))
+  HOST_FN(RTCBuffer, rtcNewSharedBuffer, (RTCDevice, void*, size_t))
+  HOST_FN(void*, rtcGetBufferData, (RTCBuffer))
+  HOST_FN(void, rtcRetainBuffer, (RTCBuffer))
+  HOST_FN(void, rtcReleaseBuffer, (RTCBuffer))
+  HOST_FN(void, rtcSetGeometryBuffer, (RTCGeometry, RTCBufferType, unsigned, RTCFormat, RTCBuffer, size_t, size_t, size_t))
+  HOST_FN(void, rtcSetGeometryMask, (RTCGeometry, unsigned))
+  HOST_FN(void, rtcGetGeometryTransform, (RTCGeometry, float, RTCFormat, void*))
+  HOST_FN(void, rtcInterpolateN, (const RTCInterpolateNArguments*))
+  HOST_FN(void, rtcSetGeometryIntersectFilterFunction, (RTCGeometry, RTCFilterFunctionN))
+  HOST_FN(void, rtcSetGeometryOccludedFilterFunction, (RTCGeometry, RTCFilterFunctionN))
+  HOST_FN(void, rtcSetGeometryUserPrimitiveCount, (RTCGeometry, unsigned))
+  HOST_FN(void, rtcSetGeometryBoundsFunction, (RTCGeometry, RTCBoundsFunction, void*))
+  HOST_FN(void, rtcSetGeometryIntersectFunction, (RTCGeometry, RTCIntersectFunctionN))
+  HOST_FN(void, rtcSetGeometryOccludedFunction, (RTCGeometry, RTCOccludedFunctionN))
+  HOST_FN(void, rtcSetSceneProgressMonitorFunction, (RTCScene, RTCProgressMonitorFunction, void*))
+  HOST_FN(void, rtcGetSceneLinearBounds, (RTCScene, RTCLinearBounds*))
+  HOST_FN(RTCBVH, rtcNewBVH, (RTCDevice))
+  HOST_FN(void*, rtcBuildBVH, (const RTCBuildArguments*))
+  HOST_FN(void*, rtcThreadLocalAlloc, (RTCThreadLocalAllocator, size_t, size_t))
+  HOST_FN(void, rtcRetainBVH, (RTCBVH))
+  HOST_FN(void, rtcReleaseBVH, (RTCBVH))
 #undef HOST_FN
 };
 
@@ -154,6 +179,15 @@ bool load_host(HostApi& h, const std::string& path, std::string& err) {
   h.rtcGetCompressedBVH_b200 = reinterpret_cast<decltype(h.rtcGetCompressedBVH_b200)>(dlsym(h.lib, "rtcGetCompressedBVH_b200"));
   h.rtcGetInstanceBVH_b200 = reinterpret_cast<decltype(h.rtcGetInstanceBVH_b200)>(dlsym(h.lib, "rtcGetInstanceBVH_b200"));  // optional
   h.rtcGetTriangleBVH_b200 = reinterpret_cast<decltype(h.rtcGetTriangleBVH_b200)>(dlsym(h.lib, "rtcGetTriangleBVH_b200"));  // optional
+#define OPTIONAL(name) h.name = reinterpret_cast<decltype(h.name)>(dlsym(h.lib, #name));
+  OPTIONAL(rtcGetDeviceProperty) OPTIONAL(rtcSetDeviceMemoryMonitorFunction) OPTIONAL(rtcNewBuffer) OPTIONAL(rtcNewSharedBuffer)
+  OPTIONAL(rtcGetBufferData) OPTIONAL(rtcRetainBuffer) OPTIONAL(rtcReleaseBuffer) OPTIONAL(rtcSetGeometryBuffer) OPTIONAL(rtcSetGeometryMask)
+  OPTIONAL(rtcGetGeometryTransform) OPTIONAL(rtcInterpolateN) OPTIONAL(rtcSetGeometryIntersectFilterFunction)
+  OPTIONAL(rtcSetGeometryOccludedFilterFunction) OPTIONAL(rtcSetGeometryUserPrimitiveCount) OPTIONAL(rtcSetGeometryBoundsFunction)
+  OPTIONAL(rtcSetGeometryIntersectFunction) OPTIONAL(rtcSetGeometryOccludedFunction) OPTIONAL(rtcSetSceneProgressMonitorFunction)
+  OPTIONAL(rtcGetSceneLinearBounds) OPTIONAL(rtcNewBVH) OPTIONAL(rtcBuildBVH) OPTIONAL(rtcThreadLocalAlloc) OPTIONAL(rtcRetainBVH)
+  OPTIONAL(rtcReleaseBVH)
+#undef OPTIONAL
   if (!h.rtcGetCompressedBVH_b200) {
     err = "host embree does not export rtcGetCompressedBVH_b200 (apply the accessor of INTEGRATION.md)";
     return false;
@@ -182,8 +216,14 @@ std::string parse_config(const char* cfg, std::string& host_path, int& verbose) 
 
 uint32_t ctx_inst(const RTCIntersectContext* c) { return c ? c->instID[0] : RTC_INVALID_GEOMETRY_ID; }
 
-bool ready(ShimScene* s, const char* what) {
+bool ready(ShimScene* s, const char* what, const RTCIntersectContext* ctx) {
   if (!s) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return false; }
+  if (ctx && ctx->filter) {
+    // a per-query filter callback (rtcore_common.h:214-219) is host code the reference calls for every hit; it cannot run
+    // inside the CUDA traversal, and tracing without it would return different hits: refuse, rays untouched
+    s->dev->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": RTCIntersectContext::filter is not supported on the device path");
+    return false;
+  }
   if (!s->gpu) {
     s->dev->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": scene not committed to the B200 path");
     return false;
@@ -361,6 +401,101 @@ RTC_API void rtcInterpolate(const RTCInterpolateArguments* args) { HOST().rtcInt
 RTC_API void rtcSetGeometryInstancedScene(RTCGeometry g, RTCScene scene) { HOST().rtcSetGeometryInstancedScene(g, scene ? reinterpret_cast<ShimScene*>(scene)->hscene : nullptr); }
 RTC_API void rtcSetGeometryTransform(RTCGeometry g, unsigned t, RTCFormat f, const void* xfm) { HOST().rtcSetGeometryTransform(g, t, f, xfm); }
 
+
+// ---- the rest of the embree3 surface: plumbing that never touches a ray, forwarded to the host -------------------------
+// (a call the host library does not export, or made before any device exists, raises RTC_ERROR_INVALID_OPERATION)
+static ShimDevice* any_device(const char* what) {
+  ShimDevice* d = g_any_device.load();
+  if (!d) g_thread_error = RTC_ERROR_INVALID_OPERATION;
+  (void)what;
+  return d;
+}
+#define FORWARD(name, what, fail, ...)                                                                    \
+  ShimDevice* d__ = any_device(what);                                                                     \
+  if (!d__) return fail;                                                                                  \
+  if (!d__->host.name) {                                                                                  \
+    d__->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": the host embree does not export it");  \
+    return fail;                                                                                          \
+  }                                                                                                       \
+  return d__->host.name(__VA_ARGS__)
+
+RTC_API ssize_t rtcGetDeviceProperty(RTCDevice device, RTCDeviceProperty prop) {
+  if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return 0; }
+  switch (prop) {
+    // the device path serves every packet width and the stream calls (the reference's compressed accel serves none of them)
+    case RTC_DEVICE_PROPERTY_NATIVE_RAY4_SUPPORTED: case RTC_DEVICE_PROPERTY_NATIVE_RAY8_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED: case RTC_DEVICE_PROPERTY_RAY_STREAM_SUPPORTED: return 1;
+    // host callbacks cannot run inside the CUDA traversal; ray masks are not evaluated (EMBREE_RAY_MASK is off in the reference build too)
+    case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED: case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED: return 0;
+    default: break;
+  }
+  ShimDevice* d = D(device);
+  if (!d->host.rtcGetDeviceProperty) { d->raise(RTC_ERROR_INVALID_OPERATION, "rtcGetDeviceProperty: the host embree does not export it"); return 0; }
+  return d->host.rtcGetDeviceProperty(d->hdev, prop);
+}
+RTC_API void rtcSetDeviceMemoryMonitorFunction(RTCDevice device, RTCMemoryMonitorFunction fn, void* ptr) {
+  if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return; }
+  if (D(device)->host.rtcSetDeviceMemoryMonitorFunction) D(device)->host.rtcSetDeviceMemoryMonitorFunction(D(device)->hdev, fn, ptr);
+}
+RTC_API RTCBuffer rtcNewBuffer(RTCDevice device, size_t bytes) {
+  if (!device || !D(device)->host.rtcNewBuffer) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
+  return D(device)->host.rtcNewBuffer(D(device)->hdev, bytes);
+}
+RTC_API RTCBuffer rtcNewSharedBuffer(RTCDevice device, void* ptr, size_t bytes) {
+  if (!device || !D(device)->host.rtcNewSharedBuffer) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
+  return D(device)->host.rtcNewSharedBuffer(D(device)->hdev, ptr, bytes);
+}
+RTC_API void* rtcGetBufferData(RTCBuffer b) { FORWARD(rtcGetBufferData, "rtcGetBufferData", nullptr, b); }
+RTC_API void rtcRetainBuffer(RTCBuffer b) { FORWARD(rtcRetainBuffer, "rtcRetainBuffer", , b); }
+RTC_API void rtcReleaseBuffer(RTCBuffer b) { FORWARD(rtcReleaseBuffer, "rtcReleaseBuffer", , b); }
+RTC_API void rtcSetGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot, RTCFormat f, RTCBuffer b, size_t off, size_t stride, size_t n) {
+  FORWARD(rtcSetGeometryBuffer, "rtcSetGeometryBuffer", , g, t, slot, f, b, off, stride, n);
+}
+RTC_API void rtcSetGeometryMask(RTCGeometry g, unsigned mask) { FORWARD(rtcSetGeometryMask, "rtcSetGeometryMask", , g, mask); }
+RTC_API void rtcGetGeometryTransform(RTCGeometry g, float time, RTCFormat f, void* xfm) {
+  FORWARD(rtcGetGeometryTransform, "rtcGetGeometryTransform", , g, time, f, xfm);
+}
+RTC_API void rtcInterpolateN(const RTCInterpolateNArguments* args) { FORWARD(rtcInterpolateN, "rtcInterpolateN", , args); }
+RTC_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry g, RTCFilterFunctionN filter) {
+  if (filter) {
+    if (ShimDevice* d = any_device("rtcSetGeometryIntersectFilterFunction"))
+      d->raise(RTC_ERROR_INVALID_OPERATION, "rtcSetGeometryIntersectFilterFunction: host callbacks cannot run inside the CUDA traversal");
+    return;
+  }
+  FORWARD(rtcSetGeometryIntersectFilterFunction, "rtcSetGeometryIntersectFilterFunction", , g, filter);
+}
+RTC_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry g, RTCFilterFunctionN filter) {
+  if (filter) {
+    if (ShimDevice* d = any_device("rtcSetGeometryOccludedFilterFunction"))
+      d->raise(RTC_ERROR_INVALID_OPERATION, "rtcSetGeometryOccludedFilterFunction: host callbacks cannot run inside the CUDA traversal");
+    return;
+  }
+  FORWARD(rtcSetGeometryOccludedFilterFunction, "rtcSetGeometryOccludedFilterFunction", , g, filter);
+}
+// user geometries are built by the host like any other geometry; rtcCommitScene refuses a scene that holds one
+RTC_API void rtcSetGeometryUserPrimitiveCount(RTCGeometry g, unsigned n) { FORWARD(rtcSetGeometryUserPrimitiveCount, "rtcSetGeometryUserPrimitiveCount", , g, n); }
+RTC_API void rtcSetGeometryBoundsFunction(RTCGeometry g, RTCBoundsFunction fn, void* ptr) { FORWARD(rtcSetGeometryBoundsFunction, "rtcSetGeometryBoundsFunction", , g, fn, ptr); }
+RTC_API void rtcSetGeometryIntersectFunction(RTCGeometry g, RTCIntersectFunctionN fn) { FORWARD(rtcSetGeometryIntersectFunction, "rtcSetGeometryIntersectFunction", , g, fn); }
+RTC_API void rtcSetGeometryOccludedFunction(RTCGeometry g, RTCOccludedFunctionN fn) { FORWARD(rtcSetGeometryOccludedFunction, "rtcSetGeometryOccludedFunction", , g, fn); }
+// only callable from inside a user-geometry callback, which never runs on the device path
+RTC_API void rtcFilterIntersection(const RTCIntersectFunctionNArguments*, const RTCFilterFunctionNArguments*) {
+  if (ShimDevice* d = any_device("rtcFilterIntersection")) d->raise(RTC_ERROR_INVALID_OPERATION, "rtcFilterIntersection: no user-geometry callbacks on the device path");
+}
+RTC_API void rtcFilterOcclusion(const RTCOccludedFunctionNArguments*, const RTCFilterFunctionNArguments*) {
+  if (ShimDevice* d = any_device("rtcFilterOcclusion")) d->raise(RTC_ERROR_INVALID_OPERATION, "rtcFilterOcclusion: no user-geometry callbacks on the device path");
+}
+RTC_API RTCBVH rtcNewBVH(RTCDevice device) {
+  if (!device || !D(device)->host.rtcNewBVH) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
+  return D(device)->host.rtcNewBVH(D(device)->hdev);
+}
+RTC_API void* rtcBuildBVH(const RTCBuildArguments* args) { FORWARD(rtcBuildBVH, "rtcBuildBVH", nullptr, args); }
+RTC_API void* rtcThreadLocalAlloc(RTCThreadLocalAllocator a, size_t bytes, size_t align) { FORWARD(rtcThreadLocalAlloc, "rtcThreadLocalAlloc", nullptr, a, bytes, align); }
+RTC_API void rtcRetainBVH(RTCBVH b) { FORWARD(rtcRetainBVH, "rtcRetainBVH", , b); }
+RTC_API void rtcReleaseBVH(RTCBVH b) { FORWARD(rtcReleaseBVH, "rtcReleaseBVH", , b); }
+#undef FORWARD
+
 // ---- scene ------------------------------------------------------------------------------------------------------------
 RTC_API RTCScene rtcNewScene(RTCDevice device) {
   if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
@@ -398,6 +533,15 @@ RTC_API void rtcSetSceneBuildQuality(RTCScene scene, RTCBuildQuality q) { S(scen
 RTC_API void rtcSetSceneFlags(RTCScene scene, RTCSceneFlags f) { S(scene)->dev->host.rtcSetSceneFlags(S(scene)->hscene, f); }
 RTC_API RTCSceneFlags rtcGetSceneFlags(RTCScene scene) { return S(scene)->dev->host.rtcGetSceneFlags(S(scene)->hscene); }
 RTC_API void rtcGetSceneBounds(RTCScene scene, RTCBounds* b) { S(scene)->dev->host.rtcGetSceneBounds(S(scene)->hscene, b); }
+RTC_API void rtcGetSceneLinearBounds(RTCScene scene, RTCLinearBounds* b) {
+  if (!scene) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return; }
+  if (S(scene)->dev->host.rtcGetSceneLinearBounds) S(scene)->dev->host.rtcGetSceneLinearBounds(S(scene)->hscene, b);
+  else S(scene)->dev->raise(RTC_ERROR_INVALID_OPERATION, "rtcGetSceneLinearBounds: the host embree does not export it");
+}
+RTC_API void rtcSetSceneProgressMonitorFunction(RTCScene scene, RTCProgressMonitorFunction fn, void* ptr) {
+  if (!scene) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return; }
+  if (S(scene)->dev->host.rtcSetSceneProgressMonitorFunction) S(scene)->dev->host.rtcSetSceneProgressMonitorFunction(S(scene)->hscene, fn, ptr);
+}
 
 // Commit: host build (kernels/common/scene.cpp:632-697), then hand-off of the committed compressed BVH4 to the device path.
 RTC_API void rtcCommitScene(RTCScene scene) {
@@ -491,72 +635,72 @@ RTC_API void rtcJoinCommitScene(RTCScene scene) { rtcCommitScene(scene); }
 // ---- ray queries: all on the device -----------------------------------------------------------------------------------
 RTC_API void rtcIntersect1(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit* rayhit) {
   ShimScene* s = S(scene);
-  if (ready(s, "rtcIntersect1")) check(s, ecbIntersect1(s->gpu, ctx_inst(ctx), rayhit), "rtcIntersect1");
+  if (ready(s, "rtcIntersect1", ctx)) check(s, ecbIntersect1(s->gpu, ctx_inst(ctx), rayhit), "rtcIntersect1");
 }
 RTC_API void rtcIntersect1M(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit* rayhit, unsigned M, size_t byteStride) {
   ShimScene* s = S(scene);
-  if (ready(s, "rtcIntersect1M")) check(s, ecbIntersect1M(s->gpu, ctx_inst(ctx), rayhit, M, byteStride), "rtcIntersect1M");
+  if (ready(s, "rtcIntersect1M", ctx)) check(s, ecbIntersect1M(s->gpu, ctx_inst(ctx), rayhit, M, byteStride), "rtcIntersect1M");
 }
 RTC_API void rtcIntersect4(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit4* rh) {
-  if (ready(S(scene), "rtcIntersect4")) packet_intersect<4>(valid, S(scene), ctx, rh, false);
+  if (ready(S(scene), "rtcIntersect4", ctx)) packet_intersect<4>(valid, S(scene), ctx, rh, false);
 }
 RTC_API void rtcIntersect8(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit8* rh) {
-  if (ready(S(scene), "rtcIntersect8")) packet_intersect<8>(valid, S(scene), ctx, rh, false);
+  if (ready(S(scene), "rtcIntersect8", ctx)) packet_intersect<8>(valid, S(scene), ctx, rh, false);
 }
 RTC_API void rtcIntersect16(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRayHit16* rh) {
-  if (ready(S(scene), "rtcIntersect16")) packet_intersect<16>(valid, S(scene), ctx, rh, false);
+  if (ready(S(scene), "rtcIntersect16", ctx)) packet_intersect<16>(valid, S(scene), ctx, rh, false);
 }
 RTC_API void rtcOccluded1(RTCScene scene, RTCIntersectContext* ctx, RTCRay* ray) {
   ShimScene* s = S(scene);
-  if (ready(s, "rtcOccluded1")) check(s, ecbOccluded1(s->gpu, ctx_inst(ctx), ray), "rtcOccluded1");
+  if (ready(s, "rtcOccluded1", ctx)) check(s, ecbOccluded1(s->gpu, ctx_inst(ctx), ray), "rtcOccluded1");
 }
 RTC_API void rtcOccluded1M(RTCScene scene, RTCIntersectContext* ctx, RTCRay* ray, unsigned M, size_t byteStride) {
   ShimScene* s = S(scene);
-  if (ready(s, "rtcOccluded1M")) check(s, ecbOccluded1M(s->gpu, ctx_inst(ctx), ray, M, byteStride), "rtcOccluded1M");
+  if (ready(s, "rtcOccluded1M", ctx)) check(s, ecbOccluded1M(s->gpu, ctx_inst(ctx), ray, M, byteStride), "rtcOccluded1M");
 }
 RTC_API void rtcOccluded4(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay4* r) {
-  if (ready(S(scene), "rtcOccluded4")) packet_intersect<4>(valid, S(scene), ctx, r, true);
+  if (ready(S(scene), "rtcOccluded4", ctx)) packet_intersect<4>(valid, S(scene), ctx, r, true);
 }
 RTC_API void rtcOccluded8(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay8* r) {
-  if (ready(S(scene), "rtcOccluded8")) packet_intersect<8>(valid, S(scene), ctx, r, true);
+  if (ready(S(scene), "rtcOccluded8", ctx)) packet_intersect<8>(valid, S(scene), ctx, r, true);
 }
 RTC_API void rtcOccluded16(const int* valid, RTCScene scene, RTCIntersectContext* ctx, RTCRay16* r) {
-  if (ready(S(scene), "rtcOccluded16")) packet_intersect<16>(valid, S(scene), ctx, r, true);
+  if (ready(S(scene), "rtcOccluded16", ctx)) packet_intersect<16>(valid, S(scene), ctx, r, true);
 }
 
 RTC_API void rtcIntersect1Mp(RTCScene scene, RTCIntersectContext* ctx, RTCRayHit** rayhit, unsigned M) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcIntersect1Mp")) return;
+  if (!ready(s, "rtcIntersect1Mp", ctx)) return;
   stream_any_layout(s, ctx, M, false, [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(rayhit[i]) + f; }, "rtcIntersect1Mp");
 }
 RTC_API void rtcOccluded1Mp(RTCScene scene, RTCIntersectContext* ctx, RTCRay** ray, unsigned M) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcOccluded1Mp")) return;
+  if (!ready(s, "rtcOccluded1Mp", ctx)) return;
   stream_any_layout(s, ctx, M, true, [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(ray[i]) + f; }, "rtcOccluded1Mp");
 }
 // M packets of N rays in SoA layout, byteStride between packets (rtcore_scene.h:115,139)
 RTC_API void rtcIntersectNM(RTCScene scene, RTCIntersectContext* ctx, RTCRayHitN* rayhit, unsigned N, unsigned M, size_t byteStride) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcIntersectNM")) return;
+  if (!ready(s, "rtcIntersectNM", ctx)) return;
   uint8_t* base = reinterpret_cast<uint8_t*>(rayhit);
   stream_any_layout(s, ctx, (size_t)N * M, false,
                     [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(base + (i / N) * byteStride) + (size_t)f * N + (i % N); }, "rtcIntersectNM");
 }
 RTC_API void rtcOccludedNM(RTCScene scene, RTCIntersectContext* ctx, RTCRayN* ray, unsigned N, unsigned M, size_t byteStride) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcOccludedNM")) return;
+  if (!ready(s, "rtcOccludedNM", ctx)) return;
   uint8_t* base = reinterpret_cast<uint8_t*>(ray);
   stream_any_layout(s, ctx, (size_t)N * M, true,
                     [&](size_t i, int f) { return reinterpret_cast<uint32_t*>(base + (i / N) * byteStride) + (size_t)f * N + (i % N); }, "rtcOccludedNM");
 }
 RTC_API void rtcIntersectNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayHitNp* rayhit, unsigned N) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcIntersectNp")) return;
+  if (!ready(s, "rtcIntersectNp", ctx)) return;
   stream_any_layout(s, ctx, N, false, [&](size_t i, int f) { return np_word(rayhit->ray, &rayhit->hit, i, f); }, "rtcIntersectNp");
 }
 RTC_API void rtcOccludedNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayNp* ray, unsigned N) {
   ShimScene* s = S(scene);
-  if (!ready(s, "rtcOccludedNp")) return;
+  if (!ready(s, "rtcOccludedNp", ctx)) return;
   stream_any_layout(s, ctx, N, true, [&](size_t i, int f) { return np_word(*ray, nullptr, i, f); }, "rtcOccludedNp");
 }
 

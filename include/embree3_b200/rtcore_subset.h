@@ -145,6 +145,62 @@ RTC_API void rtcOccluded1Mp(RTCScene scene, struct RTCIntersectContext* context,
 RTC_API void rtcOccludedNM(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayN* ray, unsigned int N, unsigned int M, size_t byteStride);
 RTC_API void rtcOccludedNp(RTCScene scene, struct RTCIntersectContext* context, const struct RTCRayNp* ray, unsigned int N);
 
+/* ---- the rest of the embree3 surface (include/embree3/rtcore_{device,buffer,geometry,scene,builder}.h): object plumbing
+ * that never touches a ray.  Forwarded to the host Embree unchanged, except that (a) rtcGetDeviceProperty answers for the
+ * device path where it differs (packets and streams are served, filter callbacks and user geometries are not) and
+ * (b) installing a filter callback is refused with RTC_ERROR_INVALID_OPERATION: host callbacks cannot run inside the
+ * CUDA traversal, and silently ignoring them would change results. ---- */
+typedef struct RTCBufferTy* RTCBuffer;
+typedef struct RTCBVHTy* RTCBVH;
+typedef struct RTCThreadLocalAllocatorTy* RTCThreadLocalAllocator;
+enum RTCDeviceProperty { RTC_DEVICE_PROPERTY_VERSION = 0, RTC_DEVICE_PROPERTY_VERSION_MAJOR = 1, RTC_DEVICE_PROPERTY_VERSION_MINOR = 2,
+                         RTC_DEVICE_PROPERTY_VERSION_PATCH = 3, RTC_DEVICE_PROPERTY_NATIVE_RAY4_SUPPORTED = 32,
+                         RTC_DEVICE_PROPERTY_NATIVE_RAY8_SUPPORTED = 33, RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED = 34,
+                         RTC_DEVICE_PROPERTY_RAY_STREAM_SUPPORTED = 35, RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED = 64,
+                         RTC_DEVICE_PROPERTY_BACKFACE_CULLING_ENABLED = 65, RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED = 66,
+                         RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED = 67, RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED = 96,
+                         RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED = 97, RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED = 98,
+                         RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED = 99, RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED = 100,
+                         RTC_DEVICE_PROPERTY_TASKING_SYSTEM = 128, RTC_DEVICE_PROPERTY_JOIN_COMMIT_SUPPORTED = 129 };
+typedef bool (*RTCMemoryMonitorFunction)(void* ptr, ssize_t bytes, bool post);
+typedef bool (*RTCProgressMonitorFunction)(void* ptr, double n);
+struct RTCBoundsFunctionArguments;
+struct RTCIntersectFunctionNArguments;
+struct RTCOccludedFunctionNArguments;
+struct RTCInterpolateNArguments;
+struct RTCLinearBounds;
+struct RTCBuildArguments;
+typedef void (*RTCBoundsFunction)(const struct RTCBoundsFunctionArguments* args);
+typedef void (*RTCIntersectFunctionN)(const struct RTCIntersectFunctionNArguments* args);
+typedef void (*RTCOccludedFunctionN)(const struct RTCOccludedFunctionNArguments* args);
+RTC_API ssize_t rtcGetDeviceProperty(RTCDevice device, enum RTCDeviceProperty prop);                         /* rtcore_device.h:67 */
+RTC_API void rtcSetDeviceMemoryMonitorFunction(RTCDevice device, RTCMemoryMonitorFunction memoryMonitor, void* userPtr);
+RTC_API RTCBuffer rtcNewBuffer(RTCDevice device, size_t byteSize);                                            /* rtcore_buffer.h:47-59 */
+RTC_API RTCBuffer rtcNewSharedBuffer(RTCDevice device, void* ptr, size_t byteSize);
+RTC_API void* rtcGetBufferData(RTCBuffer buffer);
+RTC_API void rtcRetainBuffer(RTCBuffer buffer);
+RTC_API void rtcReleaseBuffer(RTCBuffer buffer);
+RTC_API void rtcSetGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, RTCBuffer buffer,
+                                  size_t byteOffset, size_t byteStride, size_t itemCount);
+RTC_API void rtcSetGeometryMask(RTCGeometry geometry, unsigned int mask);
+RTC_API void rtcGetGeometryTransform(RTCGeometry geometry, float time, enum RTCFormat format, void* xfm);
+RTC_API void rtcInterpolateN(const struct RTCInterpolateNArguments* args);
+RTC_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);          /* refused unless NULL */
+RTC_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);           /* refused unless NULL */
+RTC_API void rtcSetGeometryUserPrimitiveCount(RTCGeometry geometry, unsigned int userPrimitiveCount);         /* user geometries build on the */
+RTC_API void rtcSetGeometryBoundsFunction(RTCGeometry geometry, RTCBoundsFunction bounds, void* userPtr);     /* host; a scene holding one is */
+RTC_API void rtcSetGeometryIntersectFunction(RTCGeometry geometry, RTCIntersectFunctionN intersect);          /* rejected by rtcCommitScene   */
+RTC_API void rtcSetGeometryOccludedFunction(RTCGeometry geometry, RTCOccludedFunctionN occluded);
+RTC_API void rtcFilterIntersection(const struct RTCIntersectFunctionNArguments* args, const struct RTCFilterFunctionNArguments* filterArgs);
+RTC_API void rtcFilterOcclusion(const struct RTCOccludedFunctionNArguments* args, const struct RTCFilterFunctionNArguments* filterArgs);
+RTC_API void rtcSetSceneProgressMonitorFunction(RTCScene scene, RTCProgressMonitorFunction progress, void* ptr);
+RTC_API void rtcGetSceneLinearBounds(RTCScene scene, struct RTCLinearBounds* bounds_o);
+RTC_API RTCBVH rtcNewBVH(RTCDevice device);                                                                   /* rtcore_builder.h:105-117 */
+RTC_API void* rtcBuildBVH(const struct RTCBuildArguments* args);
+RTC_API void* rtcThreadLocalAlloc(RTCThreadLocalAllocator allocator, size_t bytes, size_t align);
+RTC_API void rtcRetainBVH(RTCBVH bvh);
+RTC_API void rtcReleaseBVH(RTCBVH bvh);
+
 /* ---- additions of this repo ----------------------------------------------------------------------------------- */
 /* What the host Embree must export so that rtcCommitScene can hand the committed compressed accel to the plugin
  * (INTEGRATION.md shows the accessor a maintainer adds to kernels/common/rtcore.cpp; oracle/refhost.cpp supplies it

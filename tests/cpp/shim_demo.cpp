@@ -49,6 +49,13 @@ int main(int argc, char** argv) {
   rtcSetSceneFlags(scene, RTC_SCENE_FLAG_ROBUST);
   rtcSetSceneLevels(scene, (unsigned)atoi(argv[2]), (unsigned)atoi(argv[3]));
   RTCGeometry geom = rtcNewGeometry(device, RTC_GEOMETRY_TYPE_SUBDIVISION);
+  const bool plumbing = argc > 6 && std::string(argv[6]) == "plumbing";
+  if (plumbing) {  // the same vertices through a buffer object (rtcore_buffer.h) instead of a shared pointer
+    RTCBuffer vb = rtcNewSharedBuffer(device, (void*)cube_vertices, sizeof(cube_vertices));
+    if (!vb || rtcGetBufferData(vb) != (void*)cube_vertices) { fprintf(stderr, "rtcNewSharedBuffer/rtcGetBufferData failed\n"); return 7; }
+    rtcSetGeometryBuffer(geom, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, vb, 0, 16, 8);
+    rtcReleaseBuffer(vb);
+  } else
   rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, cube_vertices, 0, 16, 8);
   rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, cube_indices, 0, 4, 24);
   rtcSetSharedGeometryBuffer(geom, RTC_BUFFER_TYPE_FACE, 0, RTC_FORMAT_UINT, cube_faces, 0, 4, 6);
@@ -206,6 +213,34 @@ int main(int argc, char** argv) {
       rtcOccludedNM(scene, &ctx, (RTCRayN*)soa.data(), N4, (unsigned)(n / N4), 12 * N4 * 4);
       for (size_t i = 0; i < n / N4 * N4; i++) fwrite(&soa[(i / N4) * 12 * N4 + 8 * N4 + i % N4], 4, 1, out);
     }
+  }
+  if (plumbing) {
+    // what the device path answers for itself, what it passes on to the host, and what it refuses
+    if (rtcGetDeviceProperty(device, RTC_DEVICE_PROPERTY_RAY_STREAM_SUPPORTED) != 1 ||
+        rtcGetDeviceProperty(device, RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED) != 1 ||
+        rtcGetDeviceProperty(device, RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED) != 0 ||
+        rtcGetDeviceProperty(device, RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED) != 1 ||
+        rtcGetDeviceProperty(device, RTC_DEVICE_PROPERTY_VERSION_MAJOR) != 3) { fprintf(stderr, "rtcGetDeviceProperty: unexpected answers\n"); return 8; }
+    if (rtcGetDeviceError(device) != RTC_ERROR_NONE) return 9;
+    RTCRayHit probe = rays[n / 2 + 80], before = probe;   // a ray that hits (the frame centre)
+    RTCIntersectContext fctx;
+    rtcInitIntersectContext(&fctx);
+    fctx.filter = (RTCFilterFunctionN)on_error;            // any non-null callback: must be refused, ray untouched
+    rtcIntersect1(scene, &fctx, &probe);
+    if (memcmp(&probe, &before, sizeof(probe)) != 0) { fprintf(stderr, "a query with a filter callback modified the ray\n"); return 10; }
+    if (rtcGetDeviceError(device) != RTC_ERROR_INVALID_OPERATION) { fprintf(stderr, "filter callback in the context was not refused\n"); return 11; }
+    rtcIntersect1(scene, &ctx, &probe);
+    if (probe.hit.geomID == RTC_INVALID_GEOMETRY_ID) { fprintf(stderr, "probe ray missed\n"); return 12; }
+    RTCGeometry g0 = rtcGetGeometry(scene, 0);
+    rtcSetGeometryIntersectFilterFunction(g0, (RTCFilterFunctionN)on_error);
+    if (rtcGetDeviceError(device) != RTC_ERROR_INVALID_OPERATION) { fprintf(stderr, "geometry filter callback was not refused\n"); return 13; }
+    rtcSetGeometryIntersectFilterFunction(g0, nullptr);    // clearing one is fine
+    rtcSetGeometryMask(g0, 0xFFFFFFFFu);
+    if (rtcGetDeviceError(device) != RTC_ERROR_NONE) return 14;
+    RTCBVH bvh = rtcNewBVH(device);                        // the stand-alone builder API lives on the host
+    if (!bvh) return 15;
+    rtcReleaseBVH(bvh);
+    printf("plumbing ok\n");
   }
   fclose(out);
   const RTCError e = rtcGetDeviceError(device);

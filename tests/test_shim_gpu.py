@@ -135,3 +135,22 @@ def test_all_stream_layouts_through_the_shim(ecb, reference, ref_scene, tmp_path
         assert (got.view(np.uint32) == stream[:m].view(np.uint32)).all(), "rtcIntersect%s differs from rtcIntersect1M" % name
     for name, part in (("Np", parts[7]), ("1Mp", parts[8]), ("NM", parts[9])):
         assert (part.view(np.uint32) == occ[:len(part)].view(np.uint32)).all(), "rtcOccluded%s differs from rtcOccluded1M" % name
+
+
+def test_rest_of_the_embree3_surface_through_the_shim(ecb, reference, tmp_path):
+    """The embree3 calls that never touch a ray (buffers, device properties, builder API ...) are forwarded to the host;
+    filter callbacks -- host code the reference runs per hit -- are refused with RTC_ERROR_INVALID_OPERATION and leave the
+    rays untouched (rtcore_common.h:214-219, rtcore_geometry.h filter functions)."""
+    cam = dict(vp=(1.6, 1.45, -1.35), vi=(0.05, -0.02, 0.03), vu=(0.0, 1.0, 0.0), fov=90.0)
+    rays = rg.primary_rays(160, 128, **cam)
+    rays_path, out_path = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rays_path)
+    env = dict(os.environ, ECB200_HOST_EMBREE=reference.REF_SO)
+    base = subprocess.run([DEMO, "leaf", "4", "2", rays_path, out_path], env=env, capture_output=True, text=True, timeout=300)
+    assert base.returncode == 0, base.stdout + base.stderr
+    want = np.fromfile(out_path, np.float32)
+    r = subprocess.run([DEMO, "leaf", "4", "2", rays_path, out_path, "plumbing"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "plumbing ok" in r.stdout
+    # vertices handed over through an RTCBuffer give the scene the shared pointer gave
+    assert (np.fromfile(out_path, np.float32).view(np.uint32) == want.view(np.uint32)).all()
