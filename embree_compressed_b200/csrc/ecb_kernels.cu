@@ -835,7 +835,8 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
     const uint8_t* rp = L.in + i * L.in_stride;
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
     const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
+    if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: miss / inactive / not occluded
     if (r0.w > tfar_in) continue;
     if (ANYHIT && tfar_in < 0.0f) continue;
     if (is.root == ECB_REF_EMPTY) continue;
@@ -926,6 +927,16 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
         }
       }
       tr.tfar = hit.tfar;
+    }
+    if (L.hit_geom) {  // compact result: the host layer scatters it into the caller's record
+      if (ANYHIT) {
+        if (occluded) L.hit_geom[i] = 0u;
+      } else if (hit_inst != 0xFFFFFFFFu) {
+        L.hit_rec[i] = make_float4(hit.tfar, hit.u, hit.v, __uint_as_float(hit.primID));
+        L.hit_geom[i] = hit.geomID;
+        L.hit_inst[i] = hit_inst;
+      }
+      continue;
     }
     uint8_t* op = L.out + i * L.out_stride;
     if (ANYHIT) {

@@ -30,8 +30,8 @@ struct EcbLaunch {
   const uint8_t* in;              // RTCRayHit / RTCRay records (org,tnear,dir,time,tfar in the first 36 bytes)
   size_t in_stride;
   // byte offset of tfar inside an input record: 32 (RTCRay), or 28 for the 32-byte PACKED records the host-buffer entry
-  // points upload ({org.xyz, tnear}, {dir.xyz, tfar}: the fields this path reads; `time` is not one of them).  Only the
-  // compressed-accel kernels (intersect / occluded) honour it.
+  // points upload ({org.xyz, tnear}, {dir.xyz, tfar}: the fields this path reads; `time` is not one of them).  The compressed-accel
+  // kernels (intersect / occluded) and the instancing kernel honour it.
   uint32_t tfar_offset = 32;
   uint8_t* out;                   // RTCRayHit / RTCRay records that receive tfar + hit
   size_t out_stride;
@@ -43,6 +43,7 @@ struct EcbLaunch {
   // hit_rec[i] = {tfar, u, v, primID}.  20 bytes per ray go back over PCIe instead of the 80-byte record.
   float4* hit_rec;
   uint32_t* hit_geom;
+  uint32_t* hit_inst = nullptr;    // instancing scenes in compact result mode: instID[0] of the hit (geomID of the instance)
   uint32_t* block_out;            // optional: index of the block of the final hit per ray
   unsigned long long* counters;   // optional: instrumented variant (6 counters)
   unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)

@@ -81,3 +81,17 @@ def test_config4_tile_sharded_frame(ecb, reference):
     inst.release()
     for s in scenes:
         s.release()
+
+
+@pytest.mark.parametrize("path", ["packed", "compact", "copy"])
+def test_instanced_scene_through_every_transfer_strategy(ecb, reference, path):
+    """Hits of an instancing scene carry the instance's geomID as instID[0]: the compact result records of the host-buffer
+    path hold one more word per ray for it (csrc/ecb_api.cpp); every strategy must leave the bits the port leaves."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK="8192", ECB200_HOST_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(here, "instanced_paths_case.py"), "leaf"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "instanced host paths ok" in r.stdout
