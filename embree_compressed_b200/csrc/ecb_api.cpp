@@ -34,7 +34,7 @@ constexpr size_t kPackedBytes = 32;         // packed input record of the host-b
 constexpr int kPackPartsDefault = 8;        // pack jobs per chunk (ECB200_PACK_PARTS overrides for experiments)
 constexpr int kPackAheadDefault = 3;        // chunks packed ahead of the one being issued to the GPU (ECB200_PACK_AHEAD)
 constexpr size_t kChunkRaysMax = 1u << 17;  // capacity of a staging buffer: 128 Ki rays
-constexpr size_t kCompactBytesMax = kChunkRaysMax * 24 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n] (+ instID[n], instancing)
+constexpr size_t kCompactBytesMax = kChunkRaysMax * 32 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n] (+ instID[n]: instancing; + Ng[3n]: mixed scenes)
 constexpr int kScatterParts = 4;            // scatter jobs per chunk
 constexpr uint32_t kQueueRing = 256;
 
@@ -365,14 +365,19 @@ void pack_rays(const uint8_t* rays, size_t stride, uint8_t* dst, size_t b, size_
 #endif
 }
 
+enum { kExtraNone = 0, kExtraInst = 1, kExtraNg = 2 };  // what follows {tfar,u,v,primID}[n] in a chunk's compact results
+
 // writes the compact results of rays [b, e) of a chunk into the caller's records (hit semantics of rtcIntersect1 /
 // rtcOccluded1: compressed.h:570-591, bvh_intersector1.cpp:199)
 void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n, size_t b, size_t e, bool any_hit, uint32_t instID,
-                     bool per_ray_inst = false) {
+                     int extra = kExtraNone) {
   const uint32_t* geom = reinterpret_cast<const uint32_t*>(cmp);
   const float* rec = reinterpret_cast<const float*>(cmp + ((4 * n + 15) & ~size_t(15)));
-  // instancing scenes: instID[0] of a hit is the geomID of the instance (instance_intersector.cpp:45-83), one word per ray
-  const uint32_t* inst = per_ray_inst ? reinterpret_cast<const uint32_t*>(cmp + ((4 * n + 15) & ~size_t(15)) + 16 * n) : nullptr;
+  // instancing scenes: instID[0] of a hit is the geomID of the instance (instance_intersector.cpp:45-83), one word per ray;
+  // mixed scenes: triangle hits carry their geometric normal (intersector_epilog.h:227-306), three floats per ray
+  const uint8_t* tail_arrays = cmp + ((4 * n + 15) & ~size_t(15)) + 16 * n;
+  const uint32_t* inst = extra == kExtraInst ? reinterpret_cast<const uint32_t*>(tail_arrays) : nullptr;
+  const float* ng = extra == kExtraNg ? reinterpret_cast<const float*>(tail_arrays) : nullptr;
   const float ninf = -__builtin_inff();
   constexpr size_t kAhead = 16;  // the caller's records are not in cache: fetch the lines of the hits ahead (measured on the B200 host: -25 %)
   for (size_t i = b; i < e; i++) {
@@ -388,7 +393,7 @@ void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n,
       continue;
     }
     const float* q = rec + 4 * i;
-    const float ngu[4] = {1.f, 0.f, 0.f, q[1]};  // Ng dummy (compressed.h:574), u
+    const float ngu[4] = {ng ? ng[3 * i] : 1.f, ng ? ng[3 * i + 1] : 0.f, ng ? ng[3 * i + 2] : 0.f, q[1]};  // Ng (dummy (1,0,0) for compressed hits, compressed.h:574), u
     uint32_t tail[4];
     memcpy(&tail[0], &q[2], 4);  // v
     memcpy(&tail[1], &q[3], 4);  // primID
@@ -418,7 +423,9 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
   const bool any_hit = occluded;
   auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
   const bool inst = s->instanced;  // hits of an instancing scene carry the instance's geomID as instID[0]: one more word per ray
-  auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (inst ? 4 * n : 0)); };
+  const bool mixed = s->has_triangles();  // triangle hits carry a real normal: three more floats per ray
+  const int extra = inst ? kExtraInst : mixed ? kExtraNg : kExtraNone;
+  auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (inst ? 4 * n : 0) + (mixed ? 12 * n : 0)); };
   auto issue = [&](uint64_t c) -> ecbError {  // H2D of the packed records, kernel, D2H of the compact results
     const int k = (int)(c % kStages);
     const size_t n = chunk_size(c);
@@ -436,10 +443,17 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
     L.hit_geom = static_cast<uint32_t*>(st->d_cmp[k]);
     L.hit_rec = reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15)));
     L.hit_inst = inst ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
+    L.hit_ng = mixed ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
     L.block_out = nullptr;
     L.counters = nullptr;
     L.queue = next_queue(s);
     g_launches.fetch_add(1);
+    if (mixed) {  // AccelN order: triangle accel first, then the compressed accel on the same staging records
+      cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, q);
+      if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
+      L.keep_results = 1;
+      g_launches.fetch_add(1);
+    }
     cudaError_t le = inst                  ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
                      : (occluded && !exact) ? ecb_launch_occluded(s->dev, s->device, L, q)
                                             : ecb_launch_intersect(s->dev, s->device, L, q);
@@ -459,7 +473,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
       for (uint64_t c = c0; c < c1; c++) {
         CU(cudaStreamSynchronize(st->stream[c % kStages]));
         const size_t n = chunk_size(c);
-        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, inst);
+        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, extra);
       }
     }
     return ECB_SUCCESS;
@@ -496,7 +510,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
         for (int part = 0; part < kScatterParts; part++) {
           const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
           HostPool::get().submit([=] {
-            scatter_results(src, stride, cmp, n, b, e, any_hit, instID, inst);
+            scatter_results(src, stride, cmp, n, b, e, any_hit, instID, extra);
             std::lock_guard<std::mutex> wl(st->mutex);
             if (--st->pending[k] == 0) st->cv.notify_all();
           });
@@ -612,7 +626,8 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   const size_t chunk = pipeline_chunk();
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
   const bool pinned = is_pinned(rays);
-  const bool compact = use_compact_results() && !s->has_triangles();  // mixed scenes: triangle hits carry a real normal
+  const bool compact = use_compact_results();
+  const int extra = s->instanced ? kExtraInst : s->has_triangles() ? kExtraNg : kExtraNone;
   // auto: pageable caller memory has to go through host threads anyway -> packed.  Pinned caller memory can be DMA'd as it
   // is, which costs no host cycles: packed wins when the process has a full pool (12 threads: 650 vs 510 Mrays/s on the
   // 16-core single-GPU host), compact when the host's cores are shared between ranks (2 ranks on 24 cores, 9 threads each:
@@ -632,6 +647,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     L.hit_geom = compact ? static_cast<uint32_t*>(st->d_cmp[k]) : nullptr;
     L.hit_rec = compact ? reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15))) : nullptr;
     L.hit_inst = (compact && s->instanced) ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
+    L.hit_ng = (compact && s->has_triangles()) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
     L.block_out = nullptr;
     L.counters = nullptr;
     L.queue = next_queue(s);
@@ -640,6 +656,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     if (s->has_triangles()) {  // AccelN order: triangle accel first, in place, then the compressed accel on the same rays
       cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, st->stream[k]);
       if (te != cudaSuccess) return te;
+      L.keep_results = compact ? 1u : 0u;
       g_launches.fetch_add(1);
     }
     if (exact) return ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
@@ -698,7 +715,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     cudaError_t le = launch(k, n);
     if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
     if (compact) {
-      const size_t bytes = ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (s->instanced ? 4 * n : 0));
+      const size_t bytes = ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (s->instanced ? 4 * n : 0) + (s->has_triangles() ? 12 * n : 0));
       CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], bytes, cudaMemcpyDeviceToHost, q));
       if (use_pool) {
         CU(cudaEventRecord(st->done[k], q));
@@ -710,12 +727,11 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
           const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
           const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
           const int device = s->device;
-          const bool per_ray_inst = s->instanced;
           cudaEvent_t ev = st->done[k];
           HostPool::get().submit([=] {
             cudaError_t ce = cudaSetDevice(device);
             if (ce == cudaSuccess) ce = cudaEventSynchronize(ev);
-            if (ce == cudaSuccess) scatter_results(src, stride, cmp, n, b, e, any_hit, instID, per_ray_inst);
+            if (ce == cudaSuccess) scatter_results(src, stride, cmp, n, b, e, any_hit, instID, extra);
             std::lock_guard<std::mutex> wl(st->mutex);
             if (ce != cudaSuccess && st->worker_error == cudaSuccess) st->worker_error = ce;
             if (--st->pending[k] == 0) st->cv.notify_all();
@@ -738,7 +754,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   if (compact) {  // small call: scatter inline
     for (uint64_t c = 0; c < n_chunks; c++) {
       const size_t n = chunk_size(c);
-      scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, s->instanced);
+      scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, extra);
     }
   } else if (!pinned) {
     const uint64_t tail0 = n_chunks > (uint64_t)kStages ? n_chunks - kStages : 0;

@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
           const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));  // 32, or 28 in packed records
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
-          if (L.hit_geom) L.hit_geom[index] = 0xFFFFFFFFu;
+          if (L.hit_geom && !L.keep_results) L.hit_geom[index] = 0xFFFFFFFFu;
           if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
             org[0] = r0.x; org[1] = r0.y; org[2] = r0.z;
             dir[0] = r1.x; dir[1] = r1.y; dir[2] = r1.z;
@@ -692,6 +692,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
           if (L.hit_geom) {  // compact result: the host layer scatters it into the caller's record
             L.hit_rec[index] = make_float4(hit.tfar, hit.u, hit.v, __uint_as_float(hit.primID));
             L.hit_geom[index] = hit.geomID;
+            if (L.hit_ng) { L.hit_ng[3 * index] = 1.f; L.hit_ng[3 * index + 1] = 0.f; L.hit_ng[3 * index + 2] = 0.f; }  // replaces a triangle hit's normal
           } else {
             uint8_t* op = L.out + index * L.out_stride;
             *reinterpret_cast<float*>(op + 32) = hit.tfar;
@@ -1074,7 +1075,8 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
     const uint8_t* rp = L.in + i * L.in_stride;
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
     const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + 32));
+    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
+    if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: this pass runs first and owns the initial state
     if (r0.w > tfar_in) continue;               // inactive stream ray
     if (ANYHIT && tfar_in < 0.0f) continue;     // bvh_intersector1.cpp:133
     const float org[3] = {r0.x, r0.y, r0.z};
@@ -1086,7 +1088,9 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
     int sp = 1;
     stack_ref[0] = ts.root;
     stack_dist[0] = 0xff800000u;
-    uint8_t* op = L.out + i * L.out_stride;
+    // compact result mode: tfar goes back into the input (staging) record, where the compressed-accel pass reads it
+    uint8_t* op = L.hit_geom ? nullptr : L.out + i * L.out_stride;
+    float* tfar_out = L.hit_geom ? reinterpret_cast<float*>(const_cast<uint8_t*>(rp) + L.tfar_offset) : reinterpret_cast<float*>(op + 32);
     if (ANYHIT) {
       bool occluded = false;
       while (sp > 0 && !occluded) {
@@ -1113,7 +1117,10 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
         for (uint32_t k = 0; k < num && !occluded; k++)
           occluded = tri4v_intersect<true>(ts.blocks + first + k, org, dir, r0.w, tfar_in, th);
       }
-      if (occluded) *reinterpret_cast<float*>(op + 32) = __int_as_float(0xff800000);
+      if (occluded) {
+        *tfar_out = __int_as_float(0xff800000);
+        if (L.hit_geom) L.hit_geom[i] = 0u;
+      }
     } else {
       Work work = {0u, 0u, 0u, 0u};
       float tfar = tfar_in;
@@ -1133,7 +1140,12 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
         }
         tr.tfar = tfar;  // bvh_intersector1.cpp:117
       }
-      if (found) {
+      if (found && L.hit_geom) {
+        *tfar_out = best.t;
+        L.hit_rec[i] = make_float4(best.t, best.u, best.v, __uint_as_float(best.primID));
+        L.hit_geom[i] = best.geomID;
+        L.hit_ng[3 * i] = best.ng[0]; L.hit_ng[3 * i + 1] = best.ng[1]; L.hit_ng[3 * i + 2] = best.ng[2];
+      } else if (found) {
         *reinterpret_cast<float*>(op + 32) = best.t;
         *reinterpret_cast<float4*>(op + 48) = make_float4(best.ng[0], best.ng[1], best.ng[2], best.u);
         *reinterpret_cast<float4*>(op + 64) =
@@ -1155,8 +1167,10 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScen
       const float dir[3] = {r1.x, r1.y, r1.z};
       occluded = sc.root != ECB_REF_EMPTY && trace_any(sc, org, dir, r0.w, tfar_in);
     }
-    if (L.hit_geom) L.hit_geom[i] = occluded ? 0u : 0xFFFFFFFFu;
-    else if (occluded) *reinterpret_cast<float*>(L.out + i * L.out_stride + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
+    if (L.hit_geom) {
+      if (!L.keep_results) L.hit_geom[i] = occluded ? 0u : 0xFFFFFFFFu;
+      else if (occluded) L.hit_geom[i] = 0u;  // the triangle pass wrote the entry first
+    } else if (occluded) *reinterpret_cast<float*>(L.out + i * L.out_stride + 32) = __int_as_float(0xff800000);  // -inf (bvh_intersector1.cpp:199)
   }
 }
 

@@ -43,6 +43,12 @@ struct EcbLaunch {
   // hit_rec[i] = {tfar, u, v, primID}.  20 bytes per ray go back over PCIe instead of the 80-byte record.
   float4* hit_rec;
   uint32_t* hit_geom;
+  // mixed scenes in compact result mode (triangle accel first, then the compressed accel on the same staging buffer): the
+  // triangle pass writes the tfar of its hit back into the INPUT record (which the second pass reads), its hit into the
+  // result arrays and the real normal into hit_ng (3 floats per ray); the second pass runs with keep_results = 1, i.e. it
+  // does not reset hit_geom when it picks up a ray, and writes the dummy normal (1,0,0) with its own hits
+  float* hit_ng = nullptr;
+  uint32_t keep_results = 0;
   uint32_t* hit_inst = nullptr;    // instancing scenes in compact result mode: instID[0] of the hit (geomID of the instance)
   uint32_t* block_out;            // optional: index of the block of the final hit per ray
   unsigned long long* counters;   // optional: instrumented variant (6 counters)

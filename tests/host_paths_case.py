@@ -36,7 +36,13 @@ def main(name, reps):
             assert (arr[:, untouched].view(np.uint32) == rays[:, untouched].view(np.uint32)).all(), (memory, width, "inputs modified")
             assert (arr[:, 20:] == 7.0).all(), (memory, width, "padding modified")
             hit = arr.view(np.uint32)[:, 18] != 0xFFFFFFFF
-            assert (arr[hit, 12:15] == np.float32([1, 0, 0])).all() and (arr[~hit, 12:15].view(np.uint32) == rays[~hit, 12:15].view(np.uint32)).all()
+            if "port_primary_ng" in g:   # mixed scene: triangle hits carry their real normal, compressed hits the dummy (1,0,0)
+                want_ng = np.concatenate([g["port_primary_ng"], g["port_bounce_ng"]] * reps)
+                assert (arr[hit, 12:15].view(np.uint32) == want_ng[hit].view(np.uint32)).all(), (memory, width, "Ng")
+                assert len(np.unique(arr.view(np.uint32)[hit, 18])) >= 2, "both accels must be hit"
+            else:
+                assert (arr[hit, 12:15] == np.float32([1, 0, 0])).all()
+            assert (arr[~hit, 12:15].view(np.uint32) == rays[~hit, 12:15].view(np.uint32)).all()
             if ptr is not None:
                 ecb.host_free(ptr)
         # any-hit: 48-byte RTCRay records
