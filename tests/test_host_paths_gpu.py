@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.parametrize("path", ["packed", "compact", "copy"])
 @pytest.mark.parametrize("scene,chunk,threads", [("cube_s4c2_leaf", "1024", "3"), ("cube_s4c2_leaf", "65536", "8"),
-                                                 ("cubeplane_s4c2_leaf", "2048", "4")])   # the last one: a mixed scene
+                                                 ("cube_s4c2_leaf", "8192", "6"),
+                                                 ("cubeplane_s4c2_leaf", "2048", "4")])   # a mixed scene
 def test_host_transfer_strategies(ecb, path, scene, chunk, threads):
     env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK=chunk, ECB200_HOST_THREADS=threads)
     r = subprocess.run([sys.executable, os.path.join(HERE, "host_paths_case.py"), scene, "5"], env=env,
