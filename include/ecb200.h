@@ -155,7 +155,11 @@ ECB_API ecbError ecbSceneSetBlocks(ecbScene* scene, const void* blocks, size_t b
  * rayhit / ray point to RTCRayHit (80 B) / RTCRay (48 B) structs, include/embree3/rtcore_ray.h:26-64, mutated in
  * place exactly like the reference does: on a hit tfar,Ng,u,v,primID,geomID,instID are overwritten, on a miss
  * nothing is written; occluded sets tfar=-inf.  Stream rays with tnear > tfar are inactive.  instID is what
- * RTCIntersectContext::instID[0] holds (RTC_INVALID_GEOMETRY_ID at top level). */
+ * RTCIntersectContext::instID[0] holds (RTC_INVALID_GEOMETRY_ID at top level).
+ * The arrays may live in any host memory (malloc'ed, stack, pinned), 4-byte aligned, byteStride a multiple of 4 that is
+ * at least the struct size.  Only the fields this path reads (org, tnear, dir, tfar: 32 bytes per ray) travel to the
+ * device and only result records travel back (20-32 bytes per ray); time, mask, id and flags are never read
+ * (the reference's intersectors for this accel do not read them either; EMBREE_RAY_MASK is off). */
 ECB_API ecbError ecbIntersect1(ecbScene* scene, uint32_t instID, void* rayhit);
 ECB_API ecbError ecbIntersect1M(ecbScene* scene, uint32_t instID, void* rayhit, uint32_t M, size_t byteStride);
 ECB_API ecbError ecbIntersect16(const int* valid, ecbScene* scene, uint32_t instID, void* rayhit16);
@@ -186,7 +190,8 @@ ECB_API ecbError ecbIntersectDeviceStats(ecbScene* scene, uint32_t instID, void*
 /* World-space unit normal of a block's local frame (third row of CompressedBVH::space), 3 floats per block, host copy. */
 ECB_API ecbError ecbSceneBlockNormals(const ecbScene* scene, float* normals_out, size_t capacity_floats);
 
-/* Pinned host staging memory for callers that want the fast DMA path on the host-buffer entry points. */
+/* Pinned host memory.  The host-buffer entry points do not need it (see above); it matters for the "compact" and
+ * "copy" transfer strategies, which DMA the caller's records directly. */
 ECB_API ecbError ecbHostAlloc(void** ptr, size_t bytes);
 ECB_API void ecbHostFree(void* ptr);
 
