@@ -326,8 +326,9 @@ size_t pipeline_chunk() {
 //   compact          : the full records go up (DMA straight from pinned caller memory; pageable memory is copied into
 //                      bounce buffers by the caller's thread), compact results come back as above
 //                      (ECB200_HOST_PATH=compact)                          -> 504-521 Mrays/s pinned, 96 pageable
-//   copy             : the full records travel both ways (ECB200_HOST_PATH=copy; also what instancing and mixed scenes
-//                      use, whose hits carry an instID / a real normal)   -> 452-462 Mrays/s pinned, 53 pageable
+//   copy             : the full records travel both ways (ECB200_HOST_PATH=copy)   -> 452-462 Mrays/s pinned, 53 pageable
+// Instancing scenes (hits carry the instance's geomID as instID[0]: one more word per ray in the result records) and mixed
+// scenes (triangle hits carry a real normal: three more floats) take the same strategies.
 // Default (no ECB200_HOST_PATH): packed for pageable caller memory and whenever the process has a full pool of 12 threads,
 // compact for pinned caller memory on a host whose cores are shared between ranks (see run_host).
 // Tried and dropped: results written by the kernel straight into the caller's mapped pinned array 363 Mrays/s (small PCIe
