@@ -1,0 +1,50 @@
+"""CPU test (no GPU): the product's host pipeline under ThreadSanitizer.
+
+csrc/ecb_api.cpp and csrc/ecb_import.cpp are compiled UNMODIFIED with g++ -fsanitize=thread against tests/mock_cuda (a
+host-only stand-in for the CUDA runtime in which every stream is a worker thread, and fake kernels whose results are a
+function of the ray alone).  tests/cpp/host_pipeline_check.cpp then drives the host-buffer entry points -- plain and mixed
+scenes, pinned and pageable caller memory, dense and padded strides, 1 ... 150 001 rays in 4 Ki-ray chunks (many more
+chunks than pipeline stages), closest hit / any hit / exact any hit, concurrent callers -- and checks every word of every
+record against the API contract.  ThreadSanitizer turns a staging buffer reused too early, a scatter job that outlives
+its call or an unprotected counter into a report, which fails the test.  This is test infrastructure: the mock is only
+ever found through this build line's -I, and the product never links it."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "embree_compressed_b200", "csrc")
+EXE = os.path.join(HERE, "cpp", "host_pipeline_check")
+SOURCES = [os.path.join(CSRC, "ecb_api.cpp"), os.path.join(CSRC, "ecb_import.cpp"),
+           os.path.join(HERE, "mock_cuda", "mock_kernels.cpp"), os.path.join(HERE, "cpp", "host_pipeline_check.cpp")]
+DEPS = SOURCES + [os.path.join(HERE, "mock_cuda", f) for f in ("cuda_runtime.h", "fake_trace.h")] + \
+    [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+
+
+@pytest.fixture(scope="module")
+def checker():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in DEPS):
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I" + os.path.join(HERE, "mock_cuda"),
+               "-I" + os.path.join(ROOT, "include"), "-o", EXE] + SOURCES + ["-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 and "sanitize" in r.stderr:
+            pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-300:])
+        assert r.returncode == 0, r.stderr
+    return EXE
+
+
+@pytest.mark.parametrize("path", ["packed", "compact", "copy"])
+def test_host_pipeline_under_thread_sanitizer(checker, path):
+    env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK="4096", ECB200_HOST_THREADS="4",
+               TSAN_OPTIONS="halt_on_error=0 exitcode=66")
+    r = subprocess.run([checker, os.path.join(HERE, "golden", "cube_s4c2_leaf.rimg"), os.path.join(HERE, "golden", "cubeplane_s4c2_leaf.rimg")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert "ThreadSanitizer" not in out, out[-4000:]
+    assert r.returncode == 0, out[-4000:]
+    assert "host pipeline check: ok (path=%s)" % path in r.stdout
