@@ -498,10 +498,20 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.impl == "reference":
-        out = run_reference(args, rank, world)
-    else:
-        out = run_ours(args, rank, world)
+    # stdout carries exactly ONE line, the JSON: libraries that print there (NCCL's version banner under NCCL_DEBUG=VERSION,
+    # a compiler, ...) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            out = run_reference(args, rank, world)
+        else:
+            out = run_ours(args, rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if rank == 0 and out is not None:
         print(json.dumps(out), flush=True)
 
