@@ -212,7 +212,8 @@ typedef int (*rtcGetInstanceBVH_b200_t)(RTCScene host_scene, struct RTCInstanceB
                                         float* world2local12, RTCScene* objects);
 /* optional third accessor: root of the BVH4<Triangle4v> that AccelN visits before the compressed accel (0 if none) */
 typedef int (*rtcGetTriangleBVH_b200_t)(RTCScene host_scene, uint64_t* root);
-/* Pinned host memory for ray arrays (fast DMA path of rtcIntersect1M / rtcOccluded1M); plain malloc memory also works. */
+/* Pinned host memory for ray arrays.  Optional: the stream calls run at full speed on plain malloc'ed arrays (the host
+ * pool packs the rays out of them); pinned arrays only matter for the "compact" / "copy" transfer strategies. */
 RTC_API void* rtcAllocRays_b200(size_t bytes);
 RTC_API void rtcFreeRays_b200(void* ptr);
 
