@@ -32,22 +32,29 @@ class EcbError(RuntimeError):
 
 class ImportDesc(C.Structure):
     _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("leaf_kind", C.c_uint32), ("proj_col_major", C.c_uint32),
-                ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32), ("bounds", C.c_float * 6)]
+                ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32), ("bounds", C.c_float * 6),
+                ("image_bytes", C.c_uint64)]
 
 
 class InstanceDesc(C.Structure):
     _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("n_instances", C.c_uint32), ("reserved", C.c_uint32),
-                ("geomIDs", C.c_void_p), ("world2local", C.c_void_p), ("objects", C.c_void_p), ("bounds", C.c_float * 6)]
+                ("geomIDs", C.c_void_p), ("world2local", C.c_void_p), ("objects", C.c_void_p), ("bounds", C.c_float * 6),
+                ("image_bytes", C.c_uint64)]
 
 
 class TriangleDesc(C.Structure):
-    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64)]
+    _fields_ = [("base", C.c_void_p), ("root", C.c_uint64), ("image_bytes", C.c_uint64)]
 
 
 class BuildDesc(C.Structure):
     _fields_ = [("leaf_kind", C.c_uint32), ("comp_level", C.c_uint32), ("n_blocks", C.c_uint32), ("reserved", C.c_uint32),
                 ("grids", C.c_void_p), ("space", C.c_void_p), ("world", C.c_void_p), ("uv", C.c_void_p),
                 ("geomIDs", C.c_void_p), ("primIDs", C.c_void_p)]
+
+
+class DeviceHits(C.Structure):
+    """ecbDeviceHits: compact result arrays of a device-buffer call (device pointers, one entry per ray)."""
+    _fields_ = [("geomID", C.c_void_p), ("hit", C.c_void_p), ("instID", C.c_void_p), ("Ng", C.c_void_p)]
 
 
 class SceneInfo(C.Structure):
@@ -73,6 +80,8 @@ SYMBOLS = {
     "ecbSceneSave": (C.c_int, [_vp, C.c_char_p]),
     "ecbSceneLoad": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "ecbSceneUpload": (C.c_int, [_vp, C.c_int]),
+    "ecbSceneUploadMulti": (C.c_int, [_vp, C.POINTER(C.c_int), _u32]),
+    "ecbSceneResidentDevices": (_u32, [_vp, C.POINTER(C.c_int), _u32]),
     "ecbSceneGetInfo": (C.c_int, [_vp, C.POINTER(SceneInfo)]),
     "ecbSceneRelease": (None, [_vp]),
     "ecbIntersect1": (C.c_int, [_vp, _u32, _vp]),
@@ -86,6 +95,14 @@ SYMBOLS = {
     "ecbIntersectDeviceEx": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
     "ecbIntersectDeviceStats": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp, _vp]),
     "ecbOccludedDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
+    "ecbIntersectDeviceCompact": (C.c_int, [_vp, _u32, _vp, _u64, _sz, C.POINTER(DeviceHits), _vp]),
+    "ecbOccludedDeviceCompact": (C.c_int, [_vp, _u32, _vp, _u64, _sz, C.POINTER(DeviceHits), _vp]),
+    "ecbDeviceAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
+    "ecbDeviceFree": (None, [_vp]),
+    "ecbIpcExport": (C.c_int, [_vp, _vp]),
+    "ecbIpcImport": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ecbIpcClose": (None, [_vp]),
+    "ecbPeerCopyAsync": (C.c_int, [_vp, _vp, _sz, _vp]),
     "ecbSceneBlockNormals": (C.c_int, [_vp, _vp, _sz]),
     "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbHostFree": (None, [_vp]),
@@ -235,6 +252,17 @@ class Scene:
         _check(_lib().ecbSceneUpload(self._h, device), "ecbSceneUpload")
         return self
 
+    def upload_multi(self, devices):
+        """ecbSceneUploadMulti: replicate on several CUDA devices; long host-buffer calls then fan out over them."""
+        arr = (C.c_int * len(devices))(*devices)
+        _check(_lib().ecbSceneUploadMulti(self._h, arr, len(devices)), "ecbSceneUploadMulti")
+        return self
+
+    def resident_devices(self):
+        arr = (C.c_int * 64)()
+        n = _lib().ecbSceneResidentDevices(self._h, arr, 64)
+        return [arr[i] for i in range(min(n, 64))]
+
     def release(self):
         if self._h:
             _lib().ecbSceneRelease(self._h)
@@ -323,5 +351,48 @@ class Scene:
         _check(_lib().ecbIntersectDeviceStats(self._h, inst_id, ptr, n, stride, counters_ptr, stream),
                "ecbIntersectDeviceStats")
 
+    def intersect_device_compact(self, ptr, n, geom_ptr, hit_ptr, stride=80, stream=0, inst_ptr=0, inst_id=INVALID_GEOMETRY_ID):
+        """ecbIntersectDeviceCompact: rays are only read; geomID[n] (uint32) and {tfar,u,v,primID}[n] (4 floats, hits only)
+        are written to the given device arrays (+ instID[n] on instancing scenes)."""
+        out = DeviceHits(geom_ptr, hit_ptr, inst_ptr or None, None)
+        _check(_lib().ecbIntersectDeviceCompact(self._h, inst_id, ptr, n, stride, C.byref(out), stream), "ecbIntersectDeviceCompact")
+
+    def occluded_device_compact(self, ptr, n, geom_ptr, stride=48, stream=0, inst_id=INVALID_GEOMETRY_ID):
+        out = DeviceHits(geom_ptr, None, None, None)
+        _check(_lib().ecbOccludedDeviceCompact(self._h, inst_id, ptr, n, stride, C.byref(out), stream), "ecbOccludedDeviceCompact")
+
     def occluded_device(self, ptr, n, stride=48, stream=0, inst_id=INVALID_GEOMETRY_ID):
         _check(_lib().ecbOccludedDevice(self._h, inst_id, ptr, n, stride, stream), "ecbOccludedDevice")
+
+
+# ---- multi-GPU gather plumbing (one process per GPU): device buffers another process can map over NVLink ----
+def device_alloc(n_bytes):
+    p = _vp()
+    _check(_lib().ecbDeviceAlloc(C.byref(p), n_bytes), "ecbDeviceAlloc")
+    return p.value
+
+
+def device_free(ptr):
+    _lib().ecbDeviceFree(ptr)
+
+
+def ipc_export(ptr):
+    """64-byte CUDA IPC handle of a buffer from device_alloc (bytes)."""
+    h = (C.c_uint8 * 64)()
+    _check(_lib().ecbIpcExport(ptr, h), "ecbIpcExport")
+    return bytes(h)
+
+
+def ipc_import(handle):
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = _vp()
+    _check(_lib().ecbIpcImport(h, C.byref(p)), "ecbIpcImport")
+    return p.value
+
+
+def ipc_close(ptr):
+    _lib().ecbIpcClose(ptr)
+
+
+def peer_copy_async(dst, src, n_bytes, stream=0):
+    _check(_lib().ecbPeerCopyAsync(dst, src, n_bytes, stream), "ecbPeerCopyAsync")

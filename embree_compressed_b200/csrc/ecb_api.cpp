@@ -31,13 +31,14 @@ std::atomic<uint64_t> g_launches{0};
 
 constexpr size_t kRayHitBytes = 80, kRayBytes = 48;
 constexpr int kStages = 8;
+constexpr int kSmallStages = 2;              // stages of a small staging context (calls of up to kInlineRaysMax rays)
 constexpr size_t kPackedBytes = 32;         // packed input record of the host-buffer path: {org.xyz,tnear},{dir.xyz,tfar}
 constexpr int kPackPartsDefault = 8;        // pack jobs per chunk (ECB200_PACK_PARTS overrides for experiments)
 constexpr int kPackAheadDefault = 3;        // chunks packed ahead of the one being issued to the GPU (ECB200_PACK_AHEAD)
 constexpr size_t kChunkRaysMax = 1u << 17;  // capacity of a staging buffer: 128 Ki rays
-constexpr size_t kCompactBytesMax = kChunkRaysMax * 32 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n] (+ instID[n]: instancing; + Ng[3n]: mixed scenes)
 constexpr int kScatterParts = 4;            // scatter jobs per chunk
 constexpr uint32_t kQueueRing = 256;
+constexpr uint64_t kMultiDeviceRaysMin = 1u << 18;  // host-buffer calls of at least this many rays fan out over all devices the scene is resident on
 constexpr uint64_t kInlineRaysMax = 16384;  // calls up to this size pack and scatter on the caller's thread (measured: 8 Ki rays 59 us inline, 101 us through the pool)
 
 ecbError cuda_fail(cudaError_t e, const char* what) {
@@ -58,10 +59,15 @@ ecbError cuda_fail(cudaError_t e, const char* what) {
 
 void ecb_set_error(const std::string& msg) { g_last_error = msg; }
 
-// Host-buffer pipeline: kStages chunks in flight, each H2D -> kernel(s) -> D2H on its own stream over fixed device
-// buffers; created lazily per scene.
+// Host-buffer pipeline context: `n_stages` chunks in flight, each H2D -> kernel(s) -> D2H on its own stream over fixed
+// device buffers of `cap` rays.  Contexts belong to a Residency (one device copy of a scene) and are handed out to one
+// call at a time: concurrent callers get their own context, so rtcIntersect1 / rtcIntersect1M stay re-entrant like the
+// reference's (kernels/common/rtcore.cpp:287-304: no lock on the query path).  Two sizes: small (calls of up to
+// kInlineRaysMax rays: packets, rtcIntersect1, short streams) and large (the 8-stage pipeline of long streams).
 struct Staging {
   int device = -1;
+  int n_stages = 0;
+  size_t cap = 0;  // rays per stage
   cudaStream_t stream[kStages] = {};
   cudaEvent_t done[kStages] = {};
   void* d_buf[kStages] = {};
@@ -79,6 +85,7 @@ struct Staging {
   int pending[kStages] = {};
   cudaError_t worker_error = cudaSuccess;
   ~Staging() {
+    if (device >= 0) cudaSetDevice(device);
     for (int i = 0; i < kStages; i++) {
       if (d_buf[i]) cudaFree(d_buf[i]);
       if (h_pin[i]) cudaFreeHost(h_pin[i]);
@@ -91,76 +98,87 @@ struct Staging {
   }
 };
 
+// One device copy of a scene: device arrays, the kernel-argument structs that point at them, the ring of dynamic
+// ray-fetch cursors and the staging contexts of the host-buffer entry points.  A scene has one Residency per device it
+// was uploaded to; whatever was allocated is freed by the destructor (also when an upload fails half way).
+struct Residency {
+  int device = -1;
+  void* d_top = nullptr;
+  void* d_blocks = nullptr;
+  EcbDeviceScene dev{};
+  void* d_tri_top = nullptr;
+  void* d_tri_blocks = nullptr;
+  EcbDeviceTriScene tri_dev{nullptr, nullptr, ECB_REF_EMPTY, 0u, 0u};
+  void* d_items = nullptr;
+  void* d_instances = nullptr;
+  void* d_objects = nullptr;
+  EcbDeviceInstScene inst_dev{};
+  unsigned long long* d_queues = nullptr;  // ring of device words used as dynamic ray-fetch cursors, one per launch in flight
+  std::atomic<uint32_t> next_queue{0};
+  // staging contexts: [0] small, [1] large
+  std::mutex pool_mutex;
+  std::condition_variable pool_cv;
+  std::vector<Staging*> idle[2];
+  int created[2] = {0, 0};
+  ~Residency() {
+    if (device >= 0) cudaSetDevice(device);
+    for (int k = 0; k < 2; k++)
+      for (Staging* st : idle[k]) delete st;
+    void* ptrs[] = {d_top, d_blocks, d_tri_top, d_tri_blocks, d_items, d_instances, d_objects, d_queues};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  }
+};
+
 namespace {
 
-ecbError ensure_resident(ecbScene* s, int device);
+Residency* find_residency(const ecbScene* s, int device) {  // caller holds s->mutex
+  for (Residency* r : s->res)
+    if (r->device == device) return r;
+  return nullptr;
+}
+
+ecbError ensure_resident(ecbScene* s, int device, Residency** out);
+
+cudaError_t upload_array(void** dst, const void* src, size_t bytes) {
+  if (!bytes) return cudaSuccess;
+  cudaError_t e = cudaMalloc(dst, bytes);
+  return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+}
 
 // instancing scene: object scenes first, then instance-level nodes / items / instance records / object table
-ecbError upload_instanced(ecbScene* s, int device) {
+ecbError upload_instanced(ecbScene* s, Residency* r) {
   std::vector<EcbDeviceScene> objs;
   for (ecbScene* o : s->objects) {
-    ecbError e = ensure_resident(o, device);
+    Residency* ro = nullptr;
+    ecbError e = ensure_resident(o, r->device, &ro);
     if (e != ECB_SUCCESS) return e;
-    objs.push_back(o->dev);
+    objs.push_back(ro->dev);
   }
-  auto up = [](void** dst, const void* src, size_t bytes) -> cudaError_t {
-    if (!bytes) return cudaSuccess;
-    cudaError_t e = cudaMalloc(dst, bytes);
-    return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
-  };
-  CU(up(&s->d_top, s->top.data(), s->top.size() * sizeof(EcbTopNode)));
-  CU(up(&s->d_items, s->items.data(), s->items.size() * 4));
-  CU(up(&s->d_instances, s->instances.data(), s->instances.size() * sizeof(EcbInstance)));
-  CU(up(&s->d_objects, objs.data(), objs.size() * sizeof(EcbDeviceScene)));
-  EcbDeviceInstScene& d = s->inst_dev;
-  d.nodes = static_cast<const EcbTopNode*>(s->d_top);
-  d.items = static_cast<const uint32_t*>(s->d_items);
-  d.instances = static_cast<const EcbInstance*>(s->d_instances);
-  d.objects = static_cast<const EcbDeviceScene*>(s->d_objects);
+  CU(cudaSetDevice(r->device));
+  CU(upload_array(&r->d_top, s->top.data(), s->top.size() * sizeof(EcbTopNode)));
+  CU(upload_array(&r->d_items, s->items.data(), s->items.size() * 4));
+  CU(upload_array(&r->d_instances, s->instances.data(), s->instances.size() * sizeof(EcbInstance)));
+  CU(upload_array(&r->d_objects, objs.data(), objs.size() * sizeof(EcbDeviceScene)));
+  EcbDeviceInstScene& d = r->inst_dev;
+  d.nodes = static_cast<const EcbTopNode*>(r->d_top);
+  d.items = static_cast<const uint32_t*>(r->d_items);
+  d.instances = static_cast<const EcbInstance*>(r->d_instances);
+  d.objects = static_cast<const EcbDeviceScene*>(r->d_objects);
   d.root = s->root;
   d.n_nodes = (uint32_t)s->top.size();
   d.n_items = (uint32_t)s->items.size();
   d.n_instances = (uint32_t)s->instances.size();
   d.n_objects = (uint32_t)objs.size();
-  CU(cudaMalloc(reinterpret_cast<void**>(&s->d_queues), kQueueRing * sizeof(unsigned long long)));
-  CU(cudaMemset(s->d_queues, 0, kQueueRing * sizeof(unsigned long long)));
-  s->device = device;
-  s->info.device = device;
   return ECB_SUCCESS;
 }
 
-ecbError ensure_resident(ecbScene* s, int device) {
-  std::lock_guard<std::mutex> lock(s->mutex);
-  if (s->device >= 0) {
-    if (device >= 0 && device != s->device) {
-      g_last_error = "scene is resident on another device";
-      return ECB_ERROR_INVALID_OPERATION;
-    }
-    return ECB_SUCCESS;
-  }
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    g_last_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    return ECB_ERROR_NO_DEVICE;
-  }
-  if (device < 0) {
-    CU(cudaGetDevice(&device));
-  }
-  CU(cudaSetDevice(device));
-  if (s->instanced) return upload_instanced(s, device);
-  const size_t top_bytes = s->top.size() * sizeof(EcbTopNode);
-  if (top_bytes) {
-    CU(cudaMalloc(&s->d_top, top_bytes));
-    CU(cudaMemcpy(s->d_top, s->top.data(), top_bytes, cudaMemcpyHostToDevice));
-  }
-  if (!s->blocks.empty()) {
-    CU(cudaMalloc(&s->d_blocks, s->blocks.size()));
-    CU(cudaMemcpy(s->d_blocks, s->blocks.data(), s->blocks.size(), cudaMemcpyHostToDevice));
-  }
-  EcbDeviceScene& d = s->dev;
-  d.top = static_cast<const EcbTopNode*>(s->d_top);
-  d.blocks = static_cast<const uint8_t*>(s->d_blocks);
+ecbError upload_plain(ecbScene* s, Residency* r) {
+  CU(upload_array(&r->d_top, s->top.data(), s->top.size() * sizeof(EcbTopNode)));
+  CU(upload_array(&r->d_blocks, s->blocks.data(), s->blocks.size()));
+  EcbDeviceScene& d = r->dev;
+  d.top = static_cast<const EcbTopNode*>(r->d_top);
+  d.blocks = static_cast<const uint8_t*>(r->d_blocks);
   d.root = s->root;
   d.n_top = (uint32_t)s->top.size();
   d.n_blocks = s->info.n_blocks;
@@ -171,50 +189,142 @@ ecbError ensure_resident(ecbScene* s, int device) {
   d.elems = s->elems;
   d.grid_width = s->grid_width;
   d.rcp_edges = s->rcp_edges;
-  s->tri_dev = EcbDeviceTriScene{nullptr, nullptr, ECB_REF_EMPTY, 0u, 0u};
   if (s->has_triangles()) {  // mixed scene: triangle accel next to the compressed one
-    if (!s->tri_top.empty()) {
-      CU(cudaMalloc(&s->d_tri_top, s->tri_top.size() * sizeof(EcbTopNode)));
-      CU(cudaMemcpy(s->d_tri_top, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode), cudaMemcpyHostToDevice));
-    }
-    if (!s->tri_blocks.empty()) {
-      CU(cudaMalloc(&s->d_tri_blocks, s->tri_blocks.size() * sizeof(EcbTriBlock)));
-      CU(cudaMemcpy(s->d_tri_blocks, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock), cudaMemcpyHostToDevice));
-    }
-    s->tri_dev.nodes = static_cast<const EcbTopNode*>(s->d_tri_top);
-    s->tri_dev.blocks = static_cast<const EcbTriBlock*>(s->d_tri_blocks);
-    s->tri_dev.root = s->tri_root;
-    s->tri_dev.n_nodes = (uint32_t)s->tri_top.size();
-    s->tri_dev.n_blocks = (uint32_t)s->tri_blocks.size();
+    CU(upload_array(&r->d_tri_top, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode)));
+    CU(upload_array(&r->d_tri_blocks, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock)));
+    r->tri_dev.nodes = static_cast<const EcbTopNode*>(r->d_tri_top);
+    r->tri_dev.blocks = static_cast<const EcbTriBlock*>(r->d_tri_blocks);
+    r->tri_dev.root = s->tri_root;
+    r->tri_dev.n_nodes = (uint32_t)s->tri_top.size();
+    r->tri_dev.n_blocks = (uint32_t)s->tri_blocks.size();
   }
-  CU(cudaMalloc(reinterpret_cast<void**>(&s->d_queues), kQueueRing * sizeof(unsigned long long)));
-  CU(cudaMemset(s->d_queues, 0, kQueueRing * sizeof(unsigned long long)));
-  s->device = device;
-  s->info.device = device;
   return ECB_SUCCESS;
 }
 
-unsigned long long* next_queue(ecbScene* s) { return s->d_queues + (s->next_queue.fetch_add(1) % kQueueRing); }
-
-ecbError ensure_staging(ecbScene* s) {
-  if (s->staging) return ECB_SUCCESS;
-  Staging* st = new (std::nothrow) Staging;
-  if (!st) return ECB_ERROR_OUT_OF_MEMORY;
-  st->device = s->device;
-  for (int i = 0; i < kStages; i++) {
-    cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->done[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], kChunkRaysMax * kRayHitBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&st->d_cmp[i], kCompactBytesMax);
-    if (e == cudaSuccess) e = cudaMallocHost(&st->h_cmp[i], kCompactBytesMax);
-    if (e == cudaSuccess) e = cudaMallocHost(&st->h_pk[i], kChunkRaysMax * kPackedBytes);
-    if (e != cudaSuccess) {
-      delete st;
-      return cuda_fail(e, "staging allocation");
+// Makes the scene resident on `device` (-1: the primary residency, created on the calling thread's current device when
+// there is none yet) and returns that residency.  Leaves the calling thread's current device set to it.
+ecbError ensure_resident(ecbScene* s, int device, Residency** out) {
+  if (device < 0) {
+    if (Residency* p = s->primary.load(std::memory_order_acquire)) {
+      *out = p;
+      return ECB_SUCCESS;
     }
   }
-  s->staging = st;
+  std::lock_guard<std::mutex> lock(s->mutex);
+  if (device < 0 && !s->res.empty()) {
+    *out = s->res[0];
+    return ECB_SUCCESS;
+  }
+  if (device >= 0)
+    if (Residency* r = find_residency(s, device)) {
+      *out = r;
+      return ECB_SUCCESS;
+    }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_last_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return ECB_ERROR_NO_DEVICE;
+  }
+  if (device < 0) CU(cudaGetDevice(&device));
+  CU(cudaSetDevice(device));
+  Residency* r = new (std::nothrow) Residency;
+  if (!r) return ECB_ERROR_OUT_OF_MEMORY;
+  r->device = device;
+  ecbError err = s->instanced ? upload_instanced(s, r) : upload_plain(s, r);
+  if (err == ECB_SUCCESS) {
+    cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&r->d_queues), kQueueRing * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(r->d_queues, 0, kQueueRing * sizeof(unsigned long long));
+    if (ce != cudaSuccess) err = cuda_fail(ce, "ray-fetch cursor allocation");
+  }
+  if (err != ECB_SUCCESS) {
+    delete r;  // frees whatever the failed upload had allocated
+    return err;
+  }
+  s->res.push_back(r);
+  if (s->res.size() == 1) {
+    s->info.device = device;
+    s->primary.store(r, std::memory_order_release);
+  }
+  *out = r;
   return ECB_SUCCESS;
+}
+
+unsigned long long* next_queue(Residency* r) { return r->d_queues + (r->next_queue.fetch_add(1) % kQueueRing); }
+
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  int v = e ? atoi(e) : dflt;
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+Staging* create_staging(int device, bool large) {
+  Staging* st = new (std::nothrow) Staging;
+  if (!st) return nullptr;
+  st->device = device;
+  st->n_stages = large ? kStages : kSmallStages;
+  st->cap = large ? kChunkRaysMax : (size_t)kInlineRaysMax;
+  const size_t cmp_bytes = st->cap * 32 + 64;  // per chunk: geomID[n] (padded to 16 B) + {tfar,u,v,primID}[n] (+ instID[n]: instancing; + Ng[3n]: mixed scenes)
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < st->n_stages && e == cudaSuccess; i++) {
+    e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_buf[i], st->cap * kRayHitBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_cmp[i], cmp_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&st->h_cmp[i], cmp_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&st->h_pk[i], st->cap * kPackedBytes);
+  }
+  if (e != cudaSuccess) {
+    delete st;
+    cuda_fail(e, "staging allocation");
+    return nullptr;
+  }
+  return st;
+}
+
+// Hands a staging context of the residency to the calling thread for the duration of one call.  Small contexts are
+// created on demand (one per concurrent caller, kept for reuse); large ones up to ECB200_HOST_CONTEXTS (default 2: two
+// long streams overlap, a third waits for one of them).
+struct StagingLease {
+  Residency* r = nullptr;
+  Staging* st = nullptr;
+  int kind = 0;
+  ~StagingLease() {
+    if (!st) return;
+    {
+      std::lock_guard<std::mutex> l(r->pool_mutex);
+      r->idle[kind].push_back(st);
+    }
+    r->pool_cv.notify_one();
+  }
+};
+
+ecbError acquire_staging(Residency* r, bool large, StagingLease* lease) {
+  static const int kLargeMax = env_int("ECB200_HOST_CONTEXTS", 2, 1, 16);
+  const int kind = large ? 1 : 0, limit = large ? kLargeMax : 256;
+  lease->r = r;
+  lease->kind = kind;
+  std::unique_lock<std::mutex> l(r->pool_mutex);
+  for (;;) {
+    if (!r->idle[kind].empty()) {
+      lease->st = r->idle[kind].back();
+      r->idle[kind].pop_back();
+      return ECB_SUCCESS;
+    }
+    if (r->created[kind] < limit) {
+      r->created[kind]++;
+      l.unlock();
+      Staging* st = create_staging(r->device, large);
+      if (!st) {
+        l.lock();
+        r->created[kind]--;
+        return g_last_error.find("out of memory") != std::string::npos ? ECB_ERROR_OUT_OF_MEMORY : ECB_ERROR_CUDA;
+      }
+      lease->st = st;
+      return ECB_SUCCESS;
+    }
+    r->pool_cv.wait(l);
+  }
 }
 
 bool is_pinned(const void* p) {
@@ -433,18 +543,14 @@ void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n,
 //   pool: pack -> caller's thread: H2D (32 B/ray), kernel, D2H (20 B/ray, 4 for any-hit), event -> completion thread: waits
 //   for the event, hands the scatter jobs to the pool -> pool: scatter into the caller's records.
 // Pool threads never wait on the GPU; the caller's thread stays kPackAhead chunks ahead with the pack jobs.
-int env_int(const char* name, int dflt, int lo, int hi) {
-  const char* e = getenv(name);
-  int v = e ? atoi(e) : dflt;
-  return v < lo ? lo : (v > hi ? hi : v);
-}
-
-ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride) {
+ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride) {
   static const int kPackParts = env_int("ECB200_PACK_PARTS", kPackPartsDefault, 1, 64);
-  static const int kPackAhead = env_int("ECB200_PACK_AHEAD", kPackAheadDefault, 1, kStages - 2);
+  static const int kPackAheadCfg = env_int("ECB200_PACK_AHEAD", kPackAheadDefault, 1, kStages - 2);
+  const int nst = st->n_stages;
+  const int kPackAhead = kPackAheadCfg < nst - 1 ? kPackAheadCfg : (nst > 1 ? nst - 1 : 1);
   // rays per chunk: the configured size for long calls; a mid-sized call (a tile, a scanline block) is cut into about four
   // chunks (each chunk costs the caller's thread ~45 us of job hand-offs and CUDA calls, so not more) so that its pack, upload, traversal, download and scatter overlap instead of running one after the other
-  size_t chunk = pipeline_chunk();
+  size_t chunk = pipeline_chunk() < st->cap ? pipeline_chunk() : st->cap;
   if (M > kInlineRaysMax && M < 4 * chunk) {
     size_t c4 = (size_t)((M + 3) / 4);
     c4 = (c4 + 1023) & ~size_t(1023);
@@ -459,7 +565,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
   const int extra = inst ? kExtraInst : mixed ? kExtraNg : kExtraNone;
   auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (inst ? 4 * n : 0) + (mixed ? 12 * n : 0)); };
   auto issue = [&](uint64_t c) -> ecbError {  // H2D of the packed records, kernel, D2H of the compact results
-    const int k = (int)(c % kStages);
+    const int k = (int)(c % nst);
     const size_t n = chunk_size(c);
     cudaStream_t q = st->stream[k];
     CU(cudaMemcpyAsync(st->d_buf[k], st->h_pk[k], n * kPackedBytes, cudaMemcpyHostToDevice, q));
@@ -478,34 +584,34 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
     L.hit_ng = mixed ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
     L.block_out = nullptr;
     L.counters = nullptr;
-    L.queue = next_queue(s);
+    L.queue = next_queue(r);
     g_launches.fetch_add(1);
     if (mixed) {  // AccelN order: triangle accel first, then the compressed accel on the same staging records
-      cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, q);
+      cudaError_t te = ecb_launch_triangles(r->tri_dev, r->device, L, occluded, q);
       if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
       L.keep_results = 1;
       g_launches.fetch_add(1);
     }
-    cudaError_t le = inst                  ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
-                     : (occluded && !exact) ? ecb_launch_occluded(s->dev, s->device, L, q)
-                                            : ecb_launch_intersect(s->dev, s->device, L, q);
+    cudaError_t le = inst                  ? ecb_launch_instanced(r->inst_dev, r->device, L, occluded, q)
+                     : (occluded && !exact) ? ecb_launch_occluded(r->dev, r->device, L, q)
+                                            : ecb_launch_intersect(r->dev, r->device, L, q);
     if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
     CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], cmp_bytes(n), cudaMemcpyDeviceToHost, q));
     return ECB_SUCCESS;
   };
 
   if (M <= kInlineRaysMax) {  // small calls (rtcIntersect1, packets, short streams): everything inline on the caller's thread
-    for (uint64_t c0 = 0; c0 < n_chunks; c0 += kStages) {
-      const uint64_t c1 = c0 + kStages < n_chunks ? c0 + kStages : n_chunks;
+    for (uint64_t c0 = 0; c0 < n_chunks; c0 += nst) {
+      const uint64_t c1 = c0 + nst < n_chunks ? c0 + nst : n_chunks;
       for (uint64_t c = c0; c < c1; c++) {
-        pack_rays(base + c * chunk * stride, stride, static_cast<uint8_t*>(st->h_pk[c % kStages]), 0, chunk_size(c));
+        pack_rays(base + c * chunk * stride, stride, static_cast<uint8_t*>(st->h_pk[c % nst]), 0, chunk_size(c));
         ecbError e = issue(c);
         if (e != ECB_SUCCESS) return e;
       }
       for (uint64_t c = c0; c < c1; c++) {
-        CU(cudaStreamSynchronize(st->stream[c % kStages]));
+        CU(cudaStreamSynchronize(st->stream[c % nst]));
         const size_t n = chunk_size(c);
-        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, extra);
+        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % nst]), n, 0, n, any_hit, instID, extra);
       }
     }
     return ECB_SUCCESS;
@@ -518,12 +624,12 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
     st->scat_submitted = 0;
     st->stop = false;
   }
-  const int device = s->device;
+  const int device = r->device;
   // completion thread: chunk by chunk, waits for the chunk's results and hands the scatter jobs to the pool
   auto completion_body = [=] {
     cudaError_t se = cudaSetDevice(device);
     for (uint64_t c = 0; c < n_chunks; c++) {
-      const int k = (int)(c % kStages);
+      const int k = (int)(c % nst);
       {
         std::unique_lock<std::mutex> wl(st->mutex);
         st->cv.wait(wl, [&] { return st->gpu_issued > c || st->stop; });
@@ -576,7 +682,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
       completion->join();
       std::unique_lock<std::mutex> wl(st->mutex);
       st->cv.wait(wl, [&] {
-        for (int k = 0; k < kStages; k++)
+        for (int k = 0; k < st->n_stages; k++)
           if (st->pending[k] || st->pack_pending[k]) return false;
         return true;
       });
@@ -585,13 +691,13 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
 
   for (uint64_t c = 0; c < n_chunks + kPackAhead; c++) {
     if (c < n_chunks) {
-      const int k = (int)(c % kStages);
+      const int k = (int)(c % nst);
       const size_t n = chunk_size(c);
       const int parts = (int)(n / 4096 < 1 ? 1 : (n / 4096 > (size_t)kPackParts ? (size_t)kPackParts : n / 4096));  // >= 4 Ki rays per pack job
       {
         std::unique_lock<std::mutex> wl(st->mutex);
-        if (c >= (uint64_t)kStages)  // the stage's previous chunk is done down to its last scatter job
-          st->cv.wait(wl, [&] { return st->scat_submitted > c - kStages && st->pending[k] == 0; });
+        if (c >= (uint64_t)nst)  // the stage's previous chunk is done down to its last scatter job
+          st->cv.wait(wl, [&] { return st->scat_submitted > c - nst && st->pending[k] == 0; });
         st->pack_pending[k] = parts;
       }
       const uint8_t* src = base + c * chunk * stride;
@@ -607,7 +713,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
     }
     if (c >= (uint64_t)kPackAhead) {
       const uint64_t d = c - kPackAhead;
-      const int k = (int)(d % kStages);
+      const int k = (int)(d % nst);
       {
         std::unique_lock<std::mutex> wl(st->mutex);
         st->cv.wait(wl, [&] { return st->pack_pending[k] == 0; });
@@ -626,7 +732,7 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
     std::unique_lock<std::mutex> wl(st->mutex);
     st->cv.wait(wl, [&] {
       if (st->scat_submitted < n_chunks) return false;
-      for (int k = 0; k < kStages; k++)
+      for (int k = 0; k < st->n_stages; k++)
         if (st->pending[k]) return false;
       return true;
     });
@@ -635,37 +741,36 @@ ecbError run_host_packed(ecbScene* s, Staging* st, bool occluded, bool exact, ui
   return ECB_SUCCESS;
 }
 
-// Shared by intersect (elem = 80) and occluded (elem = 48).
-ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact = false) {
-  if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
-  if (exact && s->instanced) {
-    g_last_error = "exact any-hit is not available on instancing scenes";
-    return ECB_ERROR_INVALID_OPERATION;
-  }
+// Transfer strategy of one host-buffer call (see host_path()).  auto: pageable caller memory has to go through host threads
+// anyway -> packed.  Pinned caller memory can be DMA'd as it is, which costs no host cycles: packed wins when the process
+// has a full pool (12 threads: 650 vs 510 Mrays/s on the 16-core single-GPU host), compact when the host's cores are shared
+// -- between ranks (2 ranks on 24 cores, 9 threads each: 743 packed vs 855 compact) or between the devices of one scene
+// (ecbSceneUploadMulti: the links add up, the pool does not).
+HostPath choose_path(bool pinned, size_t n_devices) {
+  const HostPath p = host_path();
+  if (p != kPathAuto) return p;
+  if (!pinned) return kPathPacked;
+  if (n_devices > 1) return kPathCompact;
+  return HostPool::get().size() >= 12 ? kPathPacked : kPathCompact;
+}
+
+// One host-buffer call (or one device's share of it) on one residency.  Shared by intersect (elem = 80) and occluded (48).
+ecbError run_host_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact,
+                     HostPath path) {
   const size_t elem = occluded ? kRayBytes : kRayHitBytes;
-  if (stride < elem || (stride & 3)) {
-    g_last_error = "byteStride must be a multiple of 4 and at least the struct size";
-    return ECB_ERROR_INVALID_ARGUMENT;
-  }
-  if (M == 0) return ECB_SUCCESS;
-  ecbError err = ensure_resident(s, -1);
+  CU(cudaSetDevice(r->device));
+  StagingLease lease;
+  ecbError err = acquire_staging(r, M > kInlineRaysMax, &lease);
   if (err != ECB_SUCCESS) return err;
-  std::lock_guard<std::mutex> lock(s->mutex);
-  CU(cudaSetDevice(s->device));
-  err = ensure_staging(s);
-  if (err != ECB_SUCCESS) return err;
-  Staging* st = s->staging;
+  Staging* st = lease.st;
+  const int nst = st->n_stages;
   uint8_t* base = static_cast<uint8_t*>(rays);
-  const size_t chunk = pipeline_chunk();
+  const size_t chunk = pipeline_chunk() < st->cap ? pipeline_chunk() : st->cap;
   const uint64_t n_chunks = (M + chunk - 1) / chunk;
   const bool pinned = is_pinned(rays);
-  const bool compact = use_compact_results();
+  const bool compact = path != kPathCopy;
   const int extra = s->instanced ? kExtraInst : s->has_triangles() ? kExtraNg : kExtraNone;
-  // auto: pageable caller memory has to go through host threads anyway -> packed.  Pinned caller memory can be DMA'd as it
-  // is, which costs no host cycles: packed wins when the process has a full pool (12 threads: 650 vs 510 Mrays/s on the
-  // 16-core single-GPU host), compact when the host's cores are shared between ranks (2 ranks on 24 cores, 9 threads each:
-  // 743 packed vs 855 compact)
-  if (compact && (host_path() == kPathPacked || (host_path() == kPathAuto && (!pinned || HostPool::get().size() >= 12)))) return run_host_packed(s, st, occluded, exact, instID, base, M, stride);
+  if (path == kPathPacked) return run_host_packed(s, r, st, occluded, exact, instID, base, M, stride);
   const bool use_pool = compact && M > 8192;  // small calls (rtcIntersect1, packets) scatter inline
 
   auto launch = [&](int k, size_t n) -> cudaError_t {
@@ -683,22 +788,22 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     L.hit_ng = (compact && s->has_triangles()) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
     L.block_out = nullptr;
     L.counters = nullptr;
-    L.queue = next_queue(s);
+    L.queue = next_queue(r);
     g_launches.fetch_add(1);
-    if (s->instanced) return ecb_launch_instanced(s->inst_dev, s->device, L, occluded, st->stream[k]);
+    if (s->instanced) return ecb_launch_instanced(r->inst_dev, r->device, L, occluded, st->stream[k]);
     if (s->has_triangles()) {  // AccelN order: triangle accel first, in place, then the compressed accel on the same rays
-      cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, st->stream[k]);
+      cudaError_t te = ecb_launch_triangles(r->tri_dev, r->device, L, occluded, st->stream[k]);
       if (te != cudaSuccess) return te;
       L.keep_results = compact ? 1u : 0u;
       g_launches.fetch_add(1);
     }
-    if (exact) return ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
-    return occluded ? ecb_launch_occluded(s->dev, s->device, L, st->stream[k]) : ecb_launch_intersect(s->dev, s->device, L, st->stream[k]);
+    if (exact) return ecb_launch_intersect(r->dev, r->device, L, st->stream[k]);
+    return occluded ? ecb_launch_occluded(r->dev, r->device, L, st->stream[k]) : ecb_launch_intersect(r->dev, r->device, L, st->stream[k]);
   };
 
   if (!pinned) {
-    for (int i = 0; i < kStages; i++)
-      if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], kChunkRaysMax * kRayHitBytes));
+    for (int i = 0; i < st->n_stages; i++)
+      if (!st->h_pin[i]) CU(cudaMallocHost(&st->h_pin[i], st->cap * kRayHitBytes));
   }
   auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
   auto unpack = [&](uint64_t c, int k) {  // full-record mode, pageable caller memory: bounce buffer -> caller's array
@@ -720,7 +825,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     ~Drain() {
       std::unique_lock<std::mutex> wl(st->mutex);
       st->cv.wait(wl, [&] {
-        for (int k = 0; k < kStages; k++)
+        for (int k = 0; k < st->n_stages; k++)
           if (st->pending[k]) return false;
         return true;
       });
@@ -728,7 +833,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
   } drain{st};
 
   for (uint64_t c = 0; c < n_chunks; c++) {
-    const int k = (int)(c % kStages);
+    const int k = (int)(c % nst);
     const size_t n = chunk_size(c);
     uint8_t* src = base + c * chunk * stride;
     cudaStream_t q = st->stream[k];
@@ -739,7 +844,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     } else {
       // pageable caller memory: bounce through pinned buffers; first drain this stage's previous round trip
       CU(cudaStreamSynchronize(q));
-      if (!compact && c >= (uint64_t)kStages) unpack(c - kStages, k);
+      if (!compact && c >= (uint64_t)nst) unpack(c - nst, k);
       uint8_t* hb = static_cast<uint8_t*>(st->h_pin[k]);
       if (stride == elem) memcpy(hb, src, n * elem);
       else for (size_t i = 0; i < n; i++) memcpy(hb + i * elem, src + i * stride, elem);
@@ -759,7 +864,7 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
         for (int part = 0; part < kScatterParts; part++) {
           const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
           const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
-          const int device = s->device;
+          const int device = r->device;
           cudaEvent_t ev = st->done[k];
           HostPool::get().submit([=] {
             cudaError_t ce = cudaSetDevice(device);
@@ -779,32 +884,108 @@ ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint6
     }
   }
   if (use_pool) {
-    for (int k = 0; k < kStages; k++) wait_stage(k);
+    for (int k = 0; k < st->n_stages; k++) wait_stage(k);
     if (st->worker_error != cudaSuccess) return cuda_fail(st->worker_error, "result scatter");
     return ECB_SUCCESS;
   }
-  for (int k = 0; k < kStages; k++) CU(cudaStreamSynchronize(st->stream[k]));
+  for (int k = 0; k < st->n_stages; k++) CU(cudaStreamSynchronize(st->stream[k]));
   if (compact) {  // small call: scatter inline
     for (uint64_t c = 0; c < n_chunks; c++) {
       const size_t n = chunk_size(c);
-      scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % kStages]), n, 0, n, any_hit, instID, extra);
+      scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % nst]), n, 0, n, any_hit, instID, extra);
     }
   } else if (!pinned) {
-    const uint64_t tail0 = n_chunks > (uint64_t)kStages ? n_chunks - kStages : 0;
-    for (uint64_t c = tail0; c < n_chunks; c++) unpack(c, (int)(c % kStages));
+    const uint64_t tail0 = n_chunks > (uint64_t)nst ? n_chunks - nst : 0;
+    for (uint64_t c = tail0; c < n_chunks; c++) unpack(c, (int)(c % nst));
   }
   return ECB_SUCCESS;
 }
 
+// Entry of every host-buffer call: argument checks, lazy upload, and -- for a scene resident on several devices
+// (ecbSceneUploadMulti) and a call long enough to pay for it -- the fan-out: the ray range is cut into one contiguous part
+// per device, each part runs the single-device pipeline on its own thread (its own staging context, stream set and PCIe
+// link), all of them share the host pool, and the results land in the caller's array -- there is no gather step.
+ecbError run_host(ecbScene* s, bool occluded, uint32_t instID, void* rays, uint64_t M, size_t stride, bool exact = false) {
+  if (!s || (!rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
+  if (exact && s->instanced) {
+    g_last_error = "exact any-hit is not available on instancing scenes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
+  const size_t elem = occluded ? kRayBytes : kRayHitBytes;
+  if (stride < elem || (stride & 3)) {
+    g_last_error = "byteStride must be a multiple of 4 and at least the struct size";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  if (M == 0) return ECB_SUCCESS;
+  Residency* r0 = nullptr;
+  ecbError err = ensure_resident(s, -1, &r0);
+  if (err != ECB_SUCCESS) return err;
+  std::vector<Residency*> devs;
+  if (M >= kMultiDeviceRaysMin) {
+    std::lock_guard<std::mutex> lock(s->mutex);
+    devs = s->res;
+  }
+  const bool pinned = is_pinned(rays);
+  if (devs.size() <= 1) return run_host_on(s, r0, occluded, instID, rays, M, stride, exact, choose_path(pinned, 1));
+  const HostPath path = choose_path(pinned, devs.size());
+  const size_t n = devs.size();
+  std::vector<ecbError> errs(n, ECB_SUCCESS);
+  std::vector<std::string> msgs(n);
+  std::vector<std::thread> threads;
+  auto part = [&](size_t i) {
+    // contiguous parts, multiples of 1024 rays
+    const uint64_t per = ((M + n - 1) / n + 1023) & ~uint64_t(1023);
+    const uint64_t b = per * i < M ? per * i : M, e = per * (i + 1) < M ? per * (i + 1) : M;
+    if (e <= b) return;
+    errs[i] = run_host_on(s, devs[i], occluded, instID, static_cast<uint8_t*>(rays) + b * stride, e - b, stride, exact, path);
+    if (errs[i] != ECB_SUCCESS) msgs[i] = g_last_error;
+  };
+  try {
+    for (size_t i = 1; i < n; i++) threads.emplace_back(part, i);
+  } catch (const std::exception& ex) {  // never let an exception cross the C ABI
+    for (auto& t : threads) t.join();
+    g_last_error = std::string("cannot start a device thread: ") + ex.what();
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+  part(0);
+  for (auto& t : threads) t.join();
+  cudaSetDevice(r0->device);
+  for (size_t i = 0; i < n; i++)
+    if (errs[i] != ECB_SUCCESS) {
+      g_last_error = "device " + std::to_string(devs[i]->device) + ": " + msgs[i];
+      return errs[i];
+    }
+  return ECB_SUCCESS;
+}
+
+// residency a device pointer belongs to: the only one, or the one on the device that owns the allocation
+ecbError residency_for_pointer(ecbScene* s, const void* d_ptr, Residency** out) {
+  Residency* r0 = nullptr;
+  ecbError err = ensure_resident(s, -1, &r0);
+  if (err != ECB_SUCCESS) return err;
+  *out = r0;
+  std::lock_guard<std::mutex> lock(s->mutex);
+  if (s->res.size() <= 1 || !d_ptr) return ECB_SUCCESS;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, d_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return ECB_SUCCESS;
+  }
+  if (a.type == cudaMemoryTypeDevice)
+    if (Residency* r = find_residency(s, a.device)) *out = r;
+  return ECB_SUCCESS;
+}
+
 ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, uint64_t M, size_t stride, uint32_t* d_block_out,
-                    void* stream, unsigned long long* d_counters = nullptr, bool exact = false) {
+                    void* stream, unsigned long long* d_counters = nullptr, bool exact = false, const ecbDeviceHits* compact_out = nullptr) {
   if (!s || (!d_rays && M)) return ECB_ERROR_INVALID_ARGUMENT;
   const size_t elem = occluded ? kRayBytes : kRayHitBytes;
   if (stride < elem || (stride & 15) || (reinterpret_cast<uintptr_t>(d_rays) & 15)) {
     g_last_error = "device rays must be 16-byte aligned with a byteStride that is a multiple of 16";
     return ECB_ERROR_INVALID_ARGUMENT;
   }
-  ecbError err = ensure_resident(s, -1);
+  Residency* r = nullptr;
+  ecbError err = residency_for_pointer(s, d_rays, &r);
   if (err != ECB_SUCCESS) return err;
   if (M == 0) return ECB_SUCCESS;
   cudaStream_t q = static_cast<cudaStream_t>(stream);
@@ -820,24 +1001,40 @@ ecbError run_device(ecbScene* s, bool occluded, uint32_t instID, void* d_rays, u
   L.hit_geom = nullptr;
   L.block_out = d_block_out;
   L.counters = d_counters;
-  L.queue = next_queue(s);
-  if (s->instanced && (d_block_out || d_counters)) {
-    g_last_error = "block output / work counters are not available on instancing scenes";
+  L.queue = next_queue(r);
+  if (s->instanced && d_block_out) {
+    g_last_error = "block output is not available on instancing scenes";
     return ECB_ERROR_INVALID_OPERATION;
   }
   if (exact && s->instanced) {
     g_last_error = "exact any-hit is not available on instancing scenes";
     return ECB_ERROR_INVALID_OPERATION;
   }
+  if (compact_out) {  // compact result records instead of in-place write-back (what a multi-GPU frame gather moves)
+    if (!compact_out->geomID || (!occluded && !compact_out->hit) || (s->instanced && !occluded && !compact_out->instID) ||
+        (s->has_triangles() && !occluded && !compact_out->Ng)) {
+      g_last_error = "compact output needs geomID[], hit[] (closest hit), instID[] (instancing scenes) and Ng[] (mixed scenes)";
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+    L.out = nullptr;
+    L.hit_geom = compact_out->geomID;
+    L.hit_rec = reinterpret_cast<float4*>(compact_out->hit);
+    L.hit_inst = s->instanced ? compact_out->instID : nullptr;
+    L.hit_ng = s->has_triangles() ? compact_out->Ng : nullptr;
+  }
   if (!s->instanced && s->has_triangles()) {
-    cudaError_t te = ecb_launch_triangles(s->tri_dev, s->device, L, occluded, q);
+    if (compact_out) {
+      g_last_error = "compact output of a mixed scene needs writable input records (the triangle pass hands tfar to the second pass through them): use the in-place call";
+      return ECB_ERROR_INVALID_OPERATION;
+    }
+    cudaError_t te = ecb_launch_triangles(r->tri_dev, r->device, L, occluded, q);
     if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
     g_launches.fetch_add(1);
   }
-  cudaError_t le = s->instanced ? ecb_launch_instanced(s->inst_dev, s->device, L, occluded, q)
-                   : exact      ? ecb_launch_intersect(s->dev, s->device, L, q)
-                   : occluded   ? ecb_launch_occluded(s->dev, s->device, L, q)
-                                : ecb_launch_intersect(s->dev, s->device, L, q);
+  cudaError_t le = s->instanced ? ecb_launch_instanced(r->inst_dev, r->device, L, occluded, q)
+                   : exact      ? ecb_launch_intersect(r->dev, r->device, L, q)
+                   : occluded   ? ecb_launch_occluded(r->dev, r->device, L, q)
+                                : ecb_launch_intersect(r->dev, r->device, L, q);
   if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
   g_launches.fetch_add(1);
   return ECB_SUCCESS;
@@ -872,6 +1069,7 @@ ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_o
   ecbImportDesc d;
   memset(&d, 0, sizeof(d));
   d.base = image;
+  d.image_bytes = total;
   d.root = root;
   d.leaf_kind = w[1];
   d.subdiv_level = w[2];
@@ -884,6 +1082,7 @@ ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_o
   if (e == ECB_SUCCESS && tri_root) {
     ecbTriangleDesc t;
     t.base = image;
+    t.image_bytes = total;
     t.root = tri_root;
     e = ecb_import_triangles(&t, *scene_out);
     if (e != ECB_SUCCESS) {
@@ -894,25 +1093,50 @@ ecbError ecbSceneImportImage(const void* image, size_t bytes, ecbScene** scene_o
   return e;
 }
 
-ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out) {
+}  // extern "C"
+
+static bool read_file(const char* path, std::vector<uint8_t>& buf) {
   std::ifstream f(path, std::ios::binary | std::ios::ate);
-  if (!f) {
-    g_last_error = std::string("cannot open ") + (path ? path : "(null)");
-    return ECB_ERROR_INVALID_ARGUMENT;
-  }
-  const size_t n = (size_t)f.tellg();
-  std::vector<char> buf(n);
+  if (!f) return false;
+  const std::streamoff end = f.tellg();
+  if (end < 0) return false;
+  buf.resize((size_t)end);
   f.seekg(0);
-  f.read(buf.data(), (std::streamsize)n);
-  return ecbSceneImportImage(buf.data(), n, scene_out);
+  if (end > 0 && !f.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)end)) return false;
+  return true;
 }
 
-ecbError ecbSceneSave(const ecbScene* s, const char* path) {
-  if (!s || !path) return ECB_ERROR_INVALID_ARGUMENT;
-  if (s->instanced) {
-    g_last_error = "instancing scenes are not serialisable (save the object scenes)";
-    return ECB_ERROR_INVALID_OPERATION;
+extern "C" ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out) {
+  if (!path || !scene_out) return ECB_ERROR_INVALID_ARGUMENT;
+  std::vector<uint8_t> buf;
+  try {
+    if (!read_file(path, buf)) {
+      g_last_error = std::string("cannot read ") + path;
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+  } catch (const std::exception&) {
+    return ECB_ERROR_OUT_OF_MEMORY;
   }
+  return ecbSceneImportImage(buf.data(), buf.size(), scene_out);
+}
+
+// ---- native blob (ecbSceneSave / ecbSceneLoad) -----------------------------------------------------------------------
+// plain scene:      EcbBlobHeader | top nodes | blocks | [EcbBlobTriTrailer | triangle nodes | triangle blocks]
+// instancing scene: EcbBlobInstHeader | n_objects x { u64 bytes | plain-scene blob } | instance-level nodes | items | instances
+namespace {
+
+struct EcbBlobInstHeader {
+  char magic[8];  // "ECB200I1"
+  uint32_t version, n_objects, n_instances, n_items, n_nodes, root, depth, reserved;
+  float bounds[6];
+};
+
+void append(std::vector<uint8_t>& out, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  out.insert(out.end(), b, b + n);
+}
+
+void save_plain(const ecbScene* s, std::vector<uint8_t>& out) {
   EcbBlobHeader h;
   memset(&h, 0, sizeof(h));
   memcpy(h.magic, "ECB200S1", 8);
@@ -933,14 +1157,9 @@ ecbError ecbSceneSave(const ecbScene* s, const char* path) {
   h.reference_bytes = s->info.reference_bytes;
   h.top_bytes = s->top.size() * sizeof(EcbTopNode);
   h.block_bytes = s->blocks.size();
-  std::ofstream f(path, std::ios::binary);
-  if (!f) {
-    g_last_error = std::string("cannot write ") + path;
-    return ECB_ERROR_INVALID_ARGUMENT;
-  }
-  f.write(reinterpret_cast<const char*>(&h), sizeof(h));
-  f.write(reinterpret_cast<const char*>(s->top.data()), (std::streamsize)h.top_bytes);
-  f.write(reinterpret_cast<const char*>(s->blocks.data()), (std::streamsize)h.block_bytes);
+  append(out, &h, sizeof(h));
+  append(out, s->top.data(), h.top_bytes);
+  append(out, s->blocks.data(), h.block_bytes);
   if (s->has_triangles()) {
     EcbBlobTriTrailer t;
     memset(&t, 0, sizeof(t));
@@ -949,23 +1168,71 @@ ecbError ecbSceneSave(const ecbScene* s, const char* path) {
     t.n_blocks = (uint32_t)s->tri_blocks.size();
     t.root = s->tri_root;
     t.depth = s->tri_depth;
-    f.write(reinterpret_cast<const char*>(&t), sizeof(t));
-    f.write(reinterpret_cast<const char*>(s->tri_top.data()), (std::streamsize)(s->tri_top.size() * sizeof(EcbTopNode)));
-    f.write(reinterpret_cast<const char*>(s->tri_blocks.data()), (std::streamsize)(s->tri_blocks.size() * sizeof(EcbTriBlock)));
+    append(out, &t, sizeof(t));
+    append(out, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode));
+    append(out, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock));
   }
-  return f ? ECB_SUCCESS : ECB_ERROR_UNKNOWN;
 }
 
-ecbError ecbSceneLoad(const char* path, ecbScene** out) {
-  if (!path || !out) return ECB_ERROR_INVALID_ARGUMENT;
-  std::ifstream f(path, std::ios::binary);
+// The kernels trust the arrays, so a blob is checked before it becomes a scene.  `leaf_ok(ref)` validates a leaf reference.
+// Nodes are emitted in pre-order, so every child node index must be larger than its parent's: that rules out cycles (and
+// shared subtrees are harmless).  Returns the height of the tree (the importer's max leaf depth), or -1.
+template <typename LeafOk>
+int validate_tree(const std::vector<EcbTopNode>& nodes, uint32_t root, LeafOk leaf_ok) {
+  const uint32_t n = (uint32_t)nodes.size();
+  if (root == ECB_REF_EMPTY) return 0;
+  if (root & ECB_REF_LEAF) return leaf_ok(root) ? 0 : -1;
+  if (root >= n) return -1;
+  std::vector<uint16_t> height(n, 0);
+  for (uint32_t i = n; i-- > 0;) {
+    uint32_t h = 0;
+    for (int k = 0; k < 4; k++) {
+      const uint32_t c = nodes[i].child[k];
+      if (c == ECB_REF_EMPTY) continue;
+      if (c & ECB_REF_LEAF) {
+        if (!leaf_ok(c)) return -1;
+        h = h > 1 ? h : 1;
+      } else {
+        if (c <= i || c >= n) return -1;
+        h = h > (uint32_t)height[c] + 1 ? h : (uint32_t)height[c] + 1;
+      }
+    }
+    if (h > 1000) return -1;
+    height[i] = (uint16_t)h;
+  }
+  return (int)height[root];
+}
+
+struct Cursor {
+  const uint8_t* p;
+  size_t left;
+  bool take(void* dst, size_t n) {
+    if (n > left) return false;
+    memcpy(dst, p, n);
+    p += n;
+    left -= n;
+    return true;
+  }
+};
+
+ecbError load_plain(Cursor& c, ecbScene** out) {
   EcbBlobHeader h;
-  if (!f || !f.read(reinterpret_cast<char*>(&h), sizeof(h)) || memcmp(h.magic, "ECB200S1", 8) != 0 || h.version != 1) {
-    g_last_error = std::string("not an ECB200 scene blob: ") + path;
+  if (!c.take(&h, sizeof(h)) || memcmp(h.magic, "ECB200S1", 8) != 0 || h.version != 1) {
+    g_last_error = "not an ECB200 scene blob";
     return ECB_ERROR_INVALID_ARGUMENT;
   }
-  if (h.top_bytes != (uint64_t)h.n_top * sizeof(EcbTopNode) || h.block_bytes != (uint64_t)h.n_blocks * h.block_stride ||
-      h.comp_level < 1 || h.comp_level > ECB_MAX_C || h.leaf_kind > ECB_LEAF_BOX || 3 * h.top_depth + 4 > ECB_MAX_TOP_STACK) {
+  // every derived constant is recomputed from (leaf kind, C) and must match; the array sizes must fit the data that is there
+  bool ok = h.comp_level >= 1 && h.comp_level <= ECB_MAX_C && h.leaf_kind <= ECB_LEAF_BOX;
+  uint32_t leaf_offset = 0, stride = 0;
+  if (ok) {
+    ecb_block_layout(h.comp_level, h.leaf_kind, &leaf_offset, &stride);
+    const uint32_t cells = 1u << (2 * h.comp_level);
+    ok = h.block_stride == stride && h.leaf_offset == leaf_offset && h.elems == (cells - 1) / 3 && h.grid_width == (1u << h.comp_level) + 1 &&
+         h.rcp_edges == 1.0f / (float)(1u << h.comp_level) && h.top_bytes == (uint64_t)h.n_top * sizeof(EcbTopNode) &&
+         h.block_bytes == (uint64_t)h.n_blocks * stride && h.top_bytes <= c.left && h.block_bytes <= c.left - h.top_bytes &&
+         h.n_blocks < ECB_REF_LEAF;
+  }
+  if (!ok) {
     g_last_error = "corrupt scene blob header";
     return ECB_ERROR_INVALID_ARGUMENT;
   }
@@ -973,27 +1240,17 @@ ecbError ecbSceneLoad(const char* path, ecbScene** out) {
   if (!s) return ECB_ERROR_OUT_OF_MEMORY;
   s->top.resize(h.n_top);
   s->blocks.resize(h.block_bytes);
-  f.read(reinterpret_cast<char*>(s->top.data()), (std::streamsize)h.top_bytes);
-  f.read(reinterpret_cast<char*>(s->blocks.data()), (std::streamsize)h.block_bytes);
-  if (!f) {
+  c.take(s->top.data(), h.top_bytes);
+  c.take(s->blocks.data(), h.block_bytes);
+  const int depth = validate_tree(s->top, h.root, [&](uint32_t ref) { return (ref & ~ECB_REF_LEAF) < h.n_blocks; });
+  if (depth < 0 || 3 * depth + 4 > (int)ECB_MAX_TOP_STACK) {
     delete s;
-    g_last_error = "truncated scene blob";
+    g_last_error = "scene blob has an out-of-range / backward child reference or a tree too deep for the traversal stack";
     return ECB_ERROR_INVALID_ARGUMENT;
   }
-  // every child reference must stay inside the arrays: the kernels trust the blob
-  for (const EcbTopNode& n : s->top)
-    for (int i = 0; i < 4; i++) {
-      const uint32_t c = n.child[i];
-      const bool ok = c == ECB_REF_EMPTY || ((c & ECB_REF_LEAF) ? (c & ~ECB_REF_LEAF) < h.n_blocks : c < h.n_top);
-      if (!ok) {
-        delete s;
-        g_last_error = "scene blob has an out-of-range child reference";
-        return ECB_ERROR_INVALID_ARGUMENT;
-      }
-    }
   s->root = h.root;
-  s->block_stride = h.block_stride;
-  s->leaf_offset = h.leaf_offset;
+  s->block_stride = stride;
+  s->leaf_offset = leaf_offset;
   s->elems = h.elems;
   s->grid_width = h.grid_width;
   s->rcp_edges = h.rcp_edges;
@@ -1003,8 +1260,8 @@ ecbError ecbSceneLoad(const char* path, ecbScene** out) {
   in.comp_level = h.comp_level;
   in.n_top_nodes = h.n_top;
   in.n_blocks = h.n_blocks;
-  in.top_depth = h.top_depth;
-  in.block_stride = h.block_stride;
+  in.top_depth = (uint32_t)depth;
+  in.block_stride = stride;
   in.top_node_bytes = sizeof(EcbTopNode);
   in.device_bytes = h.top_bytes + h.block_bytes;
   in.reference_bytes = h.reference_bytes;
@@ -1012,42 +1269,192 @@ ecbError ecbSceneLoad(const char* path, ecbScene** out) {
   memcpy(in.bounds, h.bounds, sizeof(in.bounds));
   in.device = -1;
   EcbBlobTriTrailer t;
-  if (f.read(reinterpret_cast<char*>(&t), sizeof(t))) {  // optional: triangle accel of a mixed scene
-    bool ok = memcmp(t.magic, "ECB200T1", 8) == 0 && 3 * t.depth + 4 <= ECB_MAX_TOP_STACK && t.n_blocks < (1u << 27);
+  if (c.left >= sizeof(t) && memcmp(c.p, "ECB200T1", 8) == 0) {  // optional: triangle accel of a mixed scene
+    c.take(&t, sizeof(t));
+    ok = t.n_blocks < (1u << 27) && (uint64_t)t.n_nodes * sizeof(EcbTopNode) <= c.left &&
+         (uint64_t)t.n_blocks * sizeof(EcbTriBlock) <= c.left - (uint64_t)t.n_nodes * sizeof(EcbTopNode) && t.root != ECB_REF_EMPTY;
+    int tdepth = -1;
     if (ok) {
       s->tri_top.resize(t.n_nodes);
       s->tri_blocks.resize(t.n_blocks);
-      f.read(reinterpret_cast<char*>(s->tri_top.data()), (std::streamsize)(t.n_nodes * sizeof(EcbTopNode)));
-      f.read(reinterpret_cast<char*>(s->tri_blocks.data()), (std::streamsize)(t.n_blocks * sizeof(EcbTriBlock)));
-      ok = (bool)f;
+      c.take(s->tri_top.data(), t.n_nodes * sizeof(EcbTopNode));
+      c.take(s->tri_blocks.data(), (size_t)t.n_blocks * sizeof(EcbTriBlock));
+      tdepth = validate_tree(s->tri_top, t.root, [&](uint32_t ref) {
+        const uint32_t first = (ref & ~ECB_REF_LEAF) >> 3, num = ref & 7u;
+        return (uint64_t)first + num <= t.n_blocks;
+      });
     }
-    auto ref_ok = [&](uint32_t c) {
-      if (c == ECB_REF_EMPTY) return true;
-      if (!(c & ECB_REF_LEAF)) return c < t.n_nodes;
-      const uint32_t first = (c & ~ECB_REF_LEAF) >> 3, num = c & 7u;
-      return (uint64_t)first + num <= t.n_blocks;
-    };
-    if (ok) {
-      ok = ref_ok(t.root) && t.root != ECB_REF_EMPTY;
-      for (const EcbTopNode& n : s->tri_top)
-        for (int i = 0; i < 4; i++) ok = ok && ref_ok(n.child[i]);
-    }
-    if (!ok) {
+    if (tdepth < 0 || 3 * tdepth + 4 > (int)ECB_MAX_TOP_STACK) {
       delete s;
       g_last_error = "corrupt triangle section in scene blob";
       return ECB_ERROR_INVALID_ARGUMENT;
     }
     s->tri_root = t.root;
-    s->tri_depth = t.depth;
+    s->tri_depth = (uint32_t)tdepth;
     in.device_bytes += t.n_nodes * sizeof(EcbTopNode) + (uint64_t)t.n_blocks * sizeof(EcbTriBlock);
   }
   *out = s;
   return ECB_SUCCESS;
 }
 
+ecbError load_instanced(Cursor& c, ecbScene** out) {
+  EcbBlobInstHeader h;
+  if (!c.take(&h, sizeof(h)) || h.version != 1 || h.n_objects > (1u << 20) || h.n_items >= (1u << 27)) {
+    g_last_error = "corrupt instancing-scene blob header";
+    return ECB_ERROR_INVALID_ARGUMENT;
+  }
+  ecbScene* s = new (std::nothrow) ecbScene;
+  if (!s) return ECB_ERROR_OUT_OF_MEMORY;
+  s->instanced = true;
+  auto fail = [&](const char* msg, ecbError e) {
+    for (ecbScene* o : s->objects) ecbSceneRelease(o);
+    s->objects.clear();
+    delete s;
+    if (msg) g_last_error = msg;
+    return e;
+  };
+  for (uint32_t i = 0; i < h.n_objects; i++) {
+    uint64_t bytes = 0;
+    if (!c.take(&bytes, 8) || bytes > c.left) return fail("truncated instancing-scene blob", ECB_ERROR_INVALID_ARGUMENT);
+    Cursor sub{c.p, (size_t)bytes};
+    ecbScene* o = nullptr;
+    const ecbError e = load_plain(sub, &o);
+    if (e != ECB_SUCCESS) return fail(nullptr, e);
+    if (o->has_triangles()) {
+      ecbSceneRelease(o);
+      return fail("instanced object scenes cannot carry a triangle accel", ECB_ERROR_INVALID_ARGUMENT);
+    }
+    s->objects.push_back(o);  // the instancing scene owns the reference the load created
+    c.p += bytes;
+    c.left -= (size_t)bytes;
+  }
+  const uint64_t need = (uint64_t)h.n_nodes * sizeof(EcbTopNode) + (uint64_t)h.n_items * 4 + (uint64_t)h.n_instances * sizeof(EcbInstance);
+  if (need > c.left) return fail("truncated instancing-scene blob", ECB_ERROR_INVALID_ARGUMENT);
+  s->top.resize(h.n_nodes);
+  s->items.resize(h.n_items);
+  s->instances.resize(h.n_instances);
+  c.take(s->top.data(), h.n_nodes * sizeof(EcbTopNode));
+  c.take(s->items.data(), (size_t)h.n_items * 4);
+  c.take(s->instances.data(), (size_t)h.n_instances * sizeof(EcbInstance));
+  bool ok = true;
+  for (uint32_t it : s->items) ok = ok && it < h.n_instances;
+  for (const EcbInstance& in : s->instances) ok = ok && in.object < h.n_objects;
+  const int depth = ok ? validate_tree(s->top, h.root, [&](uint32_t ref) {
+    const uint32_t first = (ref & ~ECB_REF_LEAF) >> 3, num = ref & 7u;
+    return (uint64_t)first + num <= h.n_items;
+  }) : -1;
+  if (depth < 0 || 3 * depth + 4 > (int)ECB_MAX_TOP_STACK) return fail("instancing-scene blob has an out-of-range reference", ECB_ERROR_INVALID_ARGUMENT);
+  s->root = h.root;
+  ecbSceneInfo& in = s->info;
+  memset(&in, 0, sizeof(in));
+  in.n_top_nodes = h.n_nodes;
+  in.top_depth = (uint32_t)depth;
+  in.top_node_bytes = sizeof(EcbTopNode);
+  in.device_bytes = s->top.size() * sizeof(EcbTopNode) + s->items.size() * 4 + s->instances.size() * sizeof(EcbInstance);
+  for (const EcbInstance& i : s->instances) {
+    in.micro_triangles += s->objects[i.object]->info.micro_triangles;
+    in.n_blocks += s->objects[i.object]->info.n_blocks;
+  }
+  for (ecbScene* o : s->objects) in.device_bytes += o->info.device_bytes;
+  in.leaf_kind = s->objects.empty() ? 0 : s->objects[0]->info.leaf_kind;
+  memcpy(in.bounds, h.bounds, sizeof(in.bounds));
+  in.device = -1;
+  *out = s;
+  return ECB_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+ecbError ecbSceneSave(const ecbScene* s, const char* path) {
+  if (!s || !path) return ECB_ERROR_INVALID_ARGUMENT;
+  try {
+    std::vector<uint8_t> out;
+    if (s->instanced) {
+      EcbBlobInstHeader h;
+      memset(&h, 0, sizeof(h));
+      memcpy(h.magic, "ECB200I1", 8);
+      h.version = 1;
+      h.n_objects = (uint32_t)s->objects.size();
+      h.n_instances = (uint32_t)s->instances.size();
+      h.n_items = (uint32_t)s->items.size();
+      h.n_nodes = (uint32_t)s->top.size();
+      h.root = s->root;
+      h.depth = s->info.top_depth;
+      memcpy(h.bounds, s->info.bounds, sizeof(h.bounds));
+      append(out, &h, sizeof(h));
+      for (const ecbScene* o : s->objects) {
+        std::vector<uint8_t> sub;
+        save_plain(o, sub);
+        const uint64_t bytes = sub.size();
+        append(out, &bytes, 8);
+        append(out, sub.data(), sub.size());
+      }
+      append(out, s->top.data(), s->top.size() * sizeof(EcbTopNode));
+      append(out, s->items.data(), s->items.size() * 4);
+      append(out, s->instances.data(), s->instances.size() * sizeof(EcbInstance));
+    } else {
+      save_plain(s, out);
+    }
+    std::ofstream f(path, std::ios::binary);
+    if (!f) {
+      g_last_error = std::string("cannot write ") + path;
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+    f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
+    return f ? ECB_SUCCESS : ECB_ERROR_UNKNOWN;
+  } catch (const std::exception&) {  // never let an exception cross the C ABI
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+}
+
+ecbError ecbSceneLoad(const char* path, ecbScene** out) {
+  if (!path || !out) return ECB_ERROR_INVALID_ARGUMENT;
+  try {
+    std::vector<uint8_t> buf;
+    if (!read_file(path, buf) || buf.size() < 8) {
+      g_last_error = std::string("not an ECB200 scene blob: ") + path;
+      return ECB_ERROR_INVALID_ARGUMENT;
+    }
+    Cursor c{buf.data(), buf.size()};
+    if (memcmp(buf.data(), "ECB200I1", 8) == 0) return load_instanced(c, out);
+    return load_plain(c, out);
+  } catch (const std::exception&) {  // std::bad_alloc / length_error from a crafted size: never across the C ABI
+    g_last_error = "out of memory while loading the scene blob";
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+}
+
 ecbError ecbSceneUpload(ecbScene* s, int device) {
   if (!s) return ECB_ERROR_INVALID_ARGUMENT;
-  return ensure_resident(s, device);
+  Residency* r = nullptr;
+  return ensure_resident(s, device, &r);
+}
+
+ecbError ecbSceneUploadMulti(ecbScene* s, const int* devices, uint32_t n_devices) {
+  if (!s || (n_devices && !devices)) return ECB_ERROR_INVALID_ARGUMENT;
+  int current = -1;
+  cudaGetDevice(&current);
+  ecbError err = ECB_SUCCESS;
+  for (uint32_t i = 0; i < n_devices && err == ECB_SUCCESS; i++) {
+    if (devices[i] < 0) {
+      g_last_error = "device ordinals must be >= 0";
+      err = ECB_ERROR_INVALID_ARGUMENT;
+      break;
+    }
+    Residency* r = nullptr;
+    err = ensure_resident(s, devices[i], &r);
+  }
+  if (current >= 0) cudaSetDevice(current);  // uploads switch the calling thread's device: put it back
+  return err;
+}
+
+uint32_t ecbSceneResidentDevices(const ecbScene* s, int* devices_out, uint32_t capacity) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> lock(s->mutex);
+  for (uint32_t i = 0; i < s->res.size() && i < capacity && devices_out; i++) devices_out[i] = s->res[i]->device;
+  return (uint32_t)s->res.size();
 }
 
 ecbError ecbSceneGetInfo(const ecbScene* s, ecbSceneInfo* info) {
@@ -1060,18 +1467,10 @@ void ecbSceneRelease(ecbScene* s) {
   if (!s) return;
   if (--s->refs > 0) return;  // still referenced by an instancing scene
   for (ecbScene* o : s->objects) ecbSceneRelease(o);
-  if (s->device >= 0) {
-    cudaSetDevice(s->device);
-    delete s->staging;
-    if (s->d_top) cudaFree(s->d_top);
-    if (s->d_blocks) cudaFree(s->d_blocks);
-    if (s->d_queues) cudaFree(s->d_queues);
-    if (s->d_items) cudaFree(s->d_items);
-    if (s->d_instances) cudaFree(s->d_instances);
-    if (s->d_objects) cudaFree(s->d_objects);
-    if (s->d_tri_top) cudaFree(s->d_tri_top);
-    if (s->d_tri_blocks) cudaFree(s->d_tri_blocks);
-  }
+  int current = -1;
+  if (!s->res.empty()) cudaGetDevice(&current);
+  for (Residency* r : s->res) delete r;  // frees the device arrays and the staging contexts on the residency's device
+  if (current >= 0) cudaSetDevice(current);
   delete s;
 }
 
@@ -1128,6 +1527,50 @@ ecbError ecbIntersectDeviceStats(ecbScene* s, uint32_t instID, void* d_rayhit, u
 }
 ecbError ecbOccludedDevice(ecbScene* s, uint32_t instID, void* d_ray, uint64_t M, size_t byteStride, void* stream) {
   return run_device(s, true, instID, d_ray, M, byteStride, nullptr, stream);
+}
+
+ecbError ecbIntersectDeviceCompact(ecbScene* s, uint32_t instID, const void* d_rayhit, uint64_t M, size_t byteStride,
+                                   const ecbDeviceHits* out, void* stream) {
+  if (!out) return ECB_ERROR_INVALID_ARGUMENT;
+  return run_device(s, false, instID, const_cast<void*>(d_rayhit), M, byteStride, nullptr, stream, nullptr, false, out);
+}
+ecbError ecbOccludedDeviceCompact(ecbScene* s, uint32_t instID, const void* d_ray, uint64_t M, size_t byteStride, const ecbDeviceHits* out,
+                                  void* stream) {
+  if (!out) return ECB_ERROR_INVALID_ARGUMENT;
+  return run_device(s, true, instID, const_cast<void*>(d_ray), M, byteStride, nullptr, stream, nullptr, false, out);
+}
+
+ecbError ecbDeviceAlloc(void** d_ptr, size_t bytes) {
+  if (!d_ptr) return ECB_ERROR_INVALID_ARGUMENT;
+  CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return ECB_SUCCESS;
+}
+void ecbDeviceFree(void* d_ptr) {
+  if (d_ptr) cudaFree(d_ptr);
+}
+ecbError ecbIpcExport(void* d_ptr, void* handle64_out) {
+  if (!d_ptr || !handle64_out) return ECB_ERROR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle64_out, &h, sizeof(h));
+  return ECB_SUCCESS;
+}
+ecbError ecbIpcImport(const void* handle64, void** d_ptr_out) {
+  if (!handle64 || !d_ptr_out) return ECB_ERROR_INVALID_ARGUMENT;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return ECB_SUCCESS;
+}
+void ecbIpcClose(void* d_ptr) {
+  if (d_ptr) cudaIpcCloseMemHandle(d_ptr);
+}
+ecbError ecbPeerCopyAsync(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+  if ((!d_dst || !d_src) && bytes) return ECB_ERROR_INVALID_ARGUMENT;
+  if (!bytes) return ECB_SUCCESS;
+  CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return ECB_SUCCESS;
 }
 
 ecbError ecbSceneBlockNormals(const ecbScene* s, float* out, size_t cap) {
@@ -1217,7 +1660,7 @@ ecbError ecbSceneCopyBlocks(const ecbScene* s, void* out, size_t capacity) {
 
 ecbError ecbSceneSetBlocks(ecbScene* s, const void* blocks, size_t bytes) {
   if (!s || !blocks || s->instanced) return ECB_ERROR_INVALID_ARGUMENT;
-  if (s->device >= 0 || bytes != s->blocks.size()) {
+  if (s->resident() || bytes != s->blocks.size()) {
     g_last_error = "blocks can be replaced before the scene is resident, by the same number of bytes";
     return ECB_ERROR_INVALID_OPERATION;
   }

@@ -1,7 +1,8 @@
 // ecb_import.cpp -- converts the reference's committed compressed BVH4 into the device scene format.
 //
 // The importer reads the reference's memory directly through a hard-coded description of its layout (no reference
-// headers are included; the layout is probe-verified by tests/test_layout.py against the compiled reference):
+// headers are included; the layout is probe-verified against the compiled reference by
+// tests/test_oracle_cpu.py::test_layout_probe_matches_importer_constants):
 //   BVH4 NodeRef            kernels/bvh/bvh.h:107-140,150-400   low 4 bits = type, tyLeaf = 8, emptyNode = 8
 //   BVH4::AlignedNode       kernels/bvh/bvh.h:403-430,588-594   children[4] @0 (8 B each), 6 x vfloat4 bounds @32
 //   leaf                    encodeTypedLeaf(cbvh,1): one CompressedBVH per leaf (kernels/bvh/bvh_builder_subdiv.cpp:727-728)
@@ -12,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <new>
+#include <stdexcept>
 
 #include "ecb_scene.h"
 
@@ -30,19 +32,39 @@ T rd(const uint8_t* p) {
   return v;
 }
 
+// Range checks of a relocated image: with base != NULL and image_bytes != 0 every offset read from the image must stay
+// inside it (a truncated or corrupt image is rejected, never dereferenced).  Live memory (base == NULL) is the host
+// application's own committed BVH and is trusted like the reference trusts it.  `nodes_left` bounds the number of nodes an
+// import may visit: every distinct node occupies 128 bytes of the image, so a reference cycle (which would otherwise fan
+// out 4^depth) runs out of budget instead of memory.
+struct Range {
+  const uint8_t* base;
+  uint64_t bytes;  // 0 = unchecked
+  uint64_t nodes_left;
+  Range(const void* b, uint64_t n) : base(static_cast<const uint8_t*>(b)), bytes(b ? n : 0), nodes_left(b && n ? n / 128 + 1 : (1ull << 28)) {}
+  bool ok(uint64_t off, uint64_t len) const { return bytes == 0 || (off <= bytes && len <= bytes - off); }
+};
+
 struct Importer {
   const ecbImportDesc& d;
   ecbScene& s;
   const uint8_t* base;
+  Range range;
   uint32_t max_depth = 0;
   uint64_t ref_bytes = 0;
   std::string err;
 
-  Importer(const ecbImportDesc& desc, ecbScene& scene) : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+  Importer(const ecbImportDesc& desc, ecbScene& scene)
+      : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)), range(desc.base, desc.image_bytes) {}
 
   const uint8_t* at(uint64_t ref) const { return base + (ref & ~kAlignMask); }
+  uint32_t outside() {
+    err = "image offset out of range (truncated or corrupt image)";
+    return ECB_REF_EMPTY;
+  }
 
   uint32_t import_block(uint64_t ref) {
+    if (!range.ok(ref & ~kAlignMask, kB_Size)) return outside();
     const uint8_t* b = at(ref);
     const uint32_t elems = rd<uint32_t>(b + kB_Elems);
     const uint32_t width = rd<uint32_t>(b + kB_GridWidth);
@@ -64,6 +86,13 @@ struct Importer {
     h.extent = rd<float>(b + kB_Extent);
     h.geomID = rd<uint32_t>(b + kB_GeomID);
     h.primID = rd<uint32_t>(b + kB_PrimID);
+    const size_t n_cells = 3 * (size_t)elems + 1;
+    if (!range.ok(rd<uint64_t>(b + kB_Nodes), 4 * (uint64_t)elems) ||
+        (d.leaf_kind == ECB_LEAF_LEAF && !range.ok(rd<uint64_t>(b + kB_Leaves), 2 * (uint64_t)n_cells)) ||
+        (d.leaf_kind == ECB_LEAF_GRID && !range.ok(rd<uint64_t>(b + kB_Grid), 12 * (uint64_t)width * width))) {
+      s.blocks.resize(s.blocks.size() - s.block_stride);
+      return outside();
+    }
     const uint8_t* nodes = base + rd<uint64_t>(b + kB_Nodes);
     h.root_word = rd<uint32_t>(nodes);
     memcpy(out, &h, sizeof(h));
@@ -99,6 +128,11 @@ struct Importer {
     }
     if (depth > 512) {
       err = "top-level BVH deeper than 512";
+      return ECB_REF_EMPTY;
+    }
+    if (!range.ok(ref, kAN_Size)) return outside();
+    if (range.nodes_left-- == 0) {
+      err = "more nodes than the image can hold (reference cycle)";
       return ECB_REF_EMPTY;
     }
     const uint8_t* n = at(ref);
@@ -175,16 +209,19 @@ struct InstImporter {
   const ecbInstanceDesc& d;
   ecbScene& s;
   const uint8_t* base;
+  Range range;
   std::vector<uint32_t> geom_to_instance;
   uint32_t max_depth = 0;
   std::string err;
-  InstImporter(const ecbInstanceDesc& desc, ecbScene& scene) : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+  InstImporter(const ecbInstanceDesc& desc, ecbScene& scene)
+      : d(desc), s(scene), base(static_cast<const uint8_t*>(desc.base)), range(desc.base, desc.image_bytes) {}
 
   uint32_t import_ref(uint64_t ref, uint32_t depth) {
     if (!err.empty() || ref == kEmpty) return ECB_REF_EMPTY;
     if (ref & kTyLeaf) {
       const uint32_t num = (uint32_t)((ref & kAlignMask) - kTyLeaf);
       if (num > 7) { err = "instance leaf with more than 7 primitives"; return ECB_REF_EMPTY; }
+      if (!range.ok(ref & ~kAlignMask, 8 * (uint64_t)num)) { err = "image offset out of range (truncated or corrupt image)"; return ECB_REF_EMPTY; }
       const uint8_t* prims = base + (ref & ~kAlignMask);
       const uint32_t first = (uint32_t)s.items.size();
       uint32_t kept = 0;
@@ -203,6 +240,7 @@ struct InstImporter {
     }
     if ((ref & kAlignMask) != 0) { err = "instance BVH node is not an AlignedNode (use object_accel=bvh4.object)"; return ECB_REF_EMPTY; }
     if (depth > 512) { err = "instance BVH deeper than 512"; return ECB_REF_EMPTY; }
+    if (!range.ok(ref, kAN_Size) || range.nodes_left-- == 0) { err = "image offset out of range or reference cycle (truncated or corrupt image)"; return ECB_REF_EMPTY; }
     const uint8_t* n = base + (ref & ~kAlignMask);
     const uint32_t index = (uint32_t)s.top.size();
     s.top.emplace_back();
@@ -215,11 +253,28 @@ struct InstImporter {
 };
 }  // namespace
 
+static ecbError import_instances_impl(const ecbInstanceDesc* desc, ecbScene** out);
 ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
+  try {
+    return import_instances_impl(desc, out);
+  } catch (const std::exception&) {  // std::bad_alloc from a huge geomID / instance count: never across the C ABI
+    ecb_set_error("out of memory while importing the instancing scene");
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+}
+static ecbError import_instances_impl(const ecbInstanceDesc* desc, ecbScene** out) {
   if (!desc || !out || (desc->n_instances && (!desc->geomIDs || !desc->world2local || !desc->objects))) return ECB_ERROR_INVALID_ARGUMENT;
   ecbScene* s = new (std::nothrow) ecbScene;
   if (!s) return ECB_ERROR_OUT_OF_MEMORY;
   s->instanced = true;
+  struct Guard {  // an exception below must not leak the half-built scene or the references it took
+    ecbScene* s;
+    ~Guard() {
+      if (!s) return;
+      for (ecbScene* o : s->objects) o->refs--;
+      delete s;
+    }
+  } guard{s};
   InstImporter imp(*desc, *s);
   uint32_t max_geom = 0;
   for (uint32_t i = 0; i < desc->n_instances; i++) max_geom = desc->geomIDs[i] > max_geom ? desc->geomIDs[i] : max_geom;
@@ -228,8 +283,7 @@ ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
     ecbScene* obj = desc->objects[i];
     if (!obj || obj->instanced || obj->has_triangles()) {
       ecb_set_error("instance " + std::to_string(i) + " does not refer to an imported compressed-only (non-instanced, no triangle accel) scene");
-      delete s;
-      return ECB_ERROR_INVALID_ARGUMENT;
+      return ECB_ERROR_INVALID_ARGUMENT;  // the guard releases the scene
     }
     uint32_t oi = 0;
     for (; oi < s->objects.size(); oi++)
@@ -250,9 +304,7 @@ ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
   if (imp.err.empty() && 3 * imp.max_depth + 4 > ECB_MAX_TOP_STACK) imp.err = "instance BVH too deep for the traversal stack";
   if (!imp.err.empty()) {
     ecb_set_error(imp.err);
-    for (ecbScene* o : s->objects) o->refs--;
-    delete s;
-    return ECB_ERROR_UNSUPPORTED;
+    return ECB_ERROR_UNSUPPORTED;  // the guard releases the scene
   }
   ecbSceneInfo& in = s->info;
   memset(&in, 0, sizeof(in));
@@ -268,6 +320,7 @@ ecbError ecb_import_instances(const ecbInstanceDesc* desc, ecbScene** out) {
   in.leaf_kind = s->objects.empty() ? 0 : s->objects[0]->info.leaf_kind;
   memcpy(in.bounds, desc->bounds, sizeof(in.bounds));
   in.device = -1;
+  guard.s = nullptr;
   *out = s;
   return ECB_SUCCESS;
 }
@@ -278,9 +331,10 @@ constexpr size_t kTri_Size = 176;
 struct TriImporter {
   ecbScene& s;
   const uint8_t* base;
+  Range range;
   uint32_t max_depth = 0;
   std::string err;
-  TriImporter(const ecbTriangleDesc& desc, ecbScene& scene) : s(scene), base(static_cast<const uint8_t*>(desc.base)) {}
+  TriImporter(const ecbTriangleDesc& desc, ecbScene& scene) : s(scene), base(static_cast<const uint8_t*>(desc.base)), range(desc.base, desc.image_bytes) {}
 
   uint32_t import_ref(uint64_t ref, uint32_t depth) {
     if (!err.empty() || ref == kEmpty) return ECB_REF_EMPTY;
@@ -288,6 +342,7 @@ struct TriImporter {
       const uint32_t num = (uint32_t)((ref & kAlignMask) - kTyLeaf);
       const uint32_t first = (uint32_t)s.tri_blocks.size();
       if (first >= (1u << 27)) { err = "too many triangle blocks"; return ECB_REF_EMPTY; }
+      if (!range.ok(ref & ~kAlignMask, kTri_Size * (uint64_t)num)) { err = "image offset out of range (truncated or corrupt image)"; return ECB_REF_EMPTY; }
       const uint8_t* blocks = base + (ref & ~kAlignMask);
       for (uint32_t i = 0; i < num; i++) {
         EcbTriBlock b;
@@ -299,6 +354,7 @@ struct TriImporter {
     }
     if ((ref & kAlignMask) != 0) { err = "triangle BVH node is not an AlignedNode (use tri_accel=bvh4.triangle4v)"; return ECB_REF_EMPTY; }
     if (depth > 512) { err = "triangle BVH deeper than 512"; return ECB_REF_EMPTY; }
+    if (!range.ok(ref, kAN_Size) || range.nodes_left-- == 0) { err = "image offset out of range or reference cycle (truncated or corrupt image)"; return ECB_REF_EMPTY; }
     const uint8_t* n = base + (ref & ~kAlignMask);
     const uint32_t index = (uint32_t)s.tri_top.size();
     s.tri_top.emplace_back();
@@ -313,7 +369,7 @@ struct TriImporter {
 
 ecbError ecb_import_triangles(const ecbTriangleDesc* desc, ecbScene* s) {
   if (!desc || !s || !desc->root) return ECB_ERROR_INVALID_ARGUMENT;
-  if (s->instanced || s->device >= 0 || s->has_triangles() || s->refs.load() > 1) {
+  if (s->instanced || s->resident() || s->has_triangles() || s->refs.load() > 1) {
     ecb_set_error("triangles attach to a freshly imported, non-instancing scene that is not yet resident or instanced");
     return ECB_ERROR_INVALID_OPERATION;
   }

@@ -18,21 +18,18 @@ struct ecbScene {
   uint32_t block_stride = 0, leaf_offset = 0, elems = 0, grid_width = 0;
   float rcp_edges = 0.f;
 
-  // device residency
-  std::mutex mutex;
-  int device = -1;
-  void* d_top = nullptr;
-  void* d_blocks = nullptr;
-  EcbDeviceScene dev{};
+  // device residency: one Residency per CUDA device the scene has been uploaded to (ecbSceneUpload / ecbSceneUploadMulti);
+  // res[0] is the primary one (lazy uploads and single-device calls use it).  `mutex` guards the vector.
+  mutable std::mutex mutex;
+  std::vector<struct Residency*> res;
+  std::atomic<struct Residency*> primary{nullptr};
+  bool resident() const { return primary.load(std::memory_order_acquire) != nullptr; }
 
   // mixed scenes: the triangle accel that AccelN visits before the compressed accel
   std::vector<EcbTopNode> tri_top;
   std::vector<EcbTriBlock> tri_blocks;
   uint32_t tri_root = ECB_REF_EMPTY;
   uint32_t tri_depth = 0;
-  void* d_tri_top = nullptr;
-  void* d_tri_blocks = nullptr;
-  EcbDeviceTriScene tri_dev{};
   bool has_triangles() const { return tri_root != ECB_REF_EMPTY; }
 
   // instanced scenes: instance-level BVH4 (in `top`), Object items, instance records, retained object scenes
@@ -40,18 +37,8 @@ struct ecbScene {
   std::vector<uint32_t> items;
   std::vector<EcbInstance> instances;
   std::vector<ecbScene*> objects;
-  void* d_items = nullptr;
-  void* d_instances = nullptr;
-  void* d_objects = nullptr;
-  EcbDeviceInstScene inst_dev{};
   std::atomic<int> refs{1};
 
-  // ring of device words used as dynamic ray-fetch cursors, one per launch in flight
-  unsigned long long* d_queues = nullptr;
-  std::atomic<uint32_t> next_queue{0};
-
-  // staging for the host-buffer entry points (lazily created, per scene)
-  struct Staging* staging = nullptr;
 };
 
 // byte layout of one block in the device format for compression level C and leaf kind (ecb_format.h)

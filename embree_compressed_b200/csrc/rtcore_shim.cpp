@@ -99,6 +99,7 @@ struct HostApi {
   HOST_FN(void, rtcRetainBVH, (RTCBVH))
   HOST_FN(void, rtcReleaseBVH, (RTCBVH))
 #undef HOST_FN
+  const HostApi* registry = nullptr;  // the never-freed instance this copy was made from
 };
 
 struct ShimDevice {
@@ -110,6 +111,7 @@ struct ShimDevice {
   RTCErrorFunction callback = nullptr;
   void* callback_ptr = nullptr;
   int verbose = 0;
+  int gpus = 1;  // device config key gpus=N
 
   void raise(RTCError code, const std::string& msg) {
     RTCErrorFunction cb;
@@ -137,13 +139,34 @@ struct ShimScene {
 inline ShimDevice* D(RTCDevice d) { return reinterpret_cast<ShimDevice*>(d); }
 inline ShimScene* S(RTCScene s) { return reinterpret_cast<ShimScene*>(s); }
 
-// the device of a geometry is not recoverable from the host handle, so pass-through geometry calls use the last
-// device that created a geometry on this thread's process (one host library per process in practice)
-std::atomic<ShimDevice*> g_any_device{nullptr};
+// Geometry and buffer handles are the host library's own handles and may outlive the device object that created them
+// (the reference's Geometry ref-counts its device, kernels/common/geometry.cpp:29).  Pass-through calls therefore never
+// go through a ShimDevice: every host library is resolved once into a HostApi that is never unloaded or freed, a geometry
+// remembers the library that created it, and anything else falls back to the first library this process loaded.
+std::mutex g_host_mutex;
+std::map<std::string, HostApi*> g_host_libs;         // path -> resolved entry points (kept for the life of the process)
+std::map<RTCGeometry, const HostApi*> g_geom_host;   // geometry -> the library that created it
+std::atomic<const HostApi*> g_first_host{nullptr};
+std::atomic<ShimDevice*> g_any_device{nullptr};      // only used to REPORT errors of calls that carry no device
+
+const HostApi* host_of(RTCGeometry g) {
+  if (g) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    auto it = g_geom_host.find(g);
+    if (it != g_geom_host.end()) return it->second;
+  }
+  const HostApi* h = g_first_host.load();
+  return h;
+}
 // host scene handle -> wrapper, so that instances can find the device scene of the scene they refer to
 std::mutex g_scene_map_mutex;
 std::map<RTCScene, ShimScene*> g_scene_map;
 thread_local RTCError g_thread_error = RTC_ERROR_NONE;  // errors without a device (rtcore.cpp:79-98)
+const HostApi* host_or_error(RTCGeometry g) {
+  const HostApi* h = host_of(g);
+  if (!h) g_thread_error = RTC_ERROR_INVALID_OPERATION;  // no host library loaded yet: nothing to forward to
+  return h;
+}
 
 RTCError map_error(ecbError e) {
   switch (e) {
@@ -156,7 +179,25 @@ RTCError map_error(ecbError e) {
   }
 }
 
-bool load_host(HostApi& h, const std::string& path, std::string& err) {
+bool resolve_host(HostApi& h, const std::string& path, std::string& err);
+bool load_host(HostApi& out, const std::string& path, std::string& err) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  auto it = g_host_libs.find(path);
+  if (it == g_host_libs.end()) {
+    HostApi* h = new HostApi();
+    if (!resolve_host(*h, path, err)) {
+      delete h;
+      return false;
+    }
+    it = g_host_libs.emplace(path, h).first;
+    const HostApi* expect = nullptr;
+    g_first_host.compare_exchange_strong(expect, h);
+  }
+  out = *it->second;  // a copy of the entry points; the library itself stays loaded for the life of the process
+  out.registry = it->second;
+  return true;
+}
+bool resolve_host(HostApi& h, const std::string& path, std::string& err) {
   h.lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
   if (!h.lib) {
     err = std::string("cannot load host embree '") + path + "': " + dlerror();
@@ -196,7 +237,7 @@ bool load_host(HostApi& h, const std::string& path, std::string& err) {
 }
 
 // splits "key=value,key=value" ; returns the config for the host with our keys removed
-std::string parse_config(const char* cfg, std::string& host_path, int& verbose) {
+std::string parse_config(const char* cfg, std::string& host_path, int& verbose, int& gpus) {
   std::string rest;
   std::string s = cfg ? cfg : "";
   size_t i = 0;
@@ -207,11 +248,21 @@ std::string parse_config(const char* cfg, std::string& host_path, int& verbose) 
     i = j + 1;
     if (item.empty()) continue;
     if (item.compare(0, 12, "host_embree=") == 0) { host_path = item.substr(12); continue; }
+    // gpus=N: committed scenes are replicated on CUDA devices 0..N-1 and long stream calls fan out over them
+    if (item.compare(0, 5, "gpus=") == 0) { gpus = atoi(item.c_str() + 5); continue; }
     if (item.compare(0, 8, "verbose=") == 0) verbose = atoi(item.c_str() + 8);
     if (!rest.empty()) rest += ",";
     rest += item;
   }
   return rest;
+}
+
+// makes a freshly imported scene resident: on the current device, or on devices 0..gpus-1 (device config gpus=N)
+ecbError upload_scene(ecbScene* g, int gpus) {
+  if (gpus <= 1) return ecbSceneUpload(g, -1);
+  std::vector<int> devs;
+  for (int i = 0; i < gpus; i++) devs.push_back(i);
+  return ecbSceneUploadMulti(g, devs.data(), (uint32_t)devs.size());
 }
 
 uint32_t ctx_inst(const RTCIntersectContext* c) { return c ? c->instID[0] : RTC_INVALID_GEOMETRY_ID; }
@@ -321,7 +372,7 @@ extern "C" {
 RTC_API RTCDevice rtcNewDevice(const char* config) {
   ShimDevice* d = new ShimDevice;
   std::string host_path = getenv("ECB200_HOST_EMBREE") ? getenv("ECB200_HOST_EMBREE") : "";
-  const std::string host_cfg = parse_config(config, host_path, d->verbose);
+  const std::string host_cfg = parse_config(config, host_path, d->verbose, d->gpus);
   std::string err;
   if (host_path.empty()) err = "no host embree given (device config host_embree=<libembree3.so> or $ECB200_HOST_EMBREE)";
   if (!err.empty() || !load_host(d->host, host_path, err)) {
@@ -368,38 +419,43 @@ RTC_API void rtcSetDeviceErrorFunction(RTCDevice device, RTCErrorFunction error,
 }
 
 // ---- geometry: forwarded to the host builder --------------------------------------------------------------------------
-#define HOST() (g_any_device.load()->host)
 RTC_API RTCGeometry rtcNewGeometry(RTCDevice device, RTCGeometryType type) {
   if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return nullptr; }
-  return D(device)->host.rtcNewGeometry(D(device)->hdev, type);
+  RTCGeometry g = D(device)->host.rtcNewGeometry(D(device)->hdev, type);
+  if (g) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    g_geom_host[g] = D(device)->host.registry;  // a recycled handle value simply overwrites its stale entry
+  }
+  return g;
 }
-RTC_API void rtcRetainGeometry(RTCGeometry g) { HOST().rtcRetainGeometry(g); }
-RTC_API void rtcReleaseGeometry(RTCGeometry g) { HOST().rtcReleaseGeometry(g); }
-RTC_API void rtcCommitGeometry(RTCGeometry g) { HOST().rtcCommitGeometry(g); }
-RTC_API void rtcEnableGeometry(RTCGeometry g) { HOST().rtcEnableGeometry(g); }
-RTC_API void rtcDisableGeometry(RTCGeometry g) { HOST().rtcDisableGeometry(g); }
-RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryTimeStepCount(g, n); }
-RTC_API void rtcSetGeometryVertexAttributeCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryVertexAttributeCount(g, n); }
-RTC_API void rtcSetGeometryBuildQuality(RTCGeometry g, RTCBuildQuality q) { HOST().rtcSetGeometryBuildQuality(g, q); }
+RTC_API void rtcRetainGeometry(RTCGeometry g) { if (const HostApi* h = host_or_error(g)) h->rtcRetainGeometry(g); }
+RTC_API void rtcReleaseGeometry(RTCGeometry g) { if (const HostApi* h = host_or_error(g)) h->rtcReleaseGeometry(g); }
+RTC_API void rtcCommitGeometry(RTCGeometry g) { if (const HostApi* h = host_or_error(g)) h->rtcCommitGeometry(g); }
+RTC_API void rtcEnableGeometry(RTCGeometry g) { if (const HostApi* h = host_or_error(g)) h->rtcEnableGeometry(g); }
+RTC_API void rtcDisableGeometry(RTCGeometry g) { if (const HostApi* h = host_or_error(g)) h->rtcDisableGeometry(g); }
+RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry g, unsigned n) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryTimeStepCount(g, n); }
+RTC_API void rtcSetGeometryVertexAttributeCount(RTCGeometry g, unsigned n) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryVertexAttributeCount(g, n); }
+RTC_API void rtcSetGeometryBuildQuality(RTCGeometry g, RTCBuildQuality q) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryBuildQuality(g, q); }
 RTC_API void rtcSetSharedGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot, RTCFormat f, const void* p, size_t off, size_t stride,
                                         size_t n) {
-  HOST().rtcSetSharedGeometryBuffer(g, t, slot, f, p, off, stride, n);
+  if (const HostApi* h = host_or_error(g)) h->rtcSetSharedGeometryBuffer(g, t, slot, f, p, off, stride, n);
 }
 RTC_API void* rtcSetNewGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot, RTCFormat f, size_t stride, size_t n) {
-  return HOST().rtcSetNewGeometryBuffer(g, t, slot, f, stride, n);
+  const HostApi* h = host_or_error(g);
+  return h ? h->rtcSetNewGeometryBuffer(g, t, slot, f, stride, n) : nullptr;
 }
-RTC_API void* rtcGetGeometryBufferData(RTCGeometry g, RTCBufferType t, unsigned slot) { return HOST().rtcGetGeometryBufferData(g, t, slot); }
-RTC_API void rtcUpdateGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot) { HOST().rtcUpdateGeometryBuffer(g, t, slot); }
-RTC_API void rtcSetGeometryUserData(RTCGeometry g, void* p) { HOST().rtcSetGeometryUserData(g, p); }
-RTC_API void* rtcGetGeometryUserData(RTCGeometry g) { return HOST().rtcGetGeometryUserData(g); }
-RTC_API void rtcSetGeometryTessellationRate(RTCGeometry g, float r) { HOST().rtcSetGeometryTessellationRate(g, r); }
-RTC_API void rtcSetGeometryTopologyCount(RTCGeometry g, unsigned n) { HOST().rtcSetGeometryTopologyCount(g, n); }
-RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry g, unsigned t, RTCSubdivisionMode m) { HOST().rtcSetGeometrySubdivisionMode(g, t, m); }
-RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry g, unsigned a, unsigned t) { HOST().rtcSetGeometryVertexAttributeTopology(g, a, t); }
-RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry g, RTCDisplacementFunctionN f) { HOST().rtcSetGeometryDisplacementFunction(g, f); }
-RTC_API void rtcInterpolate(const RTCInterpolateArguments* args) { HOST().rtcInterpolate(args); }
-RTC_API void rtcSetGeometryInstancedScene(RTCGeometry g, RTCScene scene) { HOST().rtcSetGeometryInstancedScene(g, scene ? reinterpret_cast<ShimScene*>(scene)->hscene : nullptr); }
-RTC_API void rtcSetGeometryTransform(RTCGeometry g, unsigned t, RTCFormat f, const void* xfm) { HOST().rtcSetGeometryTransform(g, t, f, xfm); }
+RTC_API void* rtcGetGeometryBufferData(RTCGeometry g, RTCBufferType t, unsigned slot) { const HostApi* h = host_or_error(g); return h ? h->rtcGetGeometryBufferData(g, t, slot) : nullptr; }
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry g, RTCBufferType t, unsigned slot) { if (const HostApi* h = host_or_error(g)) h->rtcUpdateGeometryBuffer(g, t, slot); }
+RTC_API void rtcSetGeometryUserData(RTCGeometry g, void* p) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryUserData(g, p); }
+RTC_API void* rtcGetGeometryUserData(RTCGeometry g) { const HostApi* h = host_or_error(g); return h ? h->rtcGetGeometryUserData(g) : nullptr; }
+RTC_API void rtcSetGeometryTessellationRate(RTCGeometry g, float r) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryTessellationRate(g, r); }
+RTC_API void rtcSetGeometryTopologyCount(RTCGeometry g, unsigned n) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryTopologyCount(g, n); }
+RTC_API void rtcSetGeometrySubdivisionMode(RTCGeometry g, unsigned t, RTCSubdivisionMode m) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometrySubdivisionMode(g, t, m); }
+RTC_API void rtcSetGeometryVertexAttributeTopology(RTCGeometry g, unsigned a, unsigned t) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryVertexAttributeTopology(g, a, t); }
+RTC_API void rtcSetGeometryDisplacementFunction(RTCGeometry g, RTCDisplacementFunctionN f) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryDisplacementFunction(g, f); }
+RTC_API void rtcInterpolate(const RTCInterpolateArguments* args) { if (const HostApi* h = host_or_error(args ? args->geometry : nullptr)) h->rtcInterpolate(args); }
+RTC_API void rtcSetGeometryInstancedScene(RTCGeometry g, RTCScene scene) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryInstancedScene(g, scene ? reinterpret_cast<ShimScene*>(scene)->hscene : nullptr); }
+RTC_API void rtcSetGeometryTransform(RTCGeometry g, unsigned t, RTCFormat f, const void* xfm) { if (const HostApi* h = host_or_error(g)) h->rtcSetGeometryTransform(g, t, f, xfm); }
 
 
 // ---- the rest of the embree3 surface: plumbing that never touches a ray, forwarded to the host -------------------------
@@ -411,13 +467,14 @@ static ShimDevice* any_device(const char* what) {
   return d;
 }
 #define FORWARD(name, what, fail, ...)                                                                    \
-  ShimDevice* d__ = any_device(what);                                                                     \
-  if (!d__) return fail;                                                                                  \
-  if (!d__->host.name) {                                                                                  \
-    d__->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": the host embree does not export it");  \
+  const HostApi* h__ = host_or_error(nullptr);                                                            \
+  if (!h__) return fail;                                                                                  \
+  if (!h__->name) {                                                                                       \
+    if (ShimDevice* d__ = any_device(what))                                                               \
+      d__->raise(RTC_ERROR_INVALID_OPERATION, std::string(what) + ": the host embree does not export it"); \
     return fail;                                                                                          \
   }                                                                                                       \
-  return d__->host.name(__VA_ARGS__)
+  return h__->name(__VA_ARGS__)
 
 RTC_API ssize_t rtcGetDeviceProperty(RTCDevice device, RTCDeviceProperty prop) {
   if (!device) { g_thread_error = RTC_ERROR_INVALID_ARGUMENT; return 0; }
@@ -583,7 +640,7 @@ RTC_API void rtcCommitScene(RTCScene scene) {
       memcpy(d.bounds, ii.bounds, sizeof(d.bounds));
       ecbScene* g = nullptr;
       ecbError e = ecbSceneImportInstances(&d, &g);
-      if (e == ECB_SUCCESS) e = ecbSceneUpload(g, -1);
+      if (e == ECB_SUCCESS) e = upload_scene(g, s->dev->gpus);
       if (e != ECB_SUCCESS) {
         if (g) ecbSceneRelease(g);
         s->dev->raise(map_error(e), std::string("rtcCommitScene (instances): ") + ecbErrorString(e) + " " + ecbLastErrorMessage());
@@ -618,11 +675,11 @@ RTC_API void rtcCommitScene(RTCScene scene) {
   ecbError e = ecbSceneImportBVH4(&d, &g);
   if (e == ECB_SUCCESS && tri_root) {
     ecbTriangleDesc t;
-    t.base = nullptr;
+    memset(&t, 0, sizeof(t));
     t.root = tri_root;
     e = ecbSceneAttachTriangles4v(g, &t);
   }
-  if (e == ECB_SUCCESS) e = ecbSceneUpload(g, -1);
+  if (e == ECB_SUCCESS) e = upload_scene(g, s->dev->gpus);
   if (e != ECB_SUCCESS) {
     if (g) ecbSceneRelease(g);
     s->dev->raise(map_error(e), std::string("rtcCommitScene: ") + ecbErrorString(e) + " " + ecbLastErrorMessage());

@@ -65,6 +65,8 @@ typedef struct ecbImportDesc {
   uint32_t subdiv_level;   /* S of rtcSetSceneLevels (informational: bytes per micro-triangle) */
   uint32_t comp_level;     /* C of rtcSetSceneLevels; verified against every block's `elems` */
   float bounds[6];         /* scene bounds (rtcGetSceneBounds), lower xyz then upper xyz; informational */
+  uint64_t image_bytes;    /* size of the relocated image when base != NULL: every offset read from it is range-checked
+                              (a truncated or corrupt image is rejected, never dereferenced); 0 for live memory */
 } ecbImportDesc;
 
 typedef struct ecbSceneInfo {
@@ -90,6 +92,7 @@ typedef struct ecbInstanceDesc {
   const float* world2local;  /* 12 floats per instance: l.vx, l.vy, l.vz, p of Instance::world2local0 */
   ecbScene* const* objects;  /* imported scene each instance refers to (entries may repeat; retained by the new scene) */
   float bounds[6];
+  uint64_t image_bytes;      /* as in ecbImportDesc */
 } ecbInstanceDesc;
 
 /* Triangle meshes in the same scene (SURVEY 8f-1, config 1's ground plane): what the host hands over for the accel
@@ -99,6 +102,7 @@ typedef struct ecbTriangleDesc {
   const void* base;  /* as in ecbImportDesc */
   uint64_t root;     /* BVH4::root of the accel created by BVH4Factory::BVH4Triangle4v (kernels/bvh/bvh4_factory.cpp:1368-1394):
                         AlignedNodes, leaves = arrays of TriangleMv<4> blocks (kernels/geometry/trianglev.h, 176 bytes) */
+  uint64_t image_bytes; /* as in ecbImportDesc */
 } ecbTriangleDesc;
 
 /* ---- scene ---------------------------------------------------------------------------------------- */
@@ -118,8 +122,17 @@ ECB_API ecbError ecbSceneImportImageFile(const char* path, ecbScene** scene_out)
 /* Native serialisation of the converted scene (the reference has none). */
 ECB_API ecbError ecbSceneSave(const ecbScene* scene, const char* path);
 ECB_API ecbError ecbSceneLoad(const char* path, ecbScene** scene_out);
-/* Makes the scene resident on CUDA device `device` (cudaMalloc + copy).  Traversal calls do this lazily on device 0. */
+/* Makes the scene resident on CUDA device `device` (cudaMalloc + copy; -1 = the calling thread's current device).
+ * Traversal calls do this lazily.  A scene may be resident on several devices: every call adds one copy. */
 ECB_API ecbError ecbSceneUpload(ecbScene* scene, int device);
+/* Multi-GPU in ONE process (the reference's analogue is the tile-parallel parallel_for over screen tiles,
+ * tutorials/viewer/viewer_device.cpp:548-554): replicates the scene on every listed device.  From then on a host-buffer
+ * call (ecbIntersect1M / ecbOccluded1M / ...) of at least 256 Ki rays is cut into one contiguous ray range per device;
+ * every range runs its own upload -> traversal -> download pipeline over its own PCIe link and the results land in the
+ * caller's array -- no gather step.  Device-buffer calls run on the device that owns the ray buffer. */
+ECB_API ecbError ecbSceneUploadMulti(ecbScene* scene, const int* devices, uint32_t n_devices);
+/* Devices the scene is resident on (first = primary); returns their number. */
+ECB_API uint32_t ecbSceneResidentDevices(const ecbScene* scene, int* devices_out, uint32_t capacity);
 ECB_API ecbError ecbSceneGetInfo(const ecbScene* scene, ecbSceneInfo* info);
 ECB_API void ecbSceneRelease(ecbScene* scene);
 
@@ -187,6 +200,31 @@ ECB_API ecbError ecbIntersectDeviceEx(ecbScene* scene, uint32_t instID, void* d_
  * algorithmic-bytes figure is built from.  d_counters is a device pointer the caller zeroes. */
 ECB_API ecbError ecbIntersectDeviceStats(ecbScene* scene, uint32_t instID, void* d_rayhit, uint64_t M, size_t byteStride,
                                          uint64_t* d_counters, void* stream);
+/* Compact result records of a device-buffer call (device pointers on the scene's device, one entry per ray): what a
+ * multi-GPU frame gather moves instead of the 80-byte RTCRayHit records.  The ray records are only read. */
+typedef struct ecbDeviceHits {
+  uint32_t* geomID; /* geomID of the hit, 0xFFFFFFFF for a miss / inactive ray; any-hit queries: 0 = occluded */
+  float* hit;       /* 4 floats per ray: tfar, u, v, primID (bit pattern); written for hits only */
+  uint32_t* instID; /* instancing scenes: instID[0] of the hit (geomID of the instance); may be NULL otherwise */
+  float* Ng;        /* reserved for mixed scenes (3 floats per ray); may be NULL otherwise */
+} ecbDeviceHits;
+ECB_API ecbError ecbIntersectDeviceCompact(ecbScene* scene, uint32_t instID, const void* d_rayhit, uint64_t M, size_t byteStride,
+                                           const ecbDeviceHits* out, void* stream);
+ECB_API ecbError ecbOccludedDeviceCompact(ecbScene* scene, uint32_t instID, const void* d_ray, uint64_t M, size_t byteStride,
+                                          const ecbDeviceHits* out, void* stream);
+
+/* ---- multi-GPU, one process per GPU: the hit-record gather over NVLink -------------------------------
+ * The gathering rank allocates the frame's result arrays with ecbDeviceAlloc and publishes their 64-byte handles
+ * (ecbIpcExport, any transport: torch.distributed broadcast, a file, ...); every other rank maps them once (ecbIpcImport:
+ * CUDA IPC, peer access over NVLink/NVSwitch) and, after its traversal launches, copies its shard's compact records
+ * straight into place with ecbPeerCopyAsync on its own stream -- no collective, no staging on the gathering GPU. */
+ECB_API ecbError ecbDeviceAlloc(void** d_ptr, size_t bytes);
+ECB_API void ecbDeviceFree(void* d_ptr);
+ECB_API ecbError ecbIpcExport(void* d_ptr, void* handle64_out);
+ECB_API ecbError ecbIpcImport(const void* handle64, void** d_ptr_out);
+ECB_API void ecbIpcClose(void* d_ptr);
+ECB_API ecbError ecbPeerCopyAsync(void* d_dst, const void* d_src, size_t bytes, void* stream);
+
 /* World-space unit normal of a block's local frame (third row of CompressedBVH::space), 3 floats per block, host copy. */
 ECB_API ecbError ecbSceneBlockNormals(const ecbScene* scene, float* normals_out, size_t capacity_floats);
 

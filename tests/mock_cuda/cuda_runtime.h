@@ -24,9 +24,11 @@ enum cudaError_t {
   cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100,
   cudaErrorInvalidDevice = 101, cudaErrorNoKernelImageForDevice = 209, cudaErrorUnknown = 999
 };
-enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
-struct cudaPointerAttributes { cudaMemoryType type; };
+struct cudaPointerAttributes { cudaMemoryType type; int device; };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventBlockingSync = 1 };
 struct float4 { float x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
@@ -110,9 +112,22 @@ inline MockPinned& mock_pinned() {
 
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "mock CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+// MOCK_CUDA_DEVICES (default 1) fake devices: "current device" is per thread, like the real runtime's
+inline int mock_device_count() {
+  static const int n = [] { const char* e = getenv("MOCK_CUDA_DEVICES"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+  return n;
+}
+inline int& mock_current_device() { static thread_local int d = 0; return d; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = mock_device_count(); return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = mock_current_device(); return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int d) {
+  if (d < 0 || d >= mock_device_count()) return cudaErrorInvalidDevice;
+  mock_current_device() = d;
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) {
   *p = malloc(n ? n : 1);
   if (!*p) return cudaErrorMemoryAllocation;
@@ -140,6 +155,7 @@ inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void
   std::lock_guard<std::mutex> l(mock_pinned().m);
   auto it = mock_pinned().ranges.upper_bound(v);
   a->type = cudaMemoryTypeUnregistered;
+  a->device = 0;
   if (it != mock_pinned().ranges.begin()) {
     --it;
     if (v < it->first + it->second) a->type = cudaMemoryTypeHost;
