@@ -107,6 +107,7 @@ SYMBOLS = {
     "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbHostFree": (None, [_vp]),
     "ecbHostPathName": (C.c_char_p, [C.c_int]),
+    "ecbProbeReadBandwidth": (C.c_int, [_sz, C.c_int, C.POINTER(C.c_double)]),
     "ecbLaunchCount": (_u64, []),
     "ecbErrorString": (C.c_char_p, [C.c_int]),
     "ecbLastErrorMessage": (C.c_char_p, []),
@@ -142,6 +143,13 @@ def launch_count():
 def host_path_for(pinned):
     """Name of the transfer strategy the host-buffer entry points pick for this kind of caller memory."""
     return _lib().ecbHostPathName(1 if pinned else 0).decode()
+
+
+def probe_read_bandwidth(working_set_bytes, passes):
+    """GB/s of 128-bit L1-bypassing reads over a device buffer (32 MB x 64 passes: L2; 4 GB x 1: HBM)."""
+    g = C.c_double()
+    _check(_lib().ecbProbeReadBandwidth(working_set_bytes, passes, C.byref(g)), "ecbProbeReadBandwidth")
+    return g.value
 
 
 def host_alloc(n_bytes):

@@ -455,7 +455,6 @@ HostPath host_path() {
   }();
   return path;
 }
-bool use_compact_results() { return host_path() != kPathCopy; }
 
 // copies the fields this path reads of rays [b, e) of a chunk into 32-byte packed records: {org.xyz, tnear}, {dir.xyz, tfar}
 // (RTCRay layout, rtcore_ray.h:26-44: org 0, tnear 12, dir 16, time 28, tfar 32; time/mask/id/flags are not read by the
@@ -1570,6 +1569,19 @@ ecbError ecbPeerCopyAsync(void* d_dst, const void* d_src, size_t bytes, void* st
   if ((!d_dst || !d_src) && bytes) return ECB_ERROR_INVALID_ARGUMENT;
   if (!bytes) return ECB_SUCCESS;
   CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return ECB_SUCCESS;
+}
+
+ecbError ecbProbeReadBandwidth(size_t working_set_bytes, int passes, double* gbs_out) {
+  if (!gbs_out || working_set_bytes < (1u << 20) || passes < 1) return ECB_ERROR_INVALID_ARGUMENT;
+  int count = 0, device = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    g_last_error = "no CUDA device";
+    return ECB_ERROR_NO_DEVICE;
+  }
+  CU(cudaGetDevice(&device));
+  CU(ecb_probe_read_bandwidth(working_set_bytes, passes, device, gbs_out));
+  g_launches.fetch_add(6);
   return ECB_SUCCESS;
 }
 

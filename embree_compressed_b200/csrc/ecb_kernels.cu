@@ -35,6 +35,12 @@ __device__ __forceinline__ float sse_min(float a, float b) { return fminf(a, b);
 __device__ __forceinline__ float sse_max_exact(float a, float b) { return a > b ? a : b; }
 __device__ __forceinline__ float zero_fix(float a) { return fabsf(a) < 1E-18f ? 1E-18f : a; }
 
+// Ray records are read with ordinary (coherent) loads, never ld.global.nc: the in-place entry points write hits into the
+// very records they read (L.in == L.out), and the non-coherent path requires data that nothing modifies while the kernel runs.
+// ld.global.cg: coherent at L2, 128 bits wide, and the records are read exactly once, so bypassing L1 costs nothing.
+__device__ __forceinline__ float4 ld_ray4(const uint8_t* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_ray1(const uint8_t* p) { return __ldcg(reinterpret_cast<const float*>(p)); }
+
 __device__ __forceinline__ uint32_t compact1by1(uint32_t x) {
   x &= 0x55555555u;
   x = (x ^ (x >> 1)) & 0x33333333u;
@@ -656,9 +662,9 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         if (mine) {
           index = chunk_next + rank;
           const uint8_t* rp = L.in + index * L.in_stride;
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));       // org.xyz, tnear
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));  // dir.xyz, time
-          const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));  // 32, or 28 in packed records
+          const float4 r0 = ld_ray4(rp);       // org.xyz, tnear
+          const float4 r1 = ld_ray4(rp + 16);  // dir.xyz, time
+          const float tfar_in = ld_ray1(rp + L.tfar_offset);  // 32, or 28 in packed records
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
           if (L.hit_geom && !L.keep_results) L.hit_geom[index] = 0xFFFFFFFFu;
           if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
@@ -792,22 +798,21 @@ __device__ __forceinline__ unsigned fast_node(const EcbTopNode* nodes, uint32_t 
 }
 
 // closest hit inside one object scene (what rtcIntersect1 on the instanced scene does)
-template <int LEAF>
+template <int LEAF, bool STATS>
 __device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
-                                          float ray_tnear, Hit& hit) {
+                                          float ray_tnear, Hit& hit, Work& work) {
   uint32_t stack_ref[ECB_MAX_TOP_STACK];
   uint32_t stack_dist[ECB_MAX_TOP_STACK];
   if (sc.root == ECB_REF_EMPTY) return;
-  Work work = {0u, 0u, 0u, 0u};
   TravRay tr;
   travray_init(tr, org, dir, sse_max_exact(ray_tnear, 0.0f), sse_max_exact(hit.tfar, 0.0f));
   stack_ref[0] = sc.root;
   stack_dist[0] = 0xff800000u;
   int sp = 1;
   for (;;) {
-    const uint32_t leaf = next_block<false>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+    const uint32_t leaf = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
     if (leaf == ECB_REF_EMPTY) break;
-    block_intersect<LEAF, false>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+    block_intersect<LEAF, STATS>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
     tr.tfar = hit.tfar;
   }
 }
@@ -827,16 +832,18 @@ __device__ __forceinline__ void instance_ray(const EcbInstance* in, const float 
   object = e.y;
 }
 
-template <bool ANYHIT>
+template <bool ANYHIT, bool STATS>
 __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceInstScene is, EcbLaunch L) {
   __shared__ float lut[32];
   init_lut(lut);
   __syncthreads();
+  Work work = {0u, 0u, 0u, 0u};
+  uint32_t n_visits = 0, n_hits = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
+    const float4 r0 = ld_ray4(rp);
+    const float4 r1 = ld_ray4(rp + 16);
+    const float tfar_in = ld_ray1(rp + L.tfar_offset);
     if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: miss / inactive / not occluded
     if (r0.w > tfar_in) continue;
     if (ANYHIT && tfar_in < 0.0f) continue;
@@ -918,10 +925,11 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
         } else {
           const uint32_t before = hit.block;
           hit.block = 0xFFFFFFFFu;
+          if (STATS) n_visits++;
           switch (sc.leaf_kind) {
-            case 0: trace_object<0>(sc, lut, lo, ld, r0.w, hit); break;
-            case 1: trace_object<1>(sc, lut, lo, ld, r0.w, hit); break;
-            default: trace_object<2>(sc, lut, lo, ld, r0.w, hit); break;
+            case 0: trace_object<0, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+            case 1: trace_object<1, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+            default: trace_object<2, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
           }
           if (hit.block != 0xFFFFFFFFu) hit_inst = geomID;
           else hit.block = before;
@@ -929,6 +937,7 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
       }
       tr.tfar = hit.tfar;
     }
+    if (STATS && hit_inst != 0xFFFFFFFFu) n_hits++;
     if (L.hit_geom) {  // compact result: the host layer scatters it into the caller's record
       if (ANYHIT) {
         if (occluded) L.hit_geom[i] = 0u;
@@ -948,6 +957,14 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
       *reinterpret_cast<float4*>(op + 64) =
           make_float4(hit.v, __uint_as_float(hit.primID), __uint_as_float(hit.geomID), __uint_as_float(hit_inst));
     }
+  }
+  if (STATS) {  // counters[0] = object-scene traversals (instance visits), then the plain kernel's counters
+    atomicAdd(L.counters + 0, (unsigned long long)n_visits);
+    atomicAdd(L.counters + 1, (unsigned long long)work.top_nodes);
+    atomicAdd(L.counters + 2, (unsigned long long)work.blocks);
+    atomicAdd(L.counters + 3, (unsigned long long)work.cnodes);
+    atomicAdd(L.counters + 4, (unsigned long long)work.cells);
+    atomicAdd(L.counters + 5, (unsigned long long)n_hits);
   }
 }
 
@@ -1073,9 +1090,9 @@ template <bool ANYHIT>
 __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriScene ts, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
+    const float4 r0 = ld_ray4(rp);
+    const float4 r1 = ld_ray4(rp + 16);
+    const float tfar_in = ld_ray1(rp + L.tfar_offset);
     if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: this pass runs first and owns the initial state
     if (r0.w > tfar_in) continue;               // inactive stream ray
     if (ANYHIT && tfar_in < 0.0f) continue;     // bvh_intersector1.cpp:133
@@ -1158,9 +1175,9 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
 __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 16));
-    const float tfar_in = __ldg(reinterpret_cast<const float*>(rp + L.tfar_offset));
+    const float4 r0 = ld_ray4(rp);
+    const float4 r1 = ld_ray4(rp + 16);
+    const float tfar_in = ld_ray1(rp + L.tfar_offset);
     bool occluded = false;
     if (!(r0.w > tfar_in) && !(tfar_in < 0.0f)) {  // inactive stream ray; already occluded (bvh_intersector1.cpp:133)
       const float org[3] = {r0.x, r0.y, r0.z};
@@ -1174,7 +1191,64 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScen
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// read-bandwidth probe (measurement support, not on the traversal path): every thread streams 128-bit ld.global.cg loads
+// (L2-coherent, L1 bypassed) over a buffer `passes` times.  A working set well inside the 126 MB L2 measures the L2 read
+// bandwidth the traversal kernels' scene traffic is served at; one of several GB measures HBM.  The roofline's L2
+// denominator comes from this kernel (tools/bw_probe.py -> profiles/measured_l2.json).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ecb_bw_probe_kernel(const uint4* __restrict__ buf, size_t n_vec, int passes, unsigned* sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned acc = 0;
+  for (int p = 0; p < passes; p++) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n_vec; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+      const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+      acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    }
+    for (; i < n_vec; i += stride) {
+      const uint4 a = __ldcg(buf + i);
+      acc ^= a.x ^ a.y ^ a.z ^ a.w;
+    }
+  }
+  if (acc == 0x9E3779B9u) *sink = acc;  // keeps the loads alive; the buffer is zero-filled, so this never fires
+}
+
 }  // namespace
+
+cudaError_t ecb_probe_read_bandwidth(size_t bytes, int passes, int device, double* gbs_out) {
+  uint4* buf = nullptr;
+  unsigned* sink = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t n_vec = bytes / 16;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&buf), n_vec * 16);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sink), 4);
+  if (e == cudaSuccess) e = cudaMemset(buf, 0, n_vec * 16);
+  if (e == cudaSuccess) e = cudaEventCreate(&a);
+  if (e == cudaSuccess) e = cudaEventCreate(&b);
+  double best = 0.0;
+  for (int rep = 0; rep < 6 && e == cudaSuccess; rep++) {  // first repetition warms the L2, best of the rest
+    cudaEventRecord(a, nullptr);
+    ecb_bw_probe_kernel<<<sms * 8, 256>>>(buf, n_vec, passes, sink);
+    cudaEventRecord(b, nullptr);
+    e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+    if (e == cudaSuccess && rep > 0 && ms > 0.f) {
+      const double gbs = (double)n_vec * 16.0 * passes / (ms * 1e-3) / 1e9;
+      if (gbs > best) best = gbs;
+    }
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  if (buf) cudaFree(buf);
+  if (sink) cudaFree(sink);
+  *gbs_out = best;
+  return e;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
@@ -1222,8 +1296,9 @@ cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbL
 cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream) {
   if (L.M == 0) return cudaSuccess;
   const int grid = grid_for(L.M, device);
-  if (any_hit) ecb_instanced_kernel<true><<<grid, ECB_THREADS, 0, stream>>>(is, L);
-  else ecb_instanced_kernel<false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  if (any_hit) ecb_instanced_kernel<true, false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  else if (L.counters) ecb_instanced_kernel<false, true><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  else ecb_instanced_kernel<false, false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,9 @@ cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const
 // mixed scenes: the triangle accel is traversed first, in place (L.in == L.out), then the compressed accel on the same rays
 cudaError_t ecb_launch_triangles(const EcbDeviceTriScene& ts, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);
 
+// measurement support: read bandwidth of a working set of `bytes` streamed `passes` times (GB/s, best of 5)
+cudaError_t ecb_probe_read_bandwidth(size_t bytes, int passes, int device, double* gbs_out);
+
 // block construction (csrc/ecb_build.cu): all pointers are device pointers
 struct EcbBuildLaunch {
   const float* grids;        // n x (2^C+1)^2 x 3 displaced vertices, row-major

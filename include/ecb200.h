@@ -239,6 +239,12 @@ ECB_API void ecbHostFree(void* ptr);
  * Diagnostic only (bench.py reports it with its byte counts); the returned string is static. */
 ECB_API const char* ecbHostPathName(int caller_memory_is_pinned);
 
+/* Measurement support (not on the traversal path): read bandwidth in GB/s of a device buffer of `working_set_bytes`
+ * streamed `passes` times with 128-bit L1-bypassing loads from every SM.  32 MB x 64 passes measures the L2 the scene
+ * traffic of the traversal kernels is served from; 4 GB x 1 pass measures HBM.  The roofline's L2 denominator
+ * (profiles/measured_l2.json) comes from this call. */
+ECB_API ecbError ecbProbeReadBandwidth(size_t working_set_bytes, int passes, double* gbs_out);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 ECB_API uint64_t ecbLaunchCount(void);
 ECB_API const char* ecbErrorString(ecbError e);

@@ -119,7 +119,7 @@ int main(int argc, char** argv) {
   CHECK(ecbIntersect1M(scenes[0], 0, nullptr, 0, 80) == ECB_SUCCESS, "M = 0");
   float dummy[20] = {0};
   CHECK(ecbIntersect1M(scenes[0], 0, dummy, 1, 78) == ECB_ERROR_INVALID_ARGUMENT, "bad stride accepted");
-  // concurrent callers: two threads on one scene (serialised by the scene), two more on the other scene (sharing the pool)
+  // concurrent callers: two threads on one scene (each with its own staging context), two more on the other scene (sharing the pool)
   {
     std::vector<std::thread> th;
     for (int t = 0; t < 4; t++)
@@ -127,6 +127,30 @@ int main(int argc, char** argv) {
         for (int rep = 0; rep < 3; rep++) run_case(scenes[t & 1], (t & 1) != 0, (t & 2) != 0, 20, 40000u + 1000u * t, 0, 1000 + 10 * t + rep);
       });
     for (auto& x : th) x.join();
+  }
+  // a scene resident on several (mock) devices: long calls fan out, one contiguous ray range per device, every range
+  // through its own staging context; short calls stay on the primary device.  MOCK_CUDA_DEVICES > 1 enables this part.
+  if (getenv("MOCK_CUDA_DEVICES") && atoi(getenv("MOCK_CUDA_DEVICES")) > 1) {
+    const int n_dev = atoi(getenv("MOCK_CUDA_DEVICES"));
+    std::vector<int> devs;
+    for (int i = 0; i < n_dev; i++) devs.push_back(i);
+    for (int k = 0; k < 2; k++) {
+      CHECK(ecbSceneUploadMulti(scenes[k], devs.data(), (uint32_t)devs.size()) == ECB_SUCCESS, "upload multi: %s", ecbLastErrorMessage());
+      int got[8] = {0};
+      CHECK(ecbSceneResidentDevices(scenes[k], got, 8) == (uint32_t)n_dev, "resident device count");
+    }
+    for (int pinned = 0; pinned < 2; pinned++)
+      for (uint32_t M : {1000u, 262144u, 300001u, 700003u}) {
+        run_case(scenes[0], false, pinned, 20, M, 0, seed++);
+        run_case(scenes[1], true, pinned, 24, M, 0, seed++);
+        run_case(scenes[0], false, pinned, 12, M, 1, seed++);
+      }
+    std::vector<std::thread> th;
+    for (int t = 0; t < 3; t++)
+      th.emplace_back([&, t] { run_case(scenes[0], false, (t & 1) != 0, 20, 400000u + 1000u * t, 0, 5000 + t); });
+    for (auto& x : th) x.join();
+    const int bad_dev[1] = {n_dev};
+    CHECK(ecbSceneUploadMulti(scenes[0], bad_dev, 1) != ECB_SUCCESS, "upload to a device that does not exist accepted");
   }
   for (int k = 0; k < 2; k++) ecbSceneRelease(scenes[k]);
   const int f = g_failures.load();

@@ -184,3 +184,120 @@ def test_shim_exports_every_declared_embree3_symbol(ecb):
     finally:
         if env_before is not None:
             os.environ["ECB200_HOST_EMBREE"] = env_before
+
+
+def _blob_fields():
+    """Byte offsets of EcbBlobHeader fields (csrc/ecb_format.h): magic[8], 12 x u32, rcp_edges f32, bounds[6] f32, reserved u32,
+    3 x u64."""
+    names = ["version", "leaf_kind", "subdiv_level", "comp_level", "n_top", "n_blocks", "block_stride", "leaf_offset", "root",
+             "top_depth", "elems", "grid_width"]
+    off = {n: 8 + 4 * i for i, n in enumerate(names)}
+    off["rcp_edges"] = 8 + 4 * 12
+    off["header_bytes"] = 8 + 4 * 13 + 4 * 6 + 4 + 8 * 3
+    return off
+
+
+@pytest.mark.parametrize("field,value", [
+    ("root", 0x7FFFFFFF), ("root", 0x80000000 | 0x0FFFFFFF),       # node / block index past the arrays
+    ("elems", 85), ("grid_width", 9), ("block_stride", 4096), ("leaf_offset", 16), ("comp_level", 3), ("comp_level", 77),
+    ("top_depth", 1), ("n_top", 0x7FFFFFFF), ("n_blocks", 0x7FFFFFFF), ("leaf_kind", 9)])
+def test_blob_header_is_recomputed_not_believed(ecb, tmp_path, field, value):
+    """every derived constant of a blob is recomputed from (leaf kind, C); sizes are bounded by the file."""
+    scene = ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, "cube_s4c2_leaf.rimg"), np.uint8))
+    p = str(tmp_path / "s.ecbs")
+    scene.save(p)
+    raw = bytearray(open(p, "rb").read())
+    off = _blob_fields()
+    raw[off[field]:off[field] + 4] = int(value).to_bytes(4, "little")
+    bad = str(tmp_path / "bad.ecbs")
+    open(bad, "wb").write(raw)
+    if field == "top_depth":   # believed by nobody: the depth is recomputed, a wrong value in the file is harmless
+        assert ecb.Scene.load(bad).info()["top_depth"] == scene.info()["top_depth"]
+        return
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(bad)
+
+
+def test_blob_with_a_reference_cycle_or_truncation_is_rejected(ecb, tmp_path):
+    scene = ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, "cube_s5c3_leaf.rimg"), np.uint8))
+    assert scene.info()["n_top_nodes"] >= 2
+    p = str(tmp_path / "s.ecbs")
+    scene.save(p)
+    raw = bytearray(open(p, "rb").read())
+    hdr = _blob_fields()["header_bytes"]
+    cyc = bytearray(raw)
+    cyc[hdr + 112 + 96:hdr + 112 + 100] = (0).to_bytes(4, "little")     # node 1 points back at node 0: not pre-order
+    open(str(tmp_path / "cyc.ecbs"), "wb").write(cyc)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(str(tmp_path / "cyc.ecbs"))
+    self_ref = bytearray(raw)
+    self_ref[hdr + 96:hdr + 100] = (0).to_bytes(4, "little")            # node 0 points at itself
+    open(str(tmp_path / "self.ecbs"), "wb").write(self_ref)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(str(tmp_path / "self.ecbs"))
+    for cut in (10, 100, hdr + 50, len(raw) - 7):
+        open(str(tmp_path / "cut.ecbs"), "wb").write(raw[:cut])
+        with pytest.raises(ecb.EcbError):
+            ecb.Scene.load(str(tmp_path / "cut.ecbs"))
+
+
+def test_truncated_or_corrupt_image_is_rejected_not_dereferenced(ecb, tmp_path):
+    """every offset read from a relocated image is range-checked against the image size."""
+    from oracle import pyoracle as po
+    image = np.fromfile(os.path.join(GOLDEN, "cubeplane_s4c2_leaf.rimg"), np.uint8)
+    h = po.rimg_header(image)
+    root, total = int(h["root"]), int(h["total_bytes"])
+    for cut in (total // 2, total - 64, 4096):
+        with pytest.raises(ecb.EcbError):
+            ecb.Scene.from_image(image[:cut].copy())   # header says `total` bytes, the buffer is shorter
+        short = image[:cut].copy()
+        short[48:56] = np.frombuffer(int(cut).to_bytes(8, "little"), np.uint8)   # header lies consistently: offsets now dangle
+        with pytest.raises(ecb.EcbError):
+            ecb.Scene.from_image(short)
+    # a node whose first child points back at the node itself: bounded by the node budget of the image, no 4^depth fan-out
+    assert root & 8 == 0, "test scene must have an inner root node"
+    loop = image.copy()
+    loop[root:root + 8] = np.frombuffer(int(root).to_bytes(8, "little"), np.uint8)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.from_image(loop)
+    # a block whose payload pointer leaves the image
+    wild = image.copy()
+    node = wild[root:root + 128].view(np.uint64)
+    leaf_refs = [int(c) for c in node[:4] if int(c) & 8 and int(c) != 8]
+    if leaf_refs:
+        blk = leaf_refs[0] & ~15
+        wild[blk + 32:blk + 40] = np.frombuffer(int(total + (1 << 30)).to_bytes(8, "little"), np.uint8)
+        with pytest.raises(ecb.EcbError):
+            ecb.Scene.from_image(wild)
+    p = str(tmp_path / "empty.rimg")
+    open(p, "wb").close()
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.from_image_file(p)
+
+
+def test_instancing_scene_blob_round_trip(ecb, tmp_path):
+    """SURVEY 8f-3 for instancing scenes: object scenes, instance-level BVH4, items and instance records in one blob."""
+    from oracle import pyoracle as po
+    if not po.have_reference():
+        pytest.skip("needs the compiled reference to build an instanced scene")
+    from instancing_util import build_instanced, import_instanced
+    top, objs = build_instanced(po, "leaf", [("cube", 3, 2), ("cube", 4, 2)], grid=1, spacing=3.0)
+    inst, scenes = import_instanced(ecb, po, top, objs)
+    info = inst.info()
+    p = str(tmp_path / "inst.ecb")
+    inst.save(p)
+    again = ecb.Scene.load(p)
+    i2 = again.info()
+    for k in ("n_top_nodes", "n_blocks", "top_depth", "device_bytes", "micro_triangles", "leaf_kind"):
+        assert info[k] == i2[k], k
+    raw = bytearray(open(p, "rb").read())
+    # instance record pointing at an object scene that does not exist
+    bad = bytearray(raw)
+    bad[-64 + 52:-64 + 56] = (77).to_bytes(4, "little")
+    open(str(tmp_path / "bad.ecb"), "wb").write(bad)
+    with pytest.raises(ecb.EcbError):
+        ecb.Scene.load(str(tmp_path / "bad.ecb"))
+    for cut in (20, len(raw) // 2, len(raw) - 3):
+        open(str(tmp_path / "cut.ecb"), "wb").write(raw[:cut])
+        with pytest.raises(ecb.EcbError):
+            ecb.Scene.load(str(tmp_path / "cut.ecb"))

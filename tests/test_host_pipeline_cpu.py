@@ -4,7 +4,8 @@ csrc/ecb_api.cpp and csrc/ecb_import.cpp are compiled UNMODIFIED with g++ -fsani
 host-only stand-in for the CUDA runtime in which every stream is a worker thread, and fake kernels whose results are a
 function of the ray alone).  tests/cpp/host_pipeline_check.cpp then drives the host-buffer entry points -- plain and mixed
 scenes, pinned and pageable caller memory, dense and padded strides, 1 ... 150 001 rays in 4 Ki-ray chunks (many more
-chunks than pipeline stages), closest hit / any hit / exact any hit, concurrent callers -- and checks every word of every
+chunks than pipeline stages), closest hit / any hit / exact any hit, concurrent callers, scenes resident on three (mock)
+devices with calls that fan out over them -- and checks every word of every
 record against the API contract.  ThreadSanitizer turns a staging buffer reused too early, a scatter job that outlives
 its call or an unprotected counter into a report, which fails the test.  This is test infrastructure: the mock is only
 ever found through this build line's -I, and the product never links it."""
@@ -35,7 +36,9 @@ def _build(exe, flags):
 
 
 def _run(exe, path):
-    env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK="4096", ECB200_HOST_THREADS="4",
+    # three mock devices: the second half of the check uploads the scenes to all of them (ecbSceneUploadMulti) and makes
+    # calls long enough to fan out, one ray range per device
+    env = dict(os.environ, ECB200_HOST_PATH=path, ECB200_HOST_CHUNK="4096", ECB200_HOST_THREADS="4", MOCK_CUDA_DEVICES="3",
                TSAN_OPTIONS="halt_on_error=0 exitcode=66")
     r = subprocess.run([exe, os.path.join(HERE, "golden", "cube_s4c2_leaf.rimg"), os.path.join(HERE, "golden", "cubeplane_s4c2_leaf.rimg")],
                        env=env, capture_output=True, text=True, timeout=600)

@@ -1,0 +1,154 @@
+"""GPU tests (-m gpu) of the multi-GPU plumbing of the path: compact device results (what a frame gather
+moves), concurrent host-buffer callers on one scene (the reference's tile-parallel usage, rtcore.cpp:287-304 takes no
+lock), and -- on a box with at least two GPUs -- one host-buffer call fanned out over the devices of a scene
+(ecbSceneUploadMulti) and the peer-copy gather of the C ABI.  Everything is held to the single-device bits.
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from embree_compressed_b200 import raygen as rg
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _scene(ecb, name="cube_s5c3_leaf"):
+    return ecb.Scene.from_image(np.fromfile(os.path.join(GOLDEN, name + ".rimg"), np.uint8))
+
+
+def _rays(n_side=512):
+    prim = rg.primary_rays(n_side, n_side, **rg.CUBE_CAMERA)
+    prim[::7, 3], prim[::7, 8] = 2.0, 1.0   # inactive stream rays (tnear > tfar) stay untouched
+    return prim
+
+
+def test_compact_device_results_equal_the_in_place_records(ecb):
+    import torch
+    scene = _scene(ecb).upload(0)
+    rays = _rays()
+    n = len(rays)
+    dev = torch.device("cuda", 0)
+    a = torch.from_numpy(rays).to(dev)
+    scene.intersect_device(a.data_ptr(), n)
+    b = torch.from_numpy(rays).to(dev)
+    geom = torch.full((n,), 123, dtype=torch.int32, device=dev)
+    hit = torch.full((n, 4), -7.0, dtype=torch.float32, device=dev)
+    scene.intersect_device_compact(b.data_ptr(), n, geom.data_ptr(), hit.data_ptr())
+    torch.cuda.synchronize()
+    assert (b.cpu().numpy().view(np.uint32) == rays.view(np.uint32)).all(), "compact mode must not write the ray records"
+    want = a.cpu().numpy()
+    wi = want.view(np.uint32)
+    g, h = geom.cpu().numpy().view(np.uint32), hit.cpu().numpy()
+    assert (g == wi[:, 18]).all()
+    m = wi[:, 18] != 0xFFFFFFFF
+    assert m.sum() > 1000
+    assert (h[m].view(np.uint32) == want[m][:, [8, 15, 16, 17]].view(np.uint32)).all()
+    assert (h[~m] == -7.0).all(), "misses write no hit record"
+    # any-hit: geomID 0 = occluded
+    r12 = rg.rays_only(rays)
+    c = torch.from_numpy(r12).to(dev)
+    scene.occluded_device(c.data_ptr(), n)
+    d = torch.from_numpy(r12).to(dev)
+    occ = torch.full((n,), 5, dtype=torch.int32, device=dev)
+    scene.occluded_device_compact(d.data_ptr(), n, occ.data_ptr())
+    torch.cuda.synchronize()
+    assert ((occ.cpu().numpy() == 0) == np.isneginf(c.cpu().numpy()[:, 8])).all()
+
+
+def test_concurrent_host_callers_get_their_own_staging_context(ecb):
+    """Four threads on ONE scene, long and short calls mixed: every call leaves the single-caller bits."""
+    scene = _scene(ecb).upload(0)
+    rays = _rays(640)
+    want = rays.copy()
+    scene.intersect1M(want)
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                m = (len(rays), 50000, 16, 300001)[(k + rep) % 4]
+                got = rays[:m].copy()
+                scene.intersect1M(got)
+                if not (got.view(np.uint32) == want[:m].view(np.uint32)).all():
+                    errors.append("thread %d rep %d: %d rays differ" % (k, rep, m))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+def test_one_host_call_fans_out_over_the_devices_of_a_scene(ecb):
+    import torch
+    if not _two_gpus():
+        pytest.skip("needs two GPUs")
+    n_dev = min(4, torch.cuda.device_count())
+    single = _scene(ecb).upload(0)
+    multi = _scene(ecb).upload_multi(list(range(n_dev)))
+    assert multi.resident_devices() == list(range(n_dev))
+    rays = _rays(1024)   # 1 Mi rays: above the fan-out threshold
+    want = rays.copy()
+    single.intersect1M(want)
+    for pinned in (False, True):
+        if pinned:
+            buf, ptr = ecb.host_alloc(rays.nbytes)
+            got = buf.view(np.float32).reshape(rays.shape)
+            got[:] = rays
+        else:
+            got = rays.copy()
+        multi.intersect1M(got)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all(), "fan-out over %d devices differs (pinned=%s)" % (n_dev, pinned)
+        if pinned:
+            ecb.host_free(ptr)
+    occ_want, occ_got = rg.rays_only(rays), rg.rays_only(rays)
+    single.occluded1M(occ_want)
+    multi.occluded1M(occ_got)
+    assert (occ_got.view(np.uint32) == occ_want.view(np.uint32)).all()
+    # device-buffer calls run on the device that owns the buffer
+    for d in range(n_dev):
+        with torch.cuda.device(d):
+            t = torch.from_numpy(rays[:100000]).to(torch.device("cuda", d))
+            multi.intersect_device(t.data_ptr(), t.shape[0])
+            torch.cuda.synchronize()
+            assert (t.cpu().numpy().view(np.uint32) == want[:100000].view(np.uint32)).all(), "device %d" % d
+
+
+def test_peer_copy_into_another_devices_buffer(ecb):
+    """The gather primitive of the C ABI inside one process: device 1 writes its compact records into device 0's arrays."""
+    import torch
+    if not _two_gpus():
+        pytest.skip("needs two GPUs")
+    scene = _scene(ecb).upload_multi([0, 1])
+    rays = _rays()
+    n = len(rays)
+    with torch.cuda.device(0):
+        frame_geom = ecb.device_alloc(4 * n)
+        a = torch.from_numpy(rays).to("cuda:0")
+        scene.intersect_device(a.data_ptr(), n)
+        torch.cuda.synchronize()
+    with torch.cuda.device(1):
+        b = torch.from_numpy(rays).to("cuda:1")
+        geom = torch.empty(n, dtype=torch.int32, device="cuda:1")
+        hit = torch.empty((n, 4), dtype=torch.float32, device="cuda:1")
+        s = torch.cuda.current_stream().cuda_stream
+        scene.intersect_device_compact(b.data_ptr(), n, geom.data_ptr(), hit.data_ptr(), stream=s)
+        ecb.peer_copy_async(frame_geom, geom.data_ptr(), 4 * n, s)
+        torch.cuda.synchronize()
+    with torch.cuda.device(0):
+        back = torch.empty(n, dtype=torch.int32, device="cuda:0")
+        ecb.peer_copy_async(back.data_ptr(), frame_geom, 4 * n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert (back.cpu().numpy().view(np.uint32) == a.cpu().numpy().view(np.uint32)[:, 18]).all()
+        ecb.device_free(frame_geom)
