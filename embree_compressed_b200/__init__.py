@@ -107,6 +107,8 @@ SYMBOLS = {
     "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbHostFree": (None, [_vp]),
     "ecbHostPathName": (C.c_char_p, [C.c_int]),
+    "ecbSetTraversalKernel": (None, [C.c_int]),
+    "ecbGetTraversalKernel": (C.c_int, []),
     "ecbProbeReadBandwidth": (C.c_int, [_sz, C.c_int, C.POINTER(C.c_double)]),
     "ecbLaunchCount": (_u64, []),
     "ecbErrorString": (C.c_char_p, [C.c_int]),
@@ -143,6 +145,19 @@ def launch_count():
 def host_path_for(pinned):
     """Name of the transfer strategy the host-buffer entry points pick for this kind of caller memory."""
     return _lib().ecbHostPathName(1 if pinned else 0).decode()
+
+
+KERNEL_LANE, KERNEL_QUAD = 0, 1
+
+
+def set_traversal_kernel(mode):
+    """ECB_KERNEL_LANE / ECB_KERNEL_QUAD ("lane" / "quad"), or -1 / None for the default."""
+    mode = {"lane": 0, "quad": 1, None: -1}.get(mode, mode)
+    _lib().ecbSetTraversalKernel(int(mode))
+
+
+def traversal_kernel():
+    return "quad" if _lib().ecbGetTraversalKernel() == 1 else "lane"
 
 
 def probe_read_bandwidth(working_set_bytes, passes):

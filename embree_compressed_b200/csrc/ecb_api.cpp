@@ -189,6 +189,7 @@ ecbError upload_plain(ecbScene* s, Residency* r) {
   d.elems = s->elems;
   d.grid_width = s->grid_width;
   d.rcp_edges = s->rcp_edges;
+  d.top_depth = s->info.top_depth;
   if (s->has_triangles()) {  // mixed scene: triangle accel next to the compressed one
     CU(upload_array(&r->d_tri_top, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode)));
     CU(upload_array(&r->d_tri_blocks, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock)));
@@ -1571,6 +1572,9 @@ ecbError ecbPeerCopyAsync(void* d_dst, const void* d_src, size_t bytes, void* st
   CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return ECB_SUCCESS;
 }
+
+void ecbSetTraversalKernel(int mode) { ecb_set_kernel_mode(mode); }
+int ecbGetTraversalKernel(void) { return ecb_kernel_mode(); }
 
 ecbError ecbProbeReadBandwidth(size_t working_set_bytes, int passes, double* gbs_out) {
   if (!gbs_out || working_set_bytes < (1u << 20) || passes < 1) return ECB_ERROR_INVALID_ARGUMENT;

@@ -51,6 +51,7 @@ struct EcbDeviceScene {
   uint32_t elems;         // (4^C-1)/3 inner nodes per block
   uint32_t grid_width;    // 2^C+1
   float rcp_edges;        // 1/2^C
+  uint32_t top_depth;     // depth of the top-level BVH4 (sizes the shared-memory stack of the quad kernel: 3*depth+1 entries)
 };
 
 // ---- instanced scenes: a BVH4 over instances of object scenes ----

@@ -17,6 +17,10 @@
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
 
 #include "ecb_format.h"
 #include "ecb_kernels.h"
@@ -743,6 +747,8 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
   }
 }
 
+#include "ecb_quad_kernel.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------
 // instanced scenes: BVHNIntersector1<4,BVH_AN1,robust=false,ArrayIntersector1<ObjectIntersector1>> over the instances
 // (kernels/bvh/bvh_intersector1_bvh4.cpp:81), FastInstanceIntersectorN::intersect1/occluded1 per instance
@@ -1267,11 +1273,59 @@ static int grid_for(uint64_t M, int device) {
   return (int)(need < cap ? (need ? need : 1) : cap);
 }
 
+// Which closest-hit kernel a launch uses: 0 = one lane per ray (ecb_intersect_kernel), 1 = four lanes per ray
+// (ecb_intersect_quad_kernel).  Both produce the same bits.  ECB200_KERNEL=lane|quad overrides the built-in choice.
+static std::atomic<int> g_kernel_mode{-1};
+int ecb_kernel_mode() {
+  int m = g_kernel_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("ECB200_KERNEL");
+    m = (e && strcmp(e, "quad") == 0) ? 1 : (e && strcmp(e, "lane") == 0) ? 0 : ECB_DEFAULT_KERNEL_MODE;
+    g_kernel_mode.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
+void ecb_set_kernel_mode(int mode) { g_kernel_mode.store(mode < 0 ? -1 : (mode ? 1 : 0), std::memory_order_relaxed); }
+
+static cudaError_t launch_quad(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream) {
+  if (device < 0 || device >= 16) device = 0;
+  if (!g_grid_cache[device]) grid_for(1, device);
+  // shared memory: quantization tables | per-quad top-level stacks ({ref, dist}, odd entry count: no bank aliasing between
+  // quads) | per-quad block stacks (inner nodes only: 3*(C-1)+1 entries of {node, box} = 7 words)
+  uint32_t top_entries = 3u * sc.top_depth + 2u;
+  top_entries |= 1u;
+  const uint32_t blk_entries = 3u * (sc.comp_level > 0 ? sc.comp_level - 1u : 0u) + 1u;
+  const size_t smem = 4u * (32u + 2u * ECB_Q_QUADS * top_entries + 7u * ECB_Q_QUADS * blk_entries);
+  const uint64_t need = (L.M * 4 + ECB_Q_THREADS - 1) / ECB_Q_THREADS;
+  const uint64_t cap = (uint64_t)g_grid_cache[device] * ECB_Q_BLOCKS_PER_SM;
+  const int grid = (int)(need < cap ? (need ? need : 1) : cap);
+#define ECB_LAUNCH_Q(LEAF)                                                                                          \
+  {                                                                                                                 \
+    if (smem > 48u * 1024u) {                                                                                       \
+      cudaError_t ae = L.counters ? cudaFuncSetAttribute(ecb_intersect_quad_kernel<LEAF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) \
+                                  : cudaFuncSetAttribute(ecb_intersect_quad_kernel<LEAF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (ae != cudaSuccess) return ae;                                                                             \
+    }                                                                                                               \
+    if (L.counters)                                                                                                 \
+      ecb_intersect_quad_kernel<LEAF, true><<<grid, ECB_Q_THREADS, smem, stream>>>(sc, L, top_entries, blk_entries); \
+    else                                                                                                            \
+      ecb_intersect_quad_kernel<LEAF, false><<<grid, ECB_Q_THREADS, smem, stream>>>(sc, L, top_entries, blk_entries); \
+  }
+  switch (sc.leaf_kind) {
+    case 0: ECB_LAUNCH_Q(0); break;
+    case 1: ECB_LAUNCH_Q(1); break;
+    default: ECB_LAUNCH_Q(2); break;
+  }
+#undef ECB_LAUNCH_Q
+  return cudaGetLastError();
+}
+
 cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream) {
   if (L.M == 0) return cudaSuccess;
-  const int grid = grid_for(L.M, device);
   cudaError_t e = cudaMemsetAsync(L.queue, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
+  if (ecb_kernel_mode() == 1) return launch_quad(sc, device, L, stream);
+  const int grid = grid_for(L.M, device);
 #define ECB_LAUNCH(LEAF)                                                                  \
   if (L.counters)                                                                         \
     ecb_intersect_kernel<LEAF, true><<<grid, ECB_THREADS, 0, stream>>>(sc, L);            \

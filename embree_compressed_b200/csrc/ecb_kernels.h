@@ -55,6 +55,11 @@ struct EcbLaunch {
   unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)
 };
 
+#ifndef ECB_DEFAULT_KERNEL_MODE
+#define ECB_DEFAULT_KERNEL_MODE 0  // closest-hit kernel of ecb_launch_intersect: 0 = one lane per ray, 1 = four lanes per ray
+#endif
+int ecb_kernel_mode();
+void ecb_set_kernel_mode(int mode);  // 0 lane, 1 quad, -1 back to the default / ECB200_KERNEL
 cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
 cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream);
 cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);

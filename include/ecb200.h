@@ -239,6 +239,14 @@ ECB_API void ecbHostFree(void* ptr);
  * Diagnostic only (bench.py reports it with its byte counts); the returned string is static. */
 ECB_API const char* ecbHostPathName(int caller_memory_is_pinned);
 
+/* The closest-hit traversal exists as two kernels that return the same bits: ECB_KERNEL_LANE (one lane per ray, best for
+ * coherent rays on shallow blocks) and ECB_KERNEL_QUAD (four lanes per ray, one child box per lane: best for incoherent
+ * rays and displaced geometry).  Process-wide; -1 restores the default (or $ECB200_KERNEL = lane | quad). */
+#define ECB_KERNEL_LANE 0
+#define ECB_KERNEL_QUAD 1
+ECB_API void ecbSetTraversalKernel(int mode);
+ECB_API int ecbGetTraversalKernel(void);
+
 /* Measurement support (not on the traversal path): read bandwidth in GB/s of a device buffer of `working_set_bytes`
  * streamed `passes` times with 128-bit L1-bypassing loads from every SM.  32 MB x 64 passes measures the L2 the scene
  * traffic of the traversal kernels is served from; 4 GB x 1 pass measures HBM.  The roofline's L2 denominator

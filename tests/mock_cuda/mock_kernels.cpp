@@ -88,6 +88,8 @@ cudaError_t ecb_launch_instanced(const EcbDeviceInstScene&, int, const EcbLaunch
   mock_enqueue(stream, [copy, any_hit] { any_hit ? any_pass(0, copy) : closest_pass(0, copy); });
   return cudaSuccess;
 }
+int ecb_kernel_mode() { return 0; }
+void ecb_set_kernel_mode(int) {}
 cudaError_t ecb_probe_read_bandwidth(size_t, int, int, double* g) { *g = 0.0; return cudaErrorNoDevice; }
 size_t ecb_build_tmp_bytes(uint32_t) { return 0; }
 cudaError_t ecb_launch_build(const EcbBuildLaunch&, int, cudaStream_t) { return cudaErrorNoDevice; }
