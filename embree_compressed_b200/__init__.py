@@ -107,6 +107,7 @@ SYMBOLS = {
     "ecbHostAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbHostFree": (None, [_vp]),
     "ecbHostPathName": (C.c_char_p, [C.c_int]),
+    "ecbBoundsCheckFailures": (C.c_int, [C.POINTER(_u64)]),
     "ecbSetTraversalKernel": (None, [C.c_int]),
     "ecbGetTraversalKernel": (C.c_int, []),
     "ecbProbeReadBandwidth": (C.c_int, [_sz, C.c_int, C.POINTER(C.c_double)]),
@@ -145,6 +146,15 @@ def launch_count():
 def host_path_for(pinned):
     """Name of the transfer strategy the host-buffer entry points pick for this kind of caller memory."""
     return _lib().ecbHostPathName(1 if pinned else 0).decode()
+
+
+def bounds_check_failures():
+    """(enabled, [8 violation counters]) of a -DECB_BOUNDS_CHECK build; enabled is False for the shipping library."""
+    c = (_u64 * 8)()
+    r = _lib().ecbBoundsCheckFailures(c)
+    if r < 0:
+        raise RuntimeError("ecbBoundsCheckFailures: CUDA error")
+    return bool(r), [int(v) for v in c]
 
 
 KERNEL_LANE, KERNEL_QUAD = 0, 1

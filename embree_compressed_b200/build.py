@@ -33,10 +33,14 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_variant(name, defines):
-    """Developer helper: build libecb200_<name>.so with extra -D flags (kernel A/B experiments, tools/kbench.py)."""
+def build_variant(name, defines, only_if_stale=False):
+    """libecb200_<name>.so with extra -D flags: the bounds-checking build ("check", ECB_BOUNDS_CHECK=1) and kernel A/B
+    experiments (tools/kbench.py)."""
     out = os.path.join(HERE, "libecb200_%s.so" % name)
     srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_build.cu", "ecb_api.cpp", "ecb_import.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [os.path.join(HERE, "..", "include", "ecb200.h"), __file__]
+    if only_if_stale and not _stale(out, deps):
+        return out
     cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-shared", "-o", out] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -47,7 +51,7 @@ def build_variant(name, defines):
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in ("ecb_kernels.cu", "ecb_build.cu", "ecb_api.cpp", "ecb_import.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
         [os.path.join(HERE, "..", "include", "ecb200.h"), __file__]
     if force or _stale(LIB, deps):
         cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs

@@ -170,6 +170,9 @@ ecbError upload_instanced(ecbScene* s, Residency* r) {
   d.n_items = (uint32_t)s->items.size();
   d.n_instances = (uint32_t)s->instances.size();
   d.n_objects = (uint32_t)objs.size();
+  d.uniform_leaf_kind = objs.empty() ? -1 : (int32_t)objs[0].leaf_kind;
+  for (const EcbDeviceScene& o : objs)
+    if ((int32_t)o.leaf_kind != d.uniform_leaf_kind) d.uniform_leaf_kind = -1;
   return ECB_SUCCESS;
 }
 
@@ -1571,6 +1574,15 @@ ecbError ecbPeerCopyAsync(void* d_dst, const void* d_src, size_t bytes, void* st
   if (!bytes) return ECB_SUCCESS;
   CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return ECB_SUCCESS;
+}
+
+int ecbBoundsCheckFailures(uint64_t counts_out[8]) {
+  unsigned long long c[8] = {0};
+  int enabled = 0;
+  if (ecb_bounds_check_read(c, &enabled) != cudaSuccess) return -1;
+  if (counts_out)
+    for (int i = 0; i < 8; i++) counts_out[i] = c[i];
+  return enabled;
 }
 
 void ecbSetTraversalKernel(int mode) { ecb_set_kernel_mode(mode); }

@@ -72,6 +72,7 @@ struct EcbDeviceInstScene {
   const EcbDeviceScene* objects;
   uint32_t root;
   uint32_t n_nodes, n_items, n_instances, n_objects;
+  int32_t uniform_leaf_kind;  // leaf kind shared by all object scenes, or -1 (selects the kernel instantiation)
 };
 
 // ---- triangle meshes of a mixed scene: the host's BVH4 over Triangle4v blocks ----

@@ -25,6 +25,27 @@
 #include "ecb_format.h"
 #include "ecb_kernels.h"
 
+// ---------------------------------------------------------------------------------------------------------------
+// -DECB_BOUNDS_CHECK: every index the kernels derive from scene data (node / block / item / instance references, stack
+// positions, node-word and leaf offsets) is checked against the array it indexes; a violation is counted per class in
+// g_ecb_check[] (read back with ecbBoundsCheckFailures).  compute-sanitizer is not available on the B200 pool, so the
+// golden and parity tests are run against a library built with this flag instead (tests/test_bounds_check_gpu.py).
+// The shipping build compiles the checks away.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef ECB_BOUNDS_CHECK
+__device__ unsigned long long g_ecb_check[8];
+#define ECB_CHECK(cond, slot)                          \
+  do {                                                 \
+    if (!(cond)) atomicAdd(&g_ecb_check[slot], 1ull);  \
+  } while (0)
+#else
+#define ECB_CHECK(cond, slot) \
+  do {                        \
+  } while (0)
+#endif
+// slots: 0 top-level stack overflow, 1 top-level node index, 2 block index, 3 block stack overflow, 4 node word / leaf
+// offset inside a block, 5 instance item / instance / object index, 6 triangle block index, 7 ray index
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -228,6 +249,7 @@ template <int LEAF, bool STATS>
 __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const float* __restrict__ lut, uint32_t block_index,
                                                 const float rorg[3], const float rdir[3], float ray_tnear, Hit& hit, Work& work) {
   if (STATS) work.blocks++;
+  ECB_CHECK(block_index < sc.n_blocks, 2);
   const uint8_t* blk = sc.blocks + (size_t)block_index * sc.block_stride;
   const float4* h4 = reinterpret_cast<const float4*>(blk);
   // 144-byte header = 9 x 16-byte read-only loads
@@ -311,6 +333,7 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
 
     if (curr >= elems) {
       const unsigned idx = curr - elems;
+      ECB_CHECK(idx < 3u * elems + 1u, 4);
       if (STATS) work.cells++;
       if (LEAF == 1) {
         const float box_near = (idx & 2) ? ((idx & 1) ? tNear[3] : tNear[2]) : ((idx & 1) ? tNear[1] : tNear[0]);
@@ -413,6 +436,7 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
     // inner node: decode (Node::getNode), test 4 children, push the hit ones nearest-on-top
     const unsigned next = curr * 4 + 1;
     if (STATS) work.cnodes++;
+    ECB_CHECK(curr < elems, 4);
     const uint32_t w = curr == 0 ? root_word : __ldg(node_words + (curr - 1));
     const unsigned xz = w & 0xff, xb = (w >> 8) & 0xff, yz = (w >> 16) & 0xff, yb = w >> 24;
     const float dimX = pBox[3] - pBox[0], dimY = pBox[4] - pBox[1], dimZ = pBox[5] - pBox[2];
@@ -445,6 +469,7 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
 
     // stack position of child r = sp+1 + #(hit children that must be popped after it)   (compressed.h:668-749)
     const int n = __popc(mask);
+    ECB_CHECK(sp + n < 16, 3);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       if (!(mask & (1u << r))) continue;
@@ -513,7 +538,7 @@ __device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, 
 // Restates the pop loop + down loop of bvh_intersector1.cpp:73-105 with traverseClosestHit (bvh_traverser1.h:436-506).
 template <bool STATS>
 __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ nodes, const TravRay& tr, uint32_t* stack_ref, uint32_t* stack_dist,
-                                               int& sp, float ray_tfar, Work& work) {
+                                               int& sp, float ray_tfar, Work& work, uint32_t n_nodes = 0xFFFFFFFFu) {
   while (sp > 0) {
     sp--;
     uint32_t cur = stack_ref[sp];
@@ -521,6 +546,8 @@ __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ no
     bool popped = false;
     while (!(cur & ECB_REF_LEAF)) {
       if (STATS) work.top_nodes++;
+      ECB_CHECK(cur < n_nodes, 1);
+      ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
       float tNear[4];
       uint32_t child[4];
       const unsigned mask = top_node(nodes, cur, tr, tNear, child);
@@ -579,6 +606,8 @@ __device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float 
     uint32_t cur = stack_ref[sp];
     bool popped = false;
     while (!(cur & ECB_REF_LEAF)) {
+      ECB_CHECK(cur < sc.n_top, 1);
+      ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
       float tNear[4];
       uint32_t child[4];
       const unsigned mask = top_node(sc.top, cur, tr, tNear, child);
@@ -665,6 +694,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         const bool mine = ((need >> lane) & 1u) && rank < take;
         if (mine) {
           index = chunk_next + rank;
+          ECB_CHECK(index < L.M, 7);
           const uint8_t* rp = L.in + index * L.in_stride;
           const float4 r0 = ld_ray4(rp);       // org.xyz, tnear
           const float4 r1 = ld_ray4(rp + 16);  // dir.xyz, time
@@ -694,7 +724,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
 
     // ---- top level: every traversing lane runs to its next block or terminates ----
     if (busy && pending == ECB_REF_EMPTY) {
-      pending = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+      pending = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work, sc.n_top);
       if (pending == ECB_REF_EMPTY) {
         // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
         busy = false;
@@ -805,8 +835,8 @@ __device__ __forceinline__ unsigned fast_node(const EcbTopNode* nodes, uint32_t 
 
 // closest hit inside one object scene (what rtcIntersect1 on the instanced scene does)
 template <int LEAF, bool STATS>
-__device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
-                                          float ray_tnear, Hit& hit, Work& work) {
+__device__ __forceinline__ void trace_object_body(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
+                                                  float ray_tnear, Hit& hit, Work& work) {
   uint32_t stack_ref[ECB_MAX_TOP_STACK];
   uint32_t stack_dist[ECB_MAX_TOP_STACK];
   if (sc.root == ECB_REF_EMPTY) return;
@@ -816,11 +846,17 @@ __device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float*
   stack_dist[0] = 0xff800000u;
   int sp = 1;
   for (;;) {
-    const uint32_t leaf = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work);
+    const uint32_t leaf = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work, sc.n_top);
     if (leaf == ECB_REF_EMPTY) break;
     block_intersect<LEAF, STATS>(sc, lut, leaf & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
     tr.tfar = hit.tfar;
   }
+}
+// out-of-line form for instancing scenes whose object scenes mix leaf kinds (three instantiations would triple the kernel)
+template <int LEAF, bool STATS>
+__device__ __noinline__ void trace_object(const EcbDeviceScene& sc, const float* lut, const float org[3], const float dir[3],
+                                          float ray_tnear, Hit& hit, Work& work) {
+  trace_object_body<LEAF, STATS>(sc, lut, org, dir, ray_tnear, hit, work);
 }
 
 __device__ __forceinline__ void instance_ray(const EcbInstance* in, const float o[3], const float d[3], float lo[3], float ld[3],
@@ -838,7 +874,9 @@ __device__ __forceinline__ void instance_ray(const EcbInstance* in, const float 
   object = e.y;
 }
 
-template <bool ANYHIT, bool STATS>
+// KIND: leaf kind shared by every object scene (the usual case: one subdiv_accel per device) -> the object traversal is
+// inlined; -1: mixed kinds, dispatched per visit through the out-of-line form
+template <bool ANYHIT, bool STATS, int KIND>
 __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceInstScene is, EcbLaunch L) {
   __shared__ float lut[32];
   init_lut(lut);
@@ -877,6 +915,8 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
       while (!(cur & ECB_REF_LEAF)) {
         float tNear[4];
         uint32_t child[4];
+        ECB_CHECK(cur < is.n_nodes, 1);
+        ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
         const unsigned mask = fast_node(is.nodes, cur, tr, tNear, child);
         if (mask == 0) { popped = true; break; }
         uint32_t c[4], d[4];
@@ -920,11 +960,14 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
       }
       if (popped || cur == ECB_REF_EMPTY) continue;
       const uint32_t first = (cur & ~ECB_REF_LEAF) >> 3, num = cur & 7u;
+      ECB_CHECK(first + num <= is.n_items, 5);
       for (uint32_t k = 0; k < num && !occluded; k++) {
+        ECB_CHECK(__ldg(is.items + first + k) < is.n_instances, 5);
         const EcbInstance* in = is.instances + __ldg(is.items + first + k);
         float lo[3], ld[3];
         uint32_t geomID, object;
         instance_ray(in, org, dir, lo, ld, geomID, object);
+        ECB_CHECK(object < is.n_objects, 5);
         const EcbDeviceScene sc = is.objects[object];
         if (ANYHIT) {
           if (sc.root != ECB_REF_EMPTY && trace_any(sc, lo, ld, r0.w, hit.tfar)) occluded = true;
@@ -932,10 +975,14 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
           const uint32_t before = hit.block;
           hit.block = 0xFFFFFFFFu;
           if (STATS) n_visits++;
-          switch (sc.leaf_kind) {
-            case 0: trace_object<0, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
-            case 1: trace_object<1, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
-            default: trace_object<2, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+          if (KIND >= 0) {
+            trace_object_body<(KIND >= 0 ? KIND : 0), STATS>(sc, lut, lo, ld, r0.w, hit, work);
+          } else {
+            switch (sc.leaf_kind) {
+              case 0: trace_object<0, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+              case 1: trace_object<1, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+              default: trace_object<2, STATS>(sc, lut, lo, ld, r0.w, hit, work); break;
+            }
           }
           if (hit.block != 0xFFFFFFFFu) hit_inst = geomID;
           else hit.block = before;
@@ -1123,6 +1170,8 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
         while (!(cur & ECB_REF_LEAF)) {
           float tNear[4];
           uint32_t child[4];
+          ECB_CHECK(cur < ts.n_nodes, 1);
+          ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
           const unsigned mask = top_node(ts.nodes, cur, tr, tNear, child);
           if (mask == 0) { popped = true; break; }
           int last = -1;
@@ -1136,6 +1185,7 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
         }
         if (popped || cur == ECB_REF_EMPTY) continue;
         const uint32_t first = (cur & ~ECB_REF_LEAF) >> 3, num = cur & 7u;
+        ECB_CHECK(first + num <= ts.n_blocks, 6);
         TriHit th;
         for (uint32_t k = 0; k < num && !occluded; k++)
           occluded = tri4v_intersect<true>(ts.blocks + first + k, org, dir, r0.w, tfar_in, th);
@@ -1150,9 +1200,10 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
       TriHit best;
       bool found = false;
       for (;;) {
-        const uint32_t leaf = next_block<false>(ts.nodes, tr, stack_ref, stack_dist, sp, tfar, work);
+        const uint32_t leaf = next_block<false>(ts.nodes, tr, stack_ref, stack_dist, sp, tfar, work, ts.n_nodes);
         if (leaf == ECB_REF_EMPTY) break;
         const uint32_t first = (leaf & ~ECB_REF_LEAF) >> 3, num = leaf & 7u;
+        ECB_CHECK(first + num <= ts.n_blocks, 6);
         for (uint32_t k = 0; k < num; k++) {
           TriHit th;
           if (tri4v_intersect<false>(ts.blocks + first + k, org, dir, r0.w, tfar, th)) {
@@ -1221,6 +1272,17 @@ __global__ void __launch_bounds__(256) ecb_bw_probe_kernel(const uint4* __restri
 }
 
 }  // namespace
+
+cudaError_t ecb_bounds_check_read(unsigned long long out[8], int* enabled) {
+#ifdef ECB_BOUNDS_CHECK
+  *enabled = 1;
+  return cudaMemcpyFromSymbol(out, g_ecb_check, 8 * sizeof(unsigned long long));
+#else
+  *enabled = 0;
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  return cudaSuccess;
+#endif
+}
 
 cudaError_t ecb_probe_read_bandwidth(size_t bytes, int passes, int device, double* gbs_out) {
   uint4* buf = nullptr;
@@ -1347,12 +1409,23 @@ cudaError_t ecb_launch_occluded(const EcbDeviceScene& sc, int device, const EcbL
   return cudaGetLastError();
 }
 
+// ECB200_INSTANCED_INLINE=0 forces the out-of-line object traversal (A/B measurements)
+static bool instanced_inline() {
+  static const bool on = [] { const char* e = getenv("ECB200_INSTANCED_INLINE"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream) {
   if (L.M == 0) return cudaSuccess;
   const int grid = grid_for(L.M, device);
-  if (any_hit) ecb_instanced_kernel<true, false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
-  else if (L.counters) ecb_instanced_kernel<false, true><<<grid, ECB_THREADS, 0, stream>>>(is, L);
-  else ecb_instanced_kernel<false, false><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  if (any_hit) ecb_instanced_kernel<true, false, -1><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  else if (L.counters) ecb_instanced_kernel<false, true, -1><<<grid, ECB_THREADS, 0, stream>>>(is, L);
+  else switch (instanced_inline() ? (int)is.uniform_leaf_kind : -1) {
+    case 0: ecb_instanced_kernel<false, false, 0><<<grid, ECB_THREADS, 0, stream>>>(is, L); break;
+    case 1: ecb_instanced_kernel<false, false, 1><<<grid, ECB_THREADS, 0, stream>>>(is, L); break;
+    case 2: ecb_instanced_kernel<false, false, 2><<<grid, ECB_THREADS, 0, stream>>>(is, L); break;
+    default: ecb_instanced_kernel<false, false, -1><<<grid, ECB_THREADS, 0, stream>>>(is, L); break;
+  }
   return cudaGetLastError();
 }
 

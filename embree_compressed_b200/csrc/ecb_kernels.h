@@ -66,6 +66,8 @@ cudaError_t ecb_launch_instanced(const EcbDeviceInstScene& is, int device, const
 // mixed scenes: the triangle accel is traversed first, in place (L.in == L.out), then the compressed accel on the same rays
 cudaError_t ecb_launch_triangles(const EcbDeviceTriScene& ts, int device, const EcbLaunch& L, bool any_hit, cudaStream_t stream);
 
+// -DECB_BOUNDS_CHECK builds: violation counters of the kernels' index checks (8 classes, see ecb_kernels.cu); enabled = 0 otherwise
+cudaError_t ecb_bounds_check_read(unsigned long long out[8], int* enabled);
 // measurement support: read bandwidth of a working set of `bytes` streamed `passes` times (GB/s, best of 5)
 cudaError_t ecb_probe_read_bandwidth(size_t bytes, int passes, int device, double* gbs_out);
 

@@ -67,8 +67,10 @@ struct QuadHit {
 template <int LEAF, bool STATS>
 __device__ __forceinline__ void quad_block(const EcbDeviceScene& sc, const float* __restrict__ lut, uint32_t* __restrict__ bstack,
                                            const unsigned qmask, const unsigned qbase, const unsigned c, const uint32_t block_index,
-                                           const float rorg[3], const float rdir[3], const float ray_tnear, QuadHit& hit, Work& work) {
+                                           const float rorg[3], const float rdir[3], const float ray_tnear, QuadHit& hit, Work& work,
+                                           const uint32_t blk_entries) {
   if (STATS && c == 0) work.blocks++;
+  ECB_CHECK(block_index < sc.n_blocks, 2);
   const uint8_t* blk = sc.blocks + (size_t)block_index * sc.block_stride;
   const float4* h4 = reinterpret_cast<const float4*>(blk);
   const float* hf = reinterpret_cast<const float*>(blk);
@@ -190,6 +192,7 @@ __device__ __forceinline__ void quad_block(const EcbDeviceScene& sc, const float
     sp--;
     __syncwarp(qmask);  // every lane has read the entry before a push below may overwrite it
     if (STATS && c == 0) work.cnodes++;
+    ECB_CHECK(curr < elems, 4);
     const uint32_t w = curr == 0 ? __float_as_uint(s8.w) : __ldg(node_words + (curr - 1));
     const unsigned xz = w & 0xff, xb = (w >> 8) & 0xff, yz = (w >> 16) & 0xff, yb = w >> 24;
     const float dimX = pb3 - pb0, dimY = pb4 - pb1, dimZ = pb5 - pb2;
@@ -223,6 +226,7 @@ __device__ __forceinline__ void quad_block(const EcbDeviceScene& sc, const float
     const unsigned next = curr * 4 + 1;
 
     if (next < elems) {  // children are inner nodes: push them, nearest on top
+      ECB_CHECK(sp + nh < (int)blk_entries, 3);
       if (chit) {
         uint32_t* o = bstack + 7 * (sp + 1 + (nh - 1 - rank));
         o[0] = next + c;
@@ -236,6 +240,7 @@ __device__ __forceinline__ void quad_block(const EcbDeviceScene& sc, const float
 
     // ---- children are leaves: evaluate the hit ones at once, then accept in pop order ----
     const unsigned idx = next + c - elems;
+    ECB_CHECK(idx < 3u * elems + 1u, 4);
     if (STATS && c == 0) work.cells += (uint32_t)nh;
     if (LEAF == 1) {
       // intersect_patch (compressed_help.h:135-229) without its dependence on the running tfar: kind 1 = accepted whenever
@@ -449,6 +454,7 @@ ecb_intersect_quad_kernel(EcbDeviceScene sc, EcbLaunch L, uint32_t top_entries, 
         const bool mine = ((need >> qbase) & 1u) && qrank < take;
         if (mine) {
           index = chunk_next + qrank;
+          ECB_CHECK(index < L.M, 7);
           const uint8_t* rp = L.in + index * L.in_stride;
           const float4 r0 = ld_ray4(rp);       // org.xyz, tnear
           const float4 r1 = ld_ray4(rp + 16);  // dir.xyz, time
@@ -526,6 +532,8 @@ ecb_intersect_quad_kernel(EcbDeviceScene sc, EcbLaunch L, uint32_t top_entries, 
           } else {
             // node test: lane c owns child c (intersectNodeRobust, node_intersector1.h:334-349)
             if (STATS && c == 0) work.top_nodes++;
+            ECB_CHECK(cur < sc.n_top, 1);
+            ECB_CHECK(sp + 3 <= (int)top_entries, 0);
             const float* nb = reinterpret_cast<const float*>(sc.top + cur);
             const unsigned ux_ = nu & 1u, uy_ = (nu >> 1) & 1u, uz_ = (nu >> 2) & 1u;
             const float pnx = __ldg(nb + 4 * ux_ + c), pfx = __ldg(nb + 4 * (1u - ux_) + c);
@@ -597,7 +605,7 @@ ecb_intersect_quad_kernel(EcbDeviceScene sc, EcbLaunch L, uint32_t top_entries, 
     const int n_trav = QUADS_WHERE(state == 1);
     if (n_pend >= ECB_Q_BLOCK_MIN || (n_pend > 0 && (n_trav == 0 && (exhausted || n_idle < ECB_Q_REFILL_MIN)))) {
       if (state == 2) {
-        quad_block<LEAF, STATS>(sc, lut, bstack, qmask, qbase, c, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+        quad_block<LEAF, STATS>(sc, lut, bstack, qmask, qbase, c, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work, blk_entries);
         tr_tfar = hit.tfar;  // bvh_intersector1.cpp:117
         pending = ECB_REF_EMPTY;
         state = 1;  // back to the top level: pop

@@ -247,6 +247,13 @@ ECB_API const char* ecbHostPathName(int caller_memory_is_pinned);
 ECB_API void ecbSetTraversalKernel(int mode);
 ECB_API int ecbGetTraversalKernel(void);
 
+/* Libraries built with -DECB_BOUNDS_CHECK (embree_compressed_b200.build.build_variant("check", ["ECB_BOUNDS_CHECK=1"]))
+ * check every index the kernels derive from scene data against the array it indexes and count violations in eight classes
+ * (top-level stack, top-level node, block, block stack, in-block offset, instance tables, triangle blocks, ray index).
+ * Returns 1 and the counters for such a build, 0 (and zeros) for the shipping build, -1 on a CUDA error.  compute-sanitizer
+ * is not available on the B200 pool; tests/test_bounds_check_gpu.py runs the golden cases on the checking build instead. */
+ECB_API int ecbBoundsCheckFailures(uint64_t counts_out[8]);
+
 /* Measurement support (not on the traversal path): read bandwidth in GB/s of a device buffer of `working_set_bytes`
  * streamed `passes` times with 128-bit L1-bypassing loads from every SM.  32 MB x 64 passes measures the L2 the scene
  * traffic of the traversal kernels is served from; 4 GB x 1 pass measures HBM.  The roofline's L2 denominator

@@ -88,6 +88,7 @@ cudaError_t ecb_launch_instanced(const EcbDeviceInstScene&, int, const EcbLaunch
   mock_enqueue(stream, [copy, any_hit] { any_hit ? any_pass(0, copy) : closest_pass(0, copy); });
   return cudaSuccess;
 }
+cudaError_t ecb_bounds_check_read(unsigned long long out[8], int* enabled) { *enabled = 0; for (int i = 0; i < 8; i++) out[i] = 0; return cudaSuccess; }
 int ecb_kernel_mode() { return 0; }
 void ecb_set_kernel_mode(int) {}
 cudaError_t ecb_probe_read_bandwidth(size_t, int, int, double* g) { *g = 0.0; return cudaErrorNoDevice; }
