@@ -5,7 +5,8 @@ t/u/v within 1e-5 relative.  "Relative" is taken against the magnitudes the quan
 distance is obtained from world coordinates of size ~|ray.org| (frustum entry distance + local distance), so
 |dt| <= 1e-5 * max(|t|, |ray.org|); u and v live in [0,1], so |du|,|dv| <= 1e-5.  (A tolerance relative to t alone is
 not met by the reference against ITSELF: its SSE4.2 and AVX2 code paths differ by more than that on 1 % of short
-bounce rays -- tests/test_reference_spread.py measures this.)  Two comparisons are made:
+bounce rays -- tests/test_oracle_cpu.py::test_reference_is_not_bit_stable_across_its_own_isas and the
+per-ray proof classes of tests/golden/parity_report.json measure this.)  Two comparisons are made:
 
   CUDA  vs port      : the kernels follow the port operation for operation => required BIT-EXACT on every ray.
   port/CUDA vs reference (compiled, AVX2): the reference uses rcpss/rsqrtss+Newton and compiler-contracted FMAs

@@ -18,7 +18,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream().cuda_stream
 scene = ecb.Scene.from_image_file(os.path.join(ROOT, "scenes", "_built", name + ".rimg")).upload(0)
-if name.startswith("bomberman_s6c3"):
+if name.startswith("bomberman"):   # the benchmark frame (bounce rays of the S6/C3 hit file: the same surface at any S)
     prim, bounce, _ = bench.config2_rays(rg, "leaf")
 else:
     cam = rg.CUBE_CAMERA
