@@ -57,6 +57,18 @@ class DeviceHits(C.Structure):
     _fields_ = [("geomID", C.c_void_p), ("hit", C.c_void_p), ("instID", C.c_void_p), ("Ng", C.c_void_p)]
 
 
+class RayNp(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in "org_x org_y org_z tnear dir_x dir_y dir_z time tfar mask id flags".split()]
+
+
+class HitNp(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in "Ng_x Ng_y Ng_z u v primID geomID instID".split()]
+
+
+class RayHitNp(C.Structure):
+    _fields_ = [("ray", RayNp), ("hit", HitNp)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("leaf_kind", C.c_uint32), ("subdiv_level", C.c_uint32), ("comp_level", C.c_uint32),
                 ("n_top_nodes", C.c_uint32), ("n_blocks", C.c_uint32), ("top_depth", C.c_uint32),
@@ -89,6 +101,8 @@ SYMBOLS = {
     "ecbIntersect16": (C.c_int, [_vp, _vp, _u32, _vp]),
     "ecbOccluded1": (C.c_int, [_vp, _u32, _vp]),
     "ecbOccluded1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
+    "ecbIntersectNp": (C.c_int, [_vp, _u32, C.POINTER(RayHitNp), _u64]),
+    "ecbOccludedNp": (C.c_int, [_vp, _u32, C.POINTER(RayNp), _u64]),
     "ecbOccludedExact1M": (C.c_int, [_vp, _u32, _vp, _u32, _sz]),
     "ecbOccludedExactDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
     "ecbIntersectDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
@@ -206,6 +220,35 @@ def build_blocks(leaf_kind, comp_level, grids, space, world, uv, geom_ids, prim_
     ok = np.zeros(n, np.uint32)
     _check(_lib().ecbBuildBlocks(C.byref(d), blocks.ctypes.data, bounds.ctypes.data, ok.ctypes.data), "ecbBuildBlocks")
     return blocks, bounds, ok
+
+
+def _addr(a):
+    return int(a) if isinstance(a, int) else a.ctypes.data
+
+
+def soa_from_rayhits(rayhits, alloc=None):
+    """RTCRayHitNp view of an (N, 20) RTCRayHit array: one contiguous array per field (copies).  alloc(nbytes) -> (uint8 view,
+    ptr) allocates each array (e.g. host_alloc for pinned memory); default numpy."""
+    names = Scene.RAY_FIELDS + Scene.HIT_FIELDS
+    out = {}
+    for k, f in enumerate(names):
+        col = np.ascontiguousarray(rayhits[:, k]) if k < rayhits.shape[1] else np.zeros(len(rayhits), np.float32)
+        if alloc is not None:
+            buf, _ = alloc(col.nbytes)
+            arr = buf.view(np.float32)
+            arr[:] = col
+            col = arr
+        out[f] = col.view(np.uint32) if f in ("mask", "id", "flags", "primID", "geomID", "instID") else col
+    return out
+
+
+def rayhits_from_soa(soa, n):
+    """Inverse of soa_from_rayhits: (n, 20) float32."""
+    names = Scene.RAY_FIELDS + Scene.HIT_FIELDS
+    r = np.zeros((n, 20), np.float32)
+    for k, f in enumerate(names):
+        r[:, k] = soa[f][:n].view(np.float32)
+    return r
 
 
 class Scene:
@@ -358,6 +401,25 @@ class Scene:
         """Opt-in exact shadow query (not the reference's conservative any-hit): enters the blocks."""
         p, n, stride = self._host_args(rays, 12)
         _check(_lib().ecbOccludedExact1M(self._h, inst_id, p, n, stride), "ecbOccludedExact1M")
+
+    RAY_FIELDS = "org_x org_y org_z tnear dir_x dir_y dir_z time tfar mask id flags".split()
+    HIT_FIELDS = "Ng_x Ng_y Ng_z u v primID geomID instID".split()
+
+    def intersectNp(self, soa, n, inst_id=INVALID_GEOMETRY_ID):
+        """ecbIntersectNp (rtcIntersectNp): soa maps field name -> 1-D float32 / uint32 array of at least n entries, or
+        -> address (int); the arrays are mutated in place."""
+        s = RayHitNp()
+        for f in self.RAY_FIELDS:
+            setattr(s.ray, f, _addr(soa[f]))
+        for f in self.HIT_FIELDS:
+            setattr(s.hit, f, _addr(soa[f]))
+        _check(_lib().ecbIntersectNp(self._h, inst_id, C.byref(s), n), "ecbIntersectNp")
+
+    def occludedNp(self, soa, n, inst_id=INVALID_GEOMETRY_ID):
+        s = RayNp()
+        for f in self.RAY_FIELDS:
+            setattr(s, f, _addr(soa[f]))
+        _check(_lib().ecbOccludedNp(self._h, inst_id, C.byref(s), n), "ecbOccludedNp")
 
     def intersect1(self, rayhit, inst_id=INVALID_GEOMETRY_ID):
         _check(_lib().ecbIntersect1(self._h, inst_id, rayhit.ctypes.data), "ecbIntersect1")

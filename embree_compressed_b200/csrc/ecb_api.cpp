@@ -904,6 +904,218 @@ ecbError run_host_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, 
   return ECB_SUCCESS;
 }
 
+// ---- SoA streams (rtcIntersectNp / rtcOccludedNp): the eight ray arrays the path reads are contiguous, so they go up by
+// DMA exactly as they are -- 32 bytes per ray, no packing, zero host work for pinned caller memory -- and the kernels read
+// them coalesced (EcbLaunch::soa).  Compact results come back and the host pool writes the hits into the caller's arrays.
+struct NpView {
+  float* in[8];  // org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, tfar
+  float *Ng_x, *Ng_y, *Ng_z, *u, *v;
+  uint32_t *primID, *geomID, *instID;
+};
+
+void scatter_results_np(const NpView& a, size_t first, const uint8_t* cmp, size_t n, size_t b, size_t e, bool any_hit, uint32_t instID, int extra) {
+  const uint32_t* geom = reinterpret_cast<const uint32_t*>(cmp);
+  const float* rec = reinterpret_cast<const float*>(cmp + ((4 * n + 15) & ~size_t(15)));
+  const uint8_t* tail_arrays = cmp + ((4 * n + 15) & ~size_t(15)) + 16 * n;
+  const uint32_t* inst = extra == kExtraInst ? reinterpret_cast<const uint32_t*>(tail_arrays) : nullptr;
+  const float* ng = extra == kExtraNg ? reinterpret_cast<const float*>(tail_arrays) : nullptr;
+  const float ninf = -__builtin_inff();
+  for (size_t i = b; i < e; i++) {
+    const uint32_t g = geom[i];
+    if (g == 0xFFFFFFFFu) continue;  // a miss writes nothing
+    const size_t j = first + i;
+    if (any_hit) {
+      a.in[7][j] = ninf;
+      continue;
+    }
+    const float* q = rec + 4 * i;
+    a.in[7][j] = q[0];
+    a.Ng_x[j] = ng ? ng[3 * i] : 1.f;  // dummy (1,0,0) for compressed hits (compressed.h:574)
+    a.Ng_y[j] = ng ? ng[3 * i + 1] : 0.f;
+    a.Ng_z[j] = ng ? ng[3 * i + 2] : 0.f;
+    a.u[j] = q[1];
+    a.v[j] = q[2];
+    memcpy(&a.primID[j], &q[3], 4);
+    a.geomID[j] = g;
+    a.instID[j] = inst ? inst[i] : instID;
+  }
+}
+
+ecbError run_host_np_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, const NpView& a, size_t first, uint64_t M) {
+  CU(cudaSetDevice(r->device));
+  StagingLease lease;
+  ecbError err = acquire_staging(r, M > kInlineRaysMax, &lease);
+  if (err != ECB_SUCCESS) return err;
+  Staging* st = lease.st;
+  const int nst = st->n_stages;
+  const size_t chunk = pipeline_chunk() < st->cap ? pipeline_chunk() : st->cap;
+  const uint64_t n_chunks = (M + chunk - 1) / chunk;
+  const bool inst = s->instanced, mixed = s->has_triangles(), any_hit = occluded;
+  const int extra = inst ? kExtraInst : mixed ? kExtraNg : kExtraNone;
+  bool pinned = true;
+  for (int k = 0; k < 8; k++) pinned = pinned && is_pinned(a.in[k] + first);
+  const bool use_pool = M > 8192;
+  auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
+  auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (inst ? 4 * n : 0) + (mixed ? 12 * n : 0)); };
+  {
+    std::lock_guard<std::mutex> wl(st->mutex);
+    st->worker_error = cudaSuccess;
+  }
+  struct Drain {  // no pool job may outlive the call: they read and write the caller's arrays
+    Staging* st;
+    ~Drain() {
+      std::unique_lock<std::mutex> wl(st->mutex);
+      st->cv.wait(wl, [&] {
+        for (int k = 0; k < st->n_stages; k++)
+          if (st->pending[k] || st->pack_pending[k]) return false;
+        return true;
+      });
+    }
+  } drain{st};
+  auto wait_zero = [&](int* counter) {
+    std::unique_lock<std::mutex> wl(st->mutex);
+    st->cv.wait(wl, [&] { return *counter == 0; });
+  };
+  auto finish = [&](uint64_t c) -> ecbError {  // results of chunk c have landed: scatter them (pool for long calls)
+    const int k = (int)(c % nst);
+    const size_t n = chunk_size(c);
+    CU(cudaEventSynchronize(st->done[k]));
+    const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
+    const size_t base = first + (size_t)(c * chunk);
+    if (!use_pool) {
+      scatter_results_np(a, base, cmp, n, 0, n, any_hit, instID, extra);
+      return ECB_SUCCESS;
+    }
+    {
+      std::lock_guard<std::mutex> wl(st->mutex);
+      st->pending[k] = kScatterParts;
+    }
+    const NpView view = a;
+    for (int part = 0; part < kScatterParts; part++) {
+      const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
+      HostPool::get().submit([=] {
+        scatter_results_np(view, base, cmp, n, b, e, any_hit, instID, extra);
+        std::lock_guard<std::mutex> wl(st->mutex);
+        if (--st->pending[k] == 0) st->cv.notify_all();
+      });
+    }
+    return ECB_SUCCESS;
+  };
+  for (uint64_t c = 0; c < n_chunks; c++) {
+    const int k = (int)(c % nst);
+    const size_t n = chunk_size(c);
+    const size_t base = first + (size_t)(c * chunk);
+    cudaStream_t q = st->stream[k];
+    if (c >= (uint64_t)nst) {  // the stage's previous chunk: results scattered before its buffers are reused
+      err = finish(c - nst);
+      if (err != ECB_SUCCESS) return err;
+    }
+    wait_zero(&st->pending[k]);
+    float* d_soa = static_cast<float*>(st->d_buf[k]);  // eight arrays of n floats
+    if (pinned) {
+      for (int f = 0; f < 8; f++) CU(cudaMemcpyAsync(d_soa + (size_t)f * n, a.in[f] + base, 4 * n, cudaMemcpyHostToDevice, q));
+    } else {  // pageable caller memory: the pool copies the eight slices into the pinned staging buffer, one DMA follows
+      float* h_soa = static_cast<float*>(st->h_pk[k]);
+      {
+        std::lock_guard<std::mutex> wl(st->mutex);
+        st->pack_pending[k] = 8;
+      }
+      for (int f = 0; f < 8; f++) {
+        const float* src = a.in[f] + base;
+        float* dst = h_soa + (size_t)f * n;
+        auto job = [=] {
+          memcpy(dst, src, 4 * n);
+          std::lock_guard<std::mutex> wl(st->mutex);
+          if (--st->pack_pending[k] == 0) st->cv.notify_all();
+        };
+        if (use_pool) HostPool::get().submit(job);
+        else job();
+      }
+      wait_zero(&st->pack_pending[k]);
+      CU(cudaMemcpyAsync(d_soa, h_soa, 32 * n, cudaMemcpyHostToDevice, q));
+    }
+    EcbLaunch L;
+    L.in = static_cast<const uint8_t*>(st->d_buf[k]);
+    L.in_stride = 0;
+    for (int f = 0; f < 8; f++) L.soa[f] = d_soa + (size_t)f * n;
+    L.out = nullptr;
+    L.out_stride = 0;
+    L.M = n;
+    L.instID = instID;
+    L.any_hit_exact = 0;
+    L.hit_geom = static_cast<uint32_t*>(st->d_cmp[k]);
+    L.hit_rec = reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15)));
+    L.hit_inst = inst ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
+    L.hit_ng = mixed ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
+    L.block_out = nullptr;
+    L.counters = nullptr;
+    L.queue = next_queue(r);
+    g_launches.fetch_add(1);
+    if (mixed) {
+      cudaError_t te = ecb_launch_triangles(r->tri_dev, r->device, L, occluded, q);
+      if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
+      L.keep_results = 1;
+      g_launches.fetch_add(1);
+    }
+    cudaError_t le = inst ? ecb_launch_instanced(r->inst_dev, r->device, L, occluded, q)
+                     : occluded ? ecb_launch_occluded(r->dev, r->device, L, q)
+                                : ecb_launch_intersect(r->dev, r->device, L, q);
+    if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+    CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], cmp_bytes(n), cudaMemcpyDeviceToHost, q));
+    CU(cudaEventRecord(st->done[k], q));
+  }
+  for (uint64_t c = n_chunks > (uint64_t)nst ? n_chunks - nst : 0; c < n_chunks; c++) {
+    err = finish(c);
+    if (err != ECB_SUCCESS) return err;
+  }
+  for (int k = 0; k < nst; k++) wait_zero(&st->pending[k]);
+  return ECB_SUCCESS;
+}
+
+ecbError run_host_np(ecbScene* s, bool occluded, uint32_t instID, const NpView& a, uint64_t M) {
+  if (!s) return ECB_ERROR_INVALID_ARGUMENT;
+  if (M == 0) return ECB_SUCCESS;
+  for (int k = 0; k < 8; k++)
+    if (!a.in[k]) return ECB_ERROR_INVALID_ARGUMENT;
+  if (!occluded && (!a.Ng_x || !a.Ng_y || !a.Ng_z || !a.u || !a.v || !a.primID || !a.geomID || !a.instID)) return ECB_ERROR_INVALID_ARGUMENT;
+  Residency* r0 = nullptr;
+  ecbError err = ensure_resident(s, -1, &r0);
+  if (err != ECB_SUCCESS) return err;
+  std::vector<Residency*> devs;
+  if (M >= kMultiDeviceRaysMin) {
+    std::lock_guard<std::mutex> lock(s->mutex);
+    devs = s->res;
+  }
+  if (devs.size() <= 1) return run_host_np_on(s, r0, occluded, instID, a, 0, M);
+  const size_t n = devs.size();
+  std::vector<ecbError> errs(n, ECB_SUCCESS);
+  std::vector<std::string> msgs(n);
+  std::vector<std::thread> threads;
+  auto part = [&](size_t i) {
+    const uint64_t per = ((M + n - 1) / n + 1023) & ~uint64_t(1023);
+    const uint64_t b = per * i < M ? per * i : M, e = per * (i + 1) < M ? per * (i + 1) : M;
+    if (e <= b) return;
+    errs[i] = run_host_np_on(s, devs[i], occluded, instID, a, (size_t)b, e - b);
+    if (errs[i] != ECB_SUCCESS) msgs[i] = g_last_error;
+  };
+  try {
+    for (size_t i = 1; i < n; i++) threads.emplace_back(part, i);
+  } catch (const std::exception& ex) {
+    for (auto& t : threads) t.join();
+    g_last_error = std::string("cannot start a device thread: ") + ex.what();
+    return ECB_ERROR_OUT_OF_MEMORY;
+  }
+  part(0);
+  for (auto& t : threads) t.join();
+  cudaSetDevice(r0->device);
+  for (size_t i = 0; i < n; i++)
+    if (errs[i] != ECB_SUCCESS) {
+      g_last_error = "device " + std::to_string(devs[i]->device) + ": " + msgs[i];
+      return errs[i];
+    }
+  return ECB_SUCCESS;
+}
+
 // Entry of every host-buffer call: argument checks, lazy upload, and -- for a scene resident on several devices
 // (ecbSceneUploadMulti) and a call long enough to pay for it -- the fan-out: the ray range is cut into one contiguous part
 // per device, each part runs the single-device pipeline on its own thread (its own staging context, stream set and PCIe
@@ -1484,6 +1696,27 @@ ecbError ecbIntersect1M(ecbScene* s, uint32_t instID, void* rayhit, uint32_t M, 
 ecbError ecbOccluded1(ecbScene* s, uint32_t instID, void* ray) { return run_host(s, true, instID, ray, 1, kRayBytes); }
 ecbError ecbOccluded1M(ecbScene* s, uint32_t instID, void* ray, uint32_t M, size_t byteStride) {
   return run_host(s, true, instID, ray, M, byteStride);
+}
+
+static NpView np_view(const ecbRayNp* ray, const ecbHitNp* hit) {
+  NpView a;
+  memset(&a, 0, sizeof(a));
+  float* const in[8] = {ray->org_x, ray->org_y, ray->org_z, ray->tnear, ray->dir_x, ray->dir_y, ray->dir_z, ray->tfar};
+  for (int k = 0; k < 8; k++) a.in[k] = in[k];
+  if (hit) {
+    a.Ng_x = hit->Ng_x; a.Ng_y = hit->Ng_y; a.Ng_z = hit->Ng_z;
+    a.u = hit->u; a.v = hit->v;
+    a.primID = hit->primID; a.geomID = hit->geomID; a.instID = hit->instID;
+  }
+  return a;
+}
+ecbError ecbIntersectNp(ecbScene* s, uint32_t instID, const ecbRayHitNp* rayhit, uint64_t N) {
+  if (!rayhit) return ECB_ERROR_INVALID_ARGUMENT;
+  return run_host_np(s, false, instID, np_view(&rayhit->ray, &rayhit->hit), N);
+}
+ecbError ecbOccludedNp(ecbScene* s, uint32_t instID, const ecbRayNp* ray, uint64_t N) {
+  if (!ray) return ECB_ERROR_INVALID_ARGUMENT;
+  return run_host_np(s, true, instID, np_view(ray, nullptr), N);
 }
 
 ecbError ecbOccludedExact1M(ecbScene* s, uint32_t instID, void* ray, uint32_t M, size_t byteStride) {

@@ -88,6 +88,20 @@ __device__ __forceinline__ void init_lut(float* lut) {
   }
 }
 
+// ray i of a launch: from the AoS records (RTCRayHit / RTCRay / packed) or from the eight SoA arrays (EcbLaunch::soa)
+__device__ __forceinline__ void load_ray(const EcbLaunch& L, uint64_t i, float4& r0, float4& r1, float& tfar) {
+  if (L.soa[0]) {
+    r0 = make_float4(__ldcg(L.soa[0] + i), __ldcg(L.soa[1] + i), __ldcg(L.soa[2] + i), __ldcg(L.soa[3] + i));
+    r1 = make_float4(__ldcg(L.soa[4] + i), __ldcg(L.soa[5] + i), __ldcg(L.soa[6] + i), 0.f);
+    tfar = __ldcg(L.soa[7] + i);
+  } else {
+    const uint8_t* rp = L.in + i * L.in_stride;
+    r0 = ld_ray4(rp);       // org.xyz, tnear
+    r1 = ld_ray4(rp + 16);  // dir.xyz, time
+    tfar = ld_ray1(rp + L.tfar_offset);  // 32, or 28 in packed records
+  }
+}
+
 struct TravRay {
   float org[3], rdn[3], rdf[3];
   float tnear, tfar;
@@ -695,10 +709,9 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
         if (mine) {
           index = chunk_next + rank;
           ECB_CHECK(index < L.M, 7);
-          const uint8_t* rp = L.in + index * L.in_stride;
-          const float4 r0 = ld_ray4(rp);       // org.xyz, tnear
-          const float4 r1 = ld_ray4(rp + 16);  // dir.xyz, time
-          const float tfar_in = ld_ray1(rp + L.tfar_offset);  // 32, or 28 in packed records
+          float4 r0, r1;
+          float tfar_in;
+          load_ray(L, index, r0, r1, tfar_in);
           if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
           if (L.hit_geom && !L.keep_results) L.hit_geom[index] = 0xFFFFFFFFu;
           if (!(r0.w > tfar_in) && sc.root != ECB_REF_EMPTY && !(L.any_hit_exact && tfar_in < 0.0f)) {  // tnear > tfar: inactive stream ray
@@ -884,10 +897,9 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceIns
   Work work = {0u, 0u, 0u, 0u};
   uint32_t n_visits = 0, n_hits = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = ld_ray4(rp);
-    const float4 r1 = ld_ray4(rp + 16);
-    const float tfar_in = ld_ray1(rp + L.tfar_offset);
+    float4 r0, r1;
+    float tfar_in;
+    load_ray(L, i, r0, r1, tfar_in);
     if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: miss / inactive / not occluded
     if (r0.w > tfar_in) continue;
     if (ANYHIT && tfar_in < 0.0f) continue;
@@ -1143,9 +1155,9 @@ template <bool ANYHIT>
 __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriScene ts, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = ld_ray4(rp);
-    const float4 r1 = ld_ray4(rp + 16);
-    const float tfar_in = ld_ray1(rp + L.tfar_offset);
+    float4 r0, r1;
+    float tfar_in;
+    load_ray(L, i, r0, r1, tfar_in);
     if (L.hit_geom) L.hit_geom[i] = 0xFFFFFFFFu;  // compact result mode: this pass runs first and owns the initial state
     if (r0.w > tfar_in) continue;               // inactive stream ray
     if (ANYHIT && tfar_in < 0.0f) continue;     // bvh_intersector1.cpp:133
@@ -1160,7 +1172,9 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
     stack_dist[0] = 0xff800000u;
     // compact result mode: tfar goes back into the input (staging) record, where the compressed-accel pass reads it
     uint8_t* op = L.hit_geom ? nullptr : L.out + i * L.out_stride;
-    float* tfar_out = L.hit_geom ? reinterpret_cast<float*>(const_cast<uint8_t*>(rp) + L.tfar_offset) : reinterpret_cast<float*>(op + 32);
+    float* tfar_out = !L.hit_geom ? reinterpret_cast<float*>(op + 32)
+                      : L.soa[0]  ? const_cast<float*>(L.soa[7]) + i
+                                  : reinterpret_cast<float*>(const_cast<uint8_t*>(rp) + L.tfar_offset);
     if (ANYHIT) {
       bool occluded = false;
       while (sp > 0 && !occluded) {
@@ -1231,10 +1245,9 @@ __global__ void __launch_bounds__(ECB_THREADS) ecb_triangle_kernel(EcbDeviceTriS
 
 __global__ void __launch_bounds__(ECB_THREADS) ecb_occluded_kernel(EcbDeviceScene sc, EcbLaunch L) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.M; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint8_t* rp = L.in + i * L.in_stride;
-    const float4 r0 = ld_ray4(rp);
-    const float4 r1 = ld_ray4(rp + 16);
-    const float tfar_in = ld_ray1(rp + L.tfar_offset);
+    float4 r0, r1;
+    float tfar_in;
+    load_ray(L, i, r0, r1, tfar_in);
     bool occluded = false;
     if (!(r0.w > tfar_in) && !(tfar_in < 0.0f)) {  // inactive stream ray; already occluded (bvh_intersector1.cpp:133)
       const float org[3] = {r0.x, r0.y, r0.z};

@@ -33,6 +33,10 @@ struct EcbLaunch {
   // points upload ({org.xyz, tnear}, {dir.xyz, tfar}: the fields this path reads; `time` is not one of them).  The compressed-accel
   // kernels (intersect / occluded) and the instancing kernel honour it.
   uint32_t tfar_offset = 32;
+  // SoA ray input (rtcIntersectNp / rtcOccludedNp, include/embree3/rtcore_ray.h:189-206): when soa[0] != NULL the closest-hit
+  // and any-hit kernels of the compressed accel read ray i from eight arrays instead of `in` -- org_x, org_y, org_z, tnear,
+  // dir_x, dir_y, dir_z, tfar -- i.e. consecutive lanes load consecutive words (fully coalesced)
+  const float* soa[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t* out;                   // RTCRayHit / RTCRay records that receive tfar + hit
   size_t out_stride;
   uint64_t M;

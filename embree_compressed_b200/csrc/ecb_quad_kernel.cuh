@@ -455,10 +455,9 @@ ecb_intersect_quad_kernel(EcbDeviceScene sc, EcbLaunch L, uint32_t top_entries, 
         if (mine) {
           index = chunk_next + qrank;
           ECB_CHECK(index < L.M, 7);
-          const uint8_t* rp = L.in + index * L.in_stride;
-          const float4 r0 = ld_ray4(rp);       // org.xyz, tnear
-          const float4 r1 = ld_ray4(rp + 16);  // dir.xyz, time
-          const float tfar_in = ld_ray1(rp + L.tfar_offset);
+          float4 r0, r1;
+          float tfar_in;
+          load_ray(L, index, r0, r1, tfar_in);
           if (c == 0) {
             if (L.block_out) L.block_out[index] = 0xFFFFFFFFu;
             if (L.hit_geom && !L.keep_results) L.hit_geom[index] = 0xFFFFFFFFu;

@@ -351,19 +351,6 @@ void stream_any_layout(ShimScene* s, RTCIntersectContext* ctx, size_t n, bool oc
   if (pinned) ecbHostFree(pinned);
 }
 
-uint32_t* np_word(const RTCRayNp& r, const RTCHitNp* h, size_t i, int f) {
-  float* const rf[9] = {r.org_x, r.org_y, r.org_z, r.tnear, r.dir_x, r.dir_y, r.dir_z, r.time, r.tfar};
-  if (f < 9) return reinterpret_cast<uint32_t*>(rf[f] + i);
-  if (f == 9) return r.mask + i;
-  if (f == 10) return r.id + i;
-  if (f == 11) return r.flags + i;
-  float* const hf[5] = {h->Ng_x, h->Ng_y, h->Ng_z, h->u, h->v};
-  if (f < 17) return reinterpret_cast<uint32_t*>(hf[f - 12] + i);
-  if (f == 17) return h->primID + i;
-  if (f == 18) return h->geomID + i;
-  return h->instID[0] + i;
-}
-
 }  // namespace
 
 extern "C" {
@@ -753,12 +740,15 @@ RTC_API void rtcOccludedNM(RTCScene scene, RTCIntersectContext* ctx, RTCRayN* ra
 RTC_API void rtcIntersectNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayHitNp* rayhit, unsigned N) {
   ShimScene* s = S(scene);
   if (!ready(s, "rtcIntersectNp", ctx)) return;
-  stream_any_layout(s, ctx, N, false, [&](size_t i, int f) { return np_word(rayhit->ray, &rayhit->hit, i, f); }, "rtcIntersectNp");
+  // RTCRayHitNp and ecbRayHitNp have the same layout (rtcore_ray.h:189-228): the arrays go to the device as they are
+  static_assert(sizeof(RTCRayHitNp) == sizeof(ecbRayHitNp), "RTCRayHitNp layout");
+  check(s, ecbIntersectNp(s->gpu, ctx_inst(ctx), reinterpret_cast<const ecbRayHitNp*>(rayhit), N), "rtcIntersectNp");
 }
 RTC_API void rtcOccludedNp(RTCScene scene, RTCIntersectContext* ctx, const RTCRayNp* ray, unsigned N) {
   ShimScene* s = S(scene);
   if (!ready(s, "rtcOccludedNp", ctx)) return;
-  stream_any_layout(s, ctx, N, true, [&](size_t i, int f) { return np_word(*ray, nullptr, i, f); }, "rtcOccludedNp");
+  static_assert(sizeof(RTCRayNp) == sizeof(ecbRayNp), "RTCRayNp layout");
+  check(s, ecbOccludedNp(s->gpu, ctx_inst(ctx), reinterpret_cast<const ecbRayNp*>(ray), N), "rtcOccludedNp");
 }
 
 RTC_API void* rtcAllocRays_b200(size_t bytes) {

@@ -179,6 +179,30 @@ ECB_API ecbError ecbIntersect16(const int* valid, ecbScene* scene, uint32_t inst
 ECB_API ecbError ecbOccluded1(ecbScene* scene, uint32_t instID, void* ray);
 ECB_API ecbError ecbOccluded1M(ecbScene* scene, uint32_t instID, void* ray, uint32_t M, size_t byteStride);
 
+/* SoA streams: ecbIntersectNp <- rtcIntersectNp, ecbOccludedNp <- rtcOccludedNp (include/embree3/rtcore_scene.h:118,142;
+ * kernels/common/rtcore.cpp:507-539,744-772).  The structs repeat RTCRayNp / RTCHitNp / RTCRayHitNp
+ * (include/embree3/rtcore_ray.h:189-228) field for field, so an embree3 caller's struct can be passed as it is.  The eight
+ * ray arrays this path reads (org, tnear, dir, tfar) are DMA'd as they are -- 32 bytes per ray, no host-side packing for pinned
+ * caller memory -- and read coalesced by the kernels; hits are written into the hit arrays and tfar, a miss writes nothing;
+ * time, mask, id and flags are never read. */
+typedef struct ecbRayNp {
+  float *org_x, *org_y, *org_z, *tnear;
+  float *dir_x, *dir_y, *dir_z, *time;
+  float* tfar;
+  uint32_t *mask, *id, *flags;
+} ecbRayNp;
+typedef struct ecbHitNp {
+  float *Ng_x, *Ng_y, *Ng_z;
+  float *u, *v;
+  uint32_t *primID, *geomID, *instID;
+} ecbHitNp;
+typedef struct ecbRayHitNp {
+  ecbRayNp ray;
+  ecbHitNp hit;
+} ecbRayHitNp;
+ECB_API ecbError ecbIntersectNp(ecbScene* scene, uint32_t instID, const ecbRayHitNp* rayhit, uint64_t N);
+ECB_API ecbError ecbOccludedNp(ecbScene* scene, uint32_t instID, const ecbRayNp* ray, uint64_t N);
+
 /* Opt-in EXACT shadow query (NOT the reference's semantics): the ray is occluded iff the closest-hit
  * traversal would accept a leaf hit inside [tnear, tfar] -- the blocks are entered instead of stopping at their world
  * boxes.  Same RTCRay records, tfar = -inf when occluded.  Not available on instancing scenes. */

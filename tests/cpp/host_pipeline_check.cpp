@@ -99,6 +99,41 @@ static void run_case(ecbScene* scene, bool mixed, bool pinned, size_t width, uin
         width, M, query, bad, first / width, first % width);
 }
 
+// SoA streams (ecbIntersectNp / ecbOccludedNp): the same records handed over as 20 (12) separate arrays must end up with
+// exactly the words the AoS call leaves
+static void run_case_np(ecbScene* scene, bool mixed, bool pinned, uint32_t M, bool occluded, uint64_t seed) {
+  const size_t width = occluded ? 12 : 20;
+  std::vector<float> want(width * (size_t)M);
+  uint64_t s = seed;
+  for (uint32_t i = 0; i < M; i++) make_record(want.data() + i * width, width, !occluded, s);
+  std::vector<Buffer*> arrays;
+  for (size_t f = 0; f < width; f++) {
+    arrays.push_back(new Buffer((size_t)M + 1, pinned));
+    for (uint32_t i = 0; i < M; i++) arrays[f]->p[i] = want[i * width + f];
+  }
+  const uint32_t instID = 0x777u + (uint32_t)seed;
+  for (uint32_t i = 0; i < M; i++) {
+    if (!occluded) expect_closest(want.data() + i * width, mixed, instID);
+    else expect_any(want.data() + i * width, mixed);
+  }
+  ecbRayHitNp np;
+  float** rf = &np.ray.org_x;
+  for (int f = 0; f < 9; f++) rf[f] = arrays[f]->p;
+  np.ray.mask = (uint32_t*)arrays[9]->p; np.ray.id = (uint32_t*)arrays[10]->p; np.ray.flags = (uint32_t*)arrays[11]->p;
+  if (!occluded) {
+    np.hit.Ng_x = arrays[12]->p; np.hit.Ng_y = arrays[13]->p; np.hit.Ng_z = arrays[14]->p; np.hit.u = arrays[15]->p; np.hit.v = arrays[16]->p;
+    np.hit.primID = (uint32_t*)arrays[17]->p; np.hit.geomID = (uint32_t*)arrays[18]->p; np.hit.instID = (uint32_t*)arrays[19]->p;
+  }
+  ecbError e = occluded ? ecbOccludedNp(scene, instID, &np.ray, M) : ecbIntersectNp(scene, instID, &np, M);
+  CHECK(e == ECB_SUCCESS, "Np call failed: %s %s", ecbErrorString(e), ecbLastErrorMessage());
+  size_t bad = 0;
+  for (size_t f = 0; f < width; f++)
+    for (uint32_t i = 0; i < M; i++)
+      if (memcmp(&arrays[f]->p[i], &want[i * width + f], 4) != 0) bad++;
+  CHECK(bad == 0, "Np mixed=%d pinned=%d M=%u occluded=%d: %zu words differ", (int)mixed, (int)pinned, M, (int)occluded, bad);
+  for (Buffer* b : arrays) delete b;
+}
+
 int main(int argc, char** argv) {
   if (argc < 3) { fprintf(stderr, "usage: host_pipeline_check plain.rimg mixed.rimg\n"); return 2; }
   ecbScene* scenes[2] = {nullptr, nullptr};
@@ -114,6 +149,12 @@ int main(int argc, char** argv) {
         run_case(scenes[mixed], mixed, pinned, 12, M, 1, seed++);
         run_case(scenes[mixed], mixed, pinned, 16, M, 1, seed++);
         if (M <= 50000u) run_case(scenes[mixed], mixed, pinned, 12, M, 2, seed++);
+      }
+  for (int mixed = 0; mixed < 2; mixed++)
+    for (int pinned = 0; pinned < 2; pinned++)
+      for (uint32_t M : {1u, 5000u, 16385u, 70001u}) {
+        run_case_np(scenes[mixed], mixed, pinned, M, false, seed++);
+        run_case_np(scenes[mixed], mixed, pinned, M, true, seed++);
       }
   // M = 0 and argument checks never reach the pipeline
   CHECK(ecbIntersect1M(scenes[0], 0, nullptr, 0, 80) == ECB_SUCCESS, "M = 0");
@@ -144,6 +185,7 @@ int main(int argc, char** argv) {
         run_case(scenes[0], false, pinned, 20, M, 0, seed++);
         run_case(scenes[1], true, pinned, 24, M, 0, seed++);
         run_case(scenes[0], false, pinned, 12, M, 1, seed++);
+        if (M >= 262144u) run_case_np(scenes[M & 1], (M & 1) != 0, pinned, M, false, seed++);
       }
     std::vector<std::thread> th;
     for (int t = 0; t < 3; t++)

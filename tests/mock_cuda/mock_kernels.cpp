@@ -9,8 +9,14 @@ namespace {
 
 struct RayIn { float o[3], tnear, d[3], tfar; };
 RayIn load_ray(const EcbLaunch& L, uint64_t i) {
-  const uint8_t* rp = L.in + i * L.in_stride;
   RayIn r;
+  if (L.soa[0]) {  // SoA ray input (ecbIntersectNp / ecbOccludedNp)
+    for (int k = 0; k < 3; k++) { r.o[k] = L.soa[k][i]; r.d[k] = L.soa[4 + k][i]; }
+    r.tnear = L.soa[3][i];
+    r.tfar = L.soa[7][i];
+    return r;
+  }
+  const uint8_t* rp = L.in + i * L.in_stride;
   memcpy(r.o, rp, 12);
   memcpy(&r.tnear, rp + 12, 4);
   memcpy(r.d, rp + 16, 12);
@@ -38,7 +44,10 @@ void closest_pass(int pass, const EcbLaunch L) {
       L.hit_geom[i] = h.geomID;
       if (L.hit_ng) memcpy(L.hit_ng + 3 * i, h.ng, 12);
       if (L.hit_inst) L.hit_inst[i] = h.geomID + 100u;
-      if (pass == 1) memcpy(const_cast<uint8_t*>(L.in) + i * L.in_stride + L.tfar_offset, &h.t, 4);  // handed to the next pass
+      if (pass == 1) {  // handed to the next pass
+        if (L.soa[0]) const_cast<float*>(L.soa[7])[i] = h.t;
+        else memcpy(const_cast<uint8_t*>(L.in) + i * L.in_stride + L.tfar_offset, &h.t, 4);
+      }
     } else {
       uint8_t* op = L.out + i * L.out_stride;
       memcpy(op + 32, &h.t, 4);
@@ -59,7 +68,10 @@ void any_pass(int pass, const EcbLaunch L) {
     if (L.hit_geom) {
       if (!L.keep_results) L.hit_geom[i] = occ ? 0u : 0xFFFFFFFFu;
       else if (occ) L.hit_geom[i] = 0u;
-      if (occ && pass == 1) memcpy(const_cast<uint8_t*>(L.in) + i * L.in_stride + L.tfar_offset, &kNegInf, 4);
+      if (occ && pass == 1) {
+        if (L.soa[0]) const_cast<float*>(L.soa[7])[i] = kNegInf;
+        else memcpy(const_cast<uint8_t*>(L.in) + i * L.in_stride + L.tfar_offset, &kNegInf, 4);
+      }
     } else if (occ) {
       memcpy(L.out + i * L.out_stride + 32, &kNegInf, 4);
     }

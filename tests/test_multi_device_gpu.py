@@ -152,3 +152,33 @@ def test_peer_copy_into_another_devices_buffer(ecb):
         torch.cuda.synchronize()
         assert (back.cpu().numpy().view(np.uint32) == a.cpu().numpy().view(np.uint32)[:, 18]).all()
         ecb.device_free(frame_geom)
+
+
+@pytest.mark.parametrize("name", ["cube_s5c3_leaf", "cube_s4c2_grid", "cubeplane_s4c2_leaf"])
+def test_soa_stream_equals_the_aos_stream(ecb, name):
+    """ecbIntersectNp / ecbOccludedNp (rtcIntersectNp / rtcOccludedNp): the arrays go to the device as they are and the kernels
+    read them coalesced; the results must be the bits of the AoS call -- pinned and pageable arrays, long and short streams."""
+    scene = _scene(ecb, name).upload(0)
+    rays = _rays(640)
+    for n in (len(rays), 20000, 7):
+        want = rays[:n].copy()
+        scene.intersect1M(want)
+        for pinned in (False, True):
+            ptrs = []
+
+            def alloc(nbytes):
+                buf, p = ecb.host_alloc(nbytes)
+                ptrs.append(p)
+                return buf, p
+            soa = ecb.soa_from_rayhits(rays[:n], alloc if pinned else None)
+            scene.intersectNp(soa, n)
+            got = ecb.rayhits_from_soa(soa, n)
+            assert (got.view(np.uint32) == want.view(np.uint32)).all(), "%s n=%d pinned=%s" % (name, n, pinned)
+            for p in ptrs:
+                ecb.host_free(p)
+        occ_want = rg.rays_only(rays[:n])
+        scene.occluded1M(occ_want)
+        soa = ecb.soa_from_rayhits(rays[:n])
+        scene.occludedNp(soa, n)
+        assert (soa["tfar"][:n].view(np.uint32) == occ_want[:, 8].view(np.uint32)).all()
+    scene.release()
