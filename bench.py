@@ -12,8 +12,9 @@ build() time by the compiled reference (scenes/_built/bench_c2_primary_hits.npz)
 
   value      device-timed: rays resident in HBM, CUDA events around the K steps on the launching stream.
              --gpus N > 1: ONE frame sharded over the N ranks by interleaved 64x64 tiles ("scaling": "strong"), scene replicated.
-  value_with_gather   the same with the hit records of every rank copied into rank 0's frame buffer over NVLink inside
-             the timed region (peer copies on a second stream, overlapped with the next pass).
+  value_with_gather   the same with the hit records of every rank landing in rank 0's frame buffer inside the timed region:
+             the traversal kernels store them straight into rank 0's arrays (IPC-mapped peer memory, NVLink stores) -- traversal
+             and gather are one kernel, 4 bytes per ray + 16 per hit cross the link while the kernel runs.
   e2e        the same step through the reference-facing call (ecbIntersect1M == rtcIntersect1M) with pinned HOST ray
              buffers, host<->device copies inside the timed region; at N > 1 ONE call in ONE process fans out over N GPUs.
   roofline   algorithmic bytes of one launch (instrumented kernel variant, SURVEY 8d formula with this repo's node / header
@@ -229,7 +230,7 @@ class FrameGather:
         self.sizes = [4 * n_total, 16 * n_total] + ([4 * n_total] if with_inst else [])
         self.ptrs = None       # device pointers of the frame arrays as seen from THIS rank
         self.owned = []
-        self.transport = "peer copies (CUDA IPC mapping of rank 0's frame arrays, cudaMemcpyAsync on a second stream)"
+        self.transport = "fused: the traversal kernels store their hit records straight into rank 0's frame arrays (CUDA IPC mapping, peer stores over NVLink)"
         self.fallback = False
         handles = [None]
         if rank == 0:
@@ -278,7 +279,10 @@ class FrameGather:
 
 
 class ShardedPass:
-    """One traversal pass over this rank's shard of a ray set: compact results, optional copy into rank 0's frame."""
+    """One traversal pass over this rank's shard of a ray set, compact results.  trace only: results into local arrays.
+    With gather: the traversal kernels store their hit records STRAIGHT INTO rank 0's frame arrays (IPC-mapped peer memory:
+    the stores travel over NVLink while the kernel runs -- traversal and gather are one kernel, nothing is copied afterwards).
+    Without IPC mapping: NCCL send / recv of the local arrays after the pass."""
 
     def __init__(self, ecb, torch, scene, rays, offset, gather, occluded=False, chunk=None, counts=None):
         self.ecb, self.torch, self.scene, self.rays, self.offset, self.gather = ecb, torch, scene, rays, offset, gather
@@ -288,55 +292,36 @@ class ShardedPass:
         self.occluded = occluded
         self.chunk = chunk or self.n
         dev = rays.device
-        inst = gather.with_inst if gather is not None else False
-        self.direct = gather is not None and gather.rank == 0   # rank 0's kernels write straight into the frame arrays
-        self.local = []
-        if not self.direct:
-            for _ in range(2):   # double buffered: step i+1 may trace while the copies of step i are still in flight
-                g = torch.empty(self.n, dtype=torch.int32, device=dev)
-                h = torch.empty((self.n, 4), dtype=torch.float32, device=dev)
-                i = torch.empty(self.n, dtype=torch.int32, device=dev) if inst else None
-                self.local.append((g, h, i))
-        self.copy_done = [None, None]
+        self.inst = gather.with_inst if gather is not None else False
+        self.local = (torch.empty(self.n, dtype=torch.int32, device=dev), torch.empty((self.n, 4), dtype=torch.float32, device=dev),
+                      torch.empty(self.n, dtype=torch.int32, device=dev) if self.inst else None)
 
-    def out_ptrs(self, buf, first):
-        if self.direct:
+    def out_ptrs(self, to_frame, first):
+        if to_frame:
             p = self.gather.ptrs
             o = self.offset + first
-            return p[0] + 4 * o, p[1] + 16 * o, (p[2] + 4 * o) if self.gather.with_inst else 0
-        g, h, i = self.local[buf]
+            return p[0] + 4 * o, p[1] + 16 * o, (p[2] + 4 * o) if self.inst else 0
+        g, h, i = self.local
         return g.data_ptr() + 4 * first, h.data_ptr() + 16 * first, (i.data_ptr() + 4 * first) if i is not None else 0
 
-    def launch(self, buf, stream, comm_stream=None):
-        """Enqueue the pass (and, with comm_stream, the gather copies chunk by chunk behind it).  Returns #kernel launches."""
-        torch, ecb = self.torch, self.ecb
-        if comm_stream is not None and self.copy_done[buf] is not None:
-            stream.wait_event(self.copy_done[buf])   # the previous use of these output buffers has been copied out
+    def launch(self, stream, gather=False):
+        """Enqueue the pass on `stream`.  Returns the number of kernel launches."""
+        to_frame = gather and self.gather is not None and self.gather.ptrs is not None and not self.gather.fallback
         launches = 0
         for first in range(0, self.n, self.chunk):
             m = min(self.chunk, self.n - first)
-            gp, hp, ip = self.out_ptrs(buf, first)
+            gp, hp, ip = self.out_ptrs(to_frame, first)
             rp = self.rays.data_ptr() + first * self.stride
             if self.occluded:
                 self.scene.occluded_device_compact(rp, m, gp, self.stride, stream.cuda_stream)
             else:
                 self.scene.intersect_device_compact(rp, m, gp, hp, self.stride, stream.cuda_stream, ip)
             launches += 1
-            if comm_stream is not None and not self.direct:
-                if not self.gather.fallback:
-                    ev = torch.cuda.Event()
-                    ev.record(stream)
-                    comm_stream.wait_event(ev)
-                    self._copy_out(buf, first, m, comm_stream)
-        if comm_stream is not None and self.gather.fallback:
-            self._fallback_exchange(buf, stream)
-        elif comm_stream is not None and not self.direct:
-            done = torch.cuda.Event()
-            done.record(comm_stream)
-            self.copy_done[buf] = done
+        if gather and self.gather is not None and self.gather.fallback:
+            self._fallback_exchange(stream)
         return launches
 
-    def _fallback_exchange(self, buf, stream):
+    def _fallback_exchange(self, stream):
         """No IPC mapping: every rank sends its records to rank 0 with NCCL point-to-point on the launching stream."""
         g, dist, torch = self.gather, self.gather.dist, self.torch
         with torch.cuda.stream(stream):
@@ -349,21 +334,10 @@ class ShardedPass:
                     if not self.occluded:
                         dist.recv(self._recv[r][1], src=r)
             else:
-                lg, lh, _ = self.local[buf]
+                lg, lh, _ = self.local
                 dist.send(lg, dst=0)
                 if not self.occluded:
                     dist.send(lh, dst=0)
-
-    def _copy_out(self, buf, first, m, comm_stream):
-        g = self.gather
-        o = self.offset + first
-        lg, lh, li = self.local[buf]
-        q = comm_stream.cuda_stream   # peer copies straight into rank 0's arrays
-        self.ecb.peer_copy_async(g.ptrs[0] + 4 * o, lg.data_ptr() + 4 * first, 4 * m, q)
-        if not self.occluded:
-            self.ecb.peer_copy_async(g.ptrs[1] + 16 * o, lh.data_ptr() + 16 * first, 16 * m, q)
-            if li is not None:
-                self.ecb.peer_copy_async(g.ptrs[2] + 4 * o, li.data_ptr() + 4 * first, 4 * m, q)
 
 
 def interleaved_tiles(width, height, rank, world, sh):
@@ -496,7 +470,6 @@ def reference_rate(make_ref, jobs, threads=None):
 def bench_configs(args, which, ecb, rg, rgd, sh, torch, dist, dev, rank, world, hbm, peak_src, l2, sm_count, sm_mhz):
     import __graft_entry__ as ge
     stream = torch.cuda.current_stream()
-    comm = torch.cuda.Stream() if world > 1 else None
     out = {}
     cpu = world == 1 and not args.no_cpu_baseline
 
@@ -582,15 +555,15 @@ def bench_configs(args, which, ecb, rg, rgd, sh, torch, dist, dev, rank, world, 
             rays = rgd.primary_rays(W8, H8, device=dev, pixel_index=idx_t, **ge.CONFIG4_CAMERA)
             gather = FrameGather(ecb, torch, dist, rank, world, W8 * H8, with_inst=True)
             p = ShardedPass(ecb, torch, sc, rays, offset, gather, chunk=1 << 22, counts=counts)
-            ms = timed_steps(torch, dist if world > 1 else None, dev, 3, 3, lambda i: p.launch(i % 2, stream), [stream])
+            ms = timed_steps(torch, dist if world > 1 else None, dev, 3, 3, lambda i: p.launch(stream), [stream])
             e = {"workload": "25 instances (13 x bomberman S6/C3, 12 x displaced cube S6/C3, compress.grid) with distinct affine transforms, "
                              "7680x4320 primary" + (", sharded over %d ranks by interleaved 64x64 tiles" % world if world > 1 else ""),
                  "rays": W8 * H8, "ms_per_frame": round(ms / 3, 4), "value": round(W8 * H8 * 3 / ms / 1e3, 1), "unit": UNIT,
                  "results": "compact hit records (geomID, {tfar,u,v,primID}, instID = 24 bytes per ray)"}
             if world > 1:
-                ms_g = timed_steps(torch, dist, dev, 3, 3, lambda i: p.launch(i % 2, stream, comm), [stream, comm])
+                ms_g = timed_steps(torch, dist, dev, 3, 3, lambda i: p.launch(stream, gather=True), [stream])
                 e["value_with_gather"] = round(W8 * H8 * 3 / ms_g / 1e3, 1)
-                e["gather"] = {"transport": gather.transport, "bytes_into_rank0_per_frame": int(24 * (W8 * H8 - counts[0])),
+                e["gather"] = {"transport": gather.transport, "bytes_into_rank0_per_frame_upper_bound": int(24 * (W8 * H8 - counts[0])), "bytes_per_ray": "4 (geomID, every ray) + 20 per hit",
                                "ms_per_frame_with_gather": round(ms_g / 3, 4)}
             if world == 1:
                 sample = rays[::8].contiguous()   # every 8th pixel of the frame
@@ -654,15 +627,15 @@ def bench_configs(args, which, ecb, rg, rgd, sh, torch, dist, dev, rank, world, 
             gather = FrameGather(ecb, torch, dist, rank, world, M5, with_inst=False)
             p = ShardedPass(ecb, torch, sc, rays, b, gather, chunk=1 << 22,
                             counts=[sh.index_range(M5, r, world)[1] - sh.index_range(M5, r, world)[0] for r in range(world)])
-            ms = timed_steps(torch, dist if world > 1 else None, dev, 3, 3, lambda i: p.launch(i % 2, stream), [stream])
+            ms = timed_steps(torch, dist if world > 1 else None, dev, 3, 3, lambda i: p.launch(stream), [stream])
             e = {"workload": "64 Mi (67 108 864) cosine-diffuse rays leaving the primary hit points of the 1920x1080 frame (%d samples per hit, "
                              "tutorial sampler) over bomberman S6/C3 compress.leaf%s" % ((M5 + n_hit - 1) // n_hit, ", sharded over %d ranks by index range" % world if world > 1 else ""),
                  "rays": M5, "ms_per_batch": round(ms / 3, 4), "value": round(M5 * 3 / ms / 1e3, 1), "unit": UNIT,
                  "results": "compact hit records (geomID, {tfar,u,v,primID} = 20 bytes per ray); the 5.4 GB ray batch is read-only and larger than L2"}
             if world > 1:
-                ms_g = timed_steps(torch, dist, dev, 3, 3, lambda i: p.launch(i % 2, stream, comm), [stream, comm])
+                ms_g = timed_steps(torch, dist, dev, 3, 3, lambda i: p.launch(stream, gather=True), [stream])
                 e["value_with_gather"] = round(M5 * 3 / ms_g / 1e3, 1)
-                e["gather"] = {"transport": gather.transport, "bytes_into_rank0_per_batch": int(20 * (M5 - (e_ - b if rank == 0 else M5 // world))),
+                e["gather"] = {"transport": gather.transport, "bytes_into_rank0_per_batch_upper_bound": int(20 * (M5 - (e_ - b if rank == 0 else M5 // world))), "bytes_per_ray": "4 (geomID, every ray) + 16 per hit",
                                "ms_per_batch_with_gather": round(ms_g / 3, 4)}
             if world == 1:
                 sample = rays[: 1 << 23]
@@ -765,19 +738,18 @@ def run_ours(args, rank, world):
         result_mode = "in place (the RTCRayHit records on the device are updated, a fresh copy of both buffers every step)"
     else:
         # ---- one frame sharded over the ranks: compact results; trace only, then trace + gather into rank 0's frame ----
-        comm = torch.cuda.Stream()
         g_prim = FrameGather(ecb, torch, dist, rank, world, n_prim, with_inst=False)
         g_bounce = FrameGather(ecb, torch, dist, rank, world, n_prim, with_inst=False)
         p_prim = ShardedPass(ecb, torch, scene, d_prim0, offset, g_prim, counts=counts)
         p_bounce = ShardedPass(ecb, torch, scene, d_bounce0, offset, g_bounce, counts=counts)
 
         def step(i):
-            p_prim.launch(i % 2, stream_t)
-            p_bounce.launch(i % 2, stream_t)
+            p_prim.launch(stream_t)
+            p_bounce.launch(stream_t)
 
         def step_gather(i):
-            p_prim.launch(i % 2, stream_t, comm)
-            p_bounce.launch(i % 2, stream_t, comm)
+            p_prim.launch(stream_t, gather=True)
+            p_bounce.launch(stream_t, gather=True)
 
         if rank == 0:
             sampler.start()
@@ -785,7 +757,7 @@ def run_ours(args, rank, world):
         ms_max = timed_steps(torch, dist, dev, K, W, step, [stream_t])
         launches = ecb.launch_count() - launches0 - 2 * W
         clocks = sampler.stop() if rank == 0 else None
-        ms_gather = timed_steps(torch, dist, dev, K, W, step_gather, [stream_t, comm])
+        ms_gather = timed_steps(torch, dist, dev, K, W, step_gather, [stream_t])
         value_with_gather = rays_per_step * K / (ms_gather * 1e-3) / 1e6
         # the gathered frame must hold exactly what a single device leaves (rank 0 re-traces the whole frame to check)
         if rank == 0 and not g_prim.fallback:
@@ -800,7 +772,7 @@ def run_ours(args, rank, world):
             assert bool((got_geom == want.view(torch.int32)[:, 18]).all()), "gathered geomIDs differ from the single-device frame"
             assert bool((got_hit[hitm].view(torch.int32) == want[hitm][:, [8, 15, 16, 17]].view(torch.int32)).all()), "gathered hit records differ"
             del full, want
-        gather_info = {"transport": g_prim.transport, "record_bytes": 20, "bytes_into_rank0_per_step": int(2 * 20 * (n_prim - counts[0])),
+        gather_info = {"transport": g_prim.transport, "bytes_per_ray": "4 (geomID, every ray) + 16 per hit", "bytes_into_rank0_per_step_upper_bound": int(2 * 20 * (n_prim - counts[0])),
                        "ms_per_step_with_gather": round(ms_gather / K, 4), "ms_per_step_trace_only": round(ms_max / K, 4),
                        "checked": "rank 0's gathered frame == a single-device trace of the whole frame, bit for bit"}
         dist.barrier()
@@ -903,7 +875,7 @@ def run_ours(args, rank, world):
                                             "reference_layout": round(info["reference_bytes_per_micro_triangle"], 3)},
                "results": result_mode, "bounce_rays": bounce_source,
                "parallelism": ("ONE %dx%d frame sharded over %d ranks by interleaved %dx%d tiles (tile t -> rank t mod N), scene replicated per GPU, "
-                               "no data-path collective; hit records copied into rank 0's frame buffer over NVLink" % (WIDTH, HEIGHT, world, TILE, TILE))
+                               "no data-path collective; with gather the kernels store their hit records straight into rank 0's frame buffer over NVLink" % (WIDTH, HEIGHT, world, TILE, TILE))
                if world > 1 else "single GPU (at --gpus N the frame is sharded by tiles: strong scaling)"}
         out["roofline"] = roofline
         if value_with_gather is not None:
