@@ -111,6 +111,7 @@ SYMBOLS = {
     "ecbOccludedDevice": (C.c_int, [_vp, _u32, _vp, _u64, _sz, _vp]),
     "ecbIntersectDeviceCompact": (C.c_int, [_vp, _u32, _vp, _u64, _sz, C.POINTER(DeviceHits), _vp]),
     "ecbOccludedDeviceCompact": (C.c_int, [_vp, _u32, _vp, _u64, _sz, C.POINTER(DeviceHits), _vp]),
+    "ecbIntersectDeviceSoA": (C.c_int, [_vp, _u32, C.POINTER(_vp), _u64, C.POINTER(DeviceHits), _vp]),
     "ecbDeviceAlloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ecbDeviceFree": (None, [_vp]),
     "ecbIpcExport": (C.c_int, [_vp, _vp]),
@@ -451,6 +452,12 @@ class Scene:
         are written to the given device arrays (+ instID[n] on instancing scenes)."""
         out = DeviceHits(geom_ptr, hit_ptr, inst_ptr or None, None)
         _check(_lib().ecbIntersectDeviceCompact(self._h, inst_id, ptr, n, stride, C.byref(out), stream), "ecbIntersectDeviceCompact")
+
+    def intersect_device_soa(self, soa_ptrs, n, geom_ptr, hit_ptr, stream=0, inst_id=INVALID_GEOMETRY_ID):
+        """ecbIntersectDeviceSoA: soa_ptrs = 8 device pointers (org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, tfar)."""
+        arr = (_vp * 8)(*soa_ptrs)
+        out = DeviceHits(geom_ptr, hit_ptr, None, None)
+        _check(_lib().ecbIntersectDeviceSoA(self._h, inst_id, arr, n, C.byref(out), stream), "ecbIntersectDeviceSoA")
 
     def occluded_device_compact(self, ptr, n, geom_ptr, stride=48, stream=0, inst_id=INVALID_GEOMETRY_ID):
         out = DeviceHits(geom_ptr, None, None, None)

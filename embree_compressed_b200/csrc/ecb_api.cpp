@@ -542,11 +542,70 @@ void scatter_results(uint8_t* rays, size_t stride, const uint8_t* cmp, size_t n,
   }
 }
 
+// ---- SoA streams (rtcIntersectNp / rtcOccludedNp): the eight arrays the path reads are contiguous, so the pack jobs of the
+// packed pipeline read eight sequential streams (32 bytes per ray instead of the 80-byte records of the AoS call) and the
+// scatter jobs write the hits into the caller's nine result arrays.  (A direct variant -- eight DMAs per chunk straight
+// from the caller's pinned arrays into SoA device buffers that the kernels read coalesced through EcbLaunch::soa -- needs
+// no host work on the way up but ran at half the rate: 336 vs 646 Mrays/s on the bench step, eight 256 KB copies per
+// 64 Ki-ray chunk keep the copy engine at a fraction of the link rate.  The kernels keep the SoA input mode for
+// device-resident arrays: ecbIntersectDeviceSoA.)
+struct NpView {
+  float* in[8];  // org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, tfar
+  float *Ng_x, *Ng_y, *Ng_z, *u, *v;
+  uint32_t *primID, *geomID, *instID;
+};
+
+void scatter_results_np(const NpView& a, size_t first, const uint8_t* cmp, size_t n, size_t b, size_t e, bool any_hit, uint32_t instID, int extra) {
+  const uint32_t* geom = reinterpret_cast<const uint32_t*>(cmp);
+  const float* rec = reinterpret_cast<const float*>(cmp + ((4 * n + 15) & ~size_t(15)));
+  const uint8_t* tail_arrays = cmp + ((4 * n + 15) & ~size_t(15)) + 16 * n;
+  const uint32_t* inst = extra == kExtraInst ? reinterpret_cast<const uint32_t*>(tail_arrays) : nullptr;
+  const float* ng = extra == kExtraNg ? reinterpret_cast<const float*>(tail_arrays) : nullptr;
+  const float ninf = -__builtin_inff();
+  for (size_t i = b; i < e; i++) {
+    const uint32_t g = geom[i];
+    if (g == 0xFFFFFFFFu) continue;  // a miss writes nothing
+    const size_t j = first + i;
+    if (any_hit) {
+      a.in[7][j] = ninf;
+      continue;
+    }
+    const float* q = rec + 4 * i;
+    a.in[7][j] = q[0];
+    a.Ng_x[j] = ng ? ng[3 * i] : 1.f;  // dummy (1,0,0) for compressed hits (compressed.h:574)
+    a.Ng_y[j] = ng ? ng[3 * i + 1] : 0.f;
+    a.Ng_z[j] = ng ? ng[3 * i + 2] : 0.f;
+    a.u[j] = q[1];
+    a.v[j] = q[2];
+    memcpy(&a.primID[j], &q[3], 4);
+    a.geomID[j] = g;
+    a.instID[j] = inst ? inst[i] : instID;
+  }
+}
+
+void pack_rays_np(const NpView& a, size_t first, uint8_t* dst, size_t b, size_t e) {
+  const float* ox = a.in[0] + first; const float* oy = a.in[1] + first; const float* oz = a.in[2] + first; const float* tn = a.in[3] + first;
+  const float* dx = a.in[4] + first; const float* dy = a.in[5] + first; const float* dz = a.in[6] + first; const float* tf = a.in[7] + first;
+  for (size_t i = b; i < e; i++) {
+    float w[8] = {ox[i], oy[i], oz[i], tn[i], dx[i], dy[i], dz[i], tf[i]};
+#if defined(__SSE2__)
+    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes), _mm_loadu_ps(w));
+    _mm_stream_ps(reinterpret_cast<float*>(dst + i * kPackedBytes + 16), _mm_loadu_ps(w + 4));
+#else
+    memcpy(dst + i * kPackedBytes, w, 32);
+#endif
+  }
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+}
+
 // Host-buffer entry points on a compressed-accel scene, packed strategy (see host_path()).  Per chunk of rays:
 //   pool: pack -> caller's thread: H2D (32 B/ray), kernel, D2H (20 B/ray, 4 for any-hit), event -> completion thread: waits
 //   for the event, hands the scatter jobs to the pool -> pool: scatter into the caller's records.
 // Pool threads never wait on the GPU; the caller's thread stays kPackAhead chunks ahead with the pack jobs.
-ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride) {
+ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride,
+                         const NpView* np = nullptr, size_t np_first = 0) {
   static const int kPackParts = env_int("ECB200_PACK_PARTS", kPackPartsDefault, 1, 64);
   static const int kPackAheadCfg = env_int("ECB200_PACK_AHEAD", kPackAheadDefault, 1, kStages - 2);
   const int nst = st->n_stages;
@@ -607,19 +666,23 @@ ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, 
     for (uint64_t c0 = 0; c0 < n_chunks; c0 += nst) {
       const uint64_t c1 = c0 + nst < n_chunks ? c0 + nst : n_chunks;
       for (uint64_t c = c0; c < c1; c++) {
-        pack_rays(base + c * chunk * stride, stride, static_cast<uint8_t*>(st->h_pk[c % nst]), 0, chunk_size(c));
+        if (np) pack_rays_np(*np, np_first + (size_t)(c * chunk), static_cast<uint8_t*>(st->h_pk[c % nst]), 0, chunk_size(c));
+        else pack_rays(base + c * chunk * stride, stride, static_cast<uint8_t*>(st->h_pk[c % nst]), 0, chunk_size(c));
         ecbError e = issue(c);
         if (e != ECB_SUCCESS) return e;
       }
       for (uint64_t c = c0; c < c1; c++) {
         CU(cudaStreamSynchronize(st->stream[c % nst]));
         const size_t n = chunk_size(c);
-        scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % nst]), n, 0, n, any_hit, instID, extra);
+        if (np) scatter_results_np(*np, np_first + (size_t)(c * chunk), static_cast<const uint8_t*>(st->h_cmp[c % nst]), n, 0, n, any_hit, instID, extra);
+        else scatter_results(base + c * chunk * stride, stride, static_cast<const uint8_t*>(st->h_cmp[c % nst]), n, 0, n, any_hit, instID, extra);
       }
     }
     return ECB_SUCCESS;
   }
 
+  const NpView np_copy = np ? *np : NpView{};  // the completion thread and the pool jobs outlive nothing, but capture by value anyway
+  const bool is_np = np != nullptr;
   {
     std::lock_guard<std::mutex> wl(st->mutex);
     st->worker_error = cudaSuccess;
@@ -650,8 +713,10 @@ ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, 
       if (ce == cudaSuccess) {
         for (int part = 0; part < kScatterParts; part++) {
           const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
+          const size_t np_base = np_first + (size_t)(c * chunk);
           HostPool::get().submit([=] {
-            scatter_results(src, stride, cmp, n, b, e, any_hit, instID, extra);
+            if (is_np) scatter_results_np(np_copy, np_base, cmp, n, b, e, any_hit, instID, extra);
+            else scatter_results(src, stride, cmp, n, b, e, any_hit, instID, extra);
             std::lock_guard<std::mutex> wl(st->mutex);
             if (--st->pending[k] == 0) st->cv.notify_all();
           });
@@ -707,8 +772,10 @@ ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, 
       uint8_t* dst = static_cast<uint8_t*>(st->h_pk[k]);
       for (int part = 0; part < parts; part++) {
         const size_t b = n * part / parts, e = n * (part + 1) / parts;
+        const size_t np_base = np_first + (size_t)(c * chunk);
         HostPool::get().submit([=] {
-          pack_rays(src, stride, dst, b, e);
+          if (is_np) pack_rays_np(np_copy, np_base, dst, b, e);
+          else pack_rays(src, stride, dst, b, e);
           std::lock_guard<std::mutex> wl(st->mutex);
           if (--st->pack_pending[k] == 0) st->cv.notify_all();
         });
@@ -904,172 +971,12 @@ ecbError run_host_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, 
   return ECB_SUCCESS;
 }
 
-// ---- SoA streams (rtcIntersectNp / rtcOccludedNp): the eight ray arrays the path reads are contiguous, so they go up by
-// DMA exactly as they are -- 32 bytes per ray, no packing, zero host work for pinned caller memory -- and the kernels read
-// them coalesced (EcbLaunch::soa).  Compact results come back and the host pool writes the hits into the caller's arrays.
-struct NpView {
-  float* in[8];  // org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z, tfar
-  float *Ng_x, *Ng_y, *Ng_z, *u, *v;
-  uint32_t *primID, *geomID, *instID;
-};
-
-void scatter_results_np(const NpView& a, size_t first, const uint8_t* cmp, size_t n, size_t b, size_t e, bool any_hit, uint32_t instID, int extra) {
-  const uint32_t* geom = reinterpret_cast<const uint32_t*>(cmp);
-  const float* rec = reinterpret_cast<const float*>(cmp + ((4 * n + 15) & ~size_t(15)));
-  const uint8_t* tail_arrays = cmp + ((4 * n + 15) & ~size_t(15)) + 16 * n;
-  const uint32_t* inst = extra == kExtraInst ? reinterpret_cast<const uint32_t*>(tail_arrays) : nullptr;
-  const float* ng = extra == kExtraNg ? reinterpret_cast<const float*>(tail_arrays) : nullptr;
-  const float ninf = -__builtin_inff();
-  for (size_t i = b; i < e; i++) {
-    const uint32_t g = geom[i];
-    if (g == 0xFFFFFFFFu) continue;  // a miss writes nothing
-    const size_t j = first + i;
-    if (any_hit) {
-      a.in[7][j] = ninf;
-      continue;
-    }
-    const float* q = rec + 4 * i;
-    a.in[7][j] = q[0];
-    a.Ng_x[j] = ng ? ng[3 * i] : 1.f;  // dummy (1,0,0) for compressed hits (compressed.h:574)
-    a.Ng_y[j] = ng ? ng[3 * i + 1] : 0.f;
-    a.Ng_z[j] = ng ? ng[3 * i + 2] : 0.f;
-    a.u[j] = q[1];
-    a.v[j] = q[2];
-    memcpy(&a.primID[j], &q[3], 4);
-    a.geomID[j] = g;
-    a.instID[j] = inst ? inst[i] : instID;
-  }
-}
-
 ecbError run_host_np_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, const NpView& a, size_t first, uint64_t M) {
   CU(cudaSetDevice(r->device));
   StagingLease lease;
   ecbError err = acquire_staging(r, M > kInlineRaysMax, &lease);
   if (err != ECB_SUCCESS) return err;
-  Staging* st = lease.st;
-  const int nst = st->n_stages;
-  const size_t chunk = pipeline_chunk() < st->cap ? pipeline_chunk() : st->cap;
-  const uint64_t n_chunks = (M + chunk - 1) / chunk;
-  const bool inst = s->instanced, mixed = s->has_triangles(), any_hit = occluded;
-  const int extra = inst ? kExtraInst : mixed ? kExtraNg : kExtraNone;
-  bool pinned = true;
-  for (int k = 0; k < 8; k++) pinned = pinned && is_pinned(a.in[k] + first);
-  const bool use_pool = M > 8192;
-  auto chunk_size = [&](uint64_t c) { return (size_t)((M - c * chunk) < chunk ? (M - c * chunk) : chunk); };
-  auto cmp_bytes = [&](size_t n) { return ((4 * n + 15) & ~size_t(15)) + (any_hit ? 0 : 16 * n + (inst ? 4 * n : 0) + (mixed ? 12 * n : 0)); };
-  {
-    std::lock_guard<std::mutex> wl(st->mutex);
-    st->worker_error = cudaSuccess;
-  }
-  struct Drain {  // no pool job may outlive the call: they read and write the caller's arrays
-    Staging* st;
-    ~Drain() {
-      std::unique_lock<std::mutex> wl(st->mutex);
-      st->cv.wait(wl, [&] {
-        for (int k = 0; k < st->n_stages; k++)
-          if (st->pending[k] || st->pack_pending[k]) return false;
-        return true;
-      });
-    }
-  } drain{st};
-  auto wait_zero = [&](int* counter) {
-    std::unique_lock<std::mutex> wl(st->mutex);
-    st->cv.wait(wl, [&] { return *counter == 0; });
-  };
-  auto finish = [&](uint64_t c) -> ecbError {  // results of chunk c have landed: scatter them (pool for long calls)
-    const int k = (int)(c % nst);
-    const size_t n = chunk_size(c);
-    CU(cudaEventSynchronize(st->done[k]));
-    const uint8_t* cmp = static_cast<const uint8_t*>(st->h_cmp[k]);
-    const size_t base = first + (size_t)(c * chunk);
-    if (!use_pool) {
-      scatter_results_np(a, base, cmp, n, 0, n, any_hit, instID, extra);
-      return ECB_SUCCESS;
-    }
-    {
-      std::lock_guard<std::mutex> wl(st->mutex);
-      st->pending[k] = kScatterParts;
-    }
-    const NpView view = a;
-    for (int part = 0; part < kScatterParts; part++) {
-      const size_t b = n * part / kScatterParts, e = n * (part + 1) / kScatterParts;
-      HostPool::get().submit([=] {
-        scatter_results_np(view, base, cmp, n, b, e, any_hit, instID, extra);
-        std::lock_guard<std::mutex> wl(st->mutex);
-        if (--st->pending[k] == 0) st->cv.notify_all();
-      });
-    }
-    return ECB_SUCCESS;
-  };
-  for (uint64_t c = 0; c < n_chunks; c++) {
-    const int k = (int)(c % nst);
-    const size_t n = chunk_size(c);
-    const size_t base = first + (size_t)(c * chunk);
-    cudaStream_t q = st->stream[k];
-    if (c >= (uint64_t)nst) {  // the stage's previous chunk: results scattered before its buffers are reused
-      err = finish(c - nst);
-      if (err != ECB_SUCCESS) return err;
-    }
-    wait_zero(&st->pending[k]);
-    float* d_soa = static_cast<float*>(st->d_buf[k]);  // eight arrays of n floats
-    if (pinned) {
-      for (int f = 0; f < 8; f++) CU(cudaMemcpyAsync(d_soa + (size_t)f * n, a.in[f] + base, 4 * n, cudaMemcpyHostToDevice, q));
-    } else {  // pageable caller memory: the pool copies the eight slices into the pinned staging buffer, one DMA follows
-      float* h_soa = static_cast<float*>(st->h_pk[k]);
-      {
-        std::lock_guard<std::mutex> wl(st->mutex);
-        st->pack_pending[k] = 8;
-      }
-      for (int f = 0; f < 8; f++) {
-        const float* src = a.in[f] + base;
-        float* dst = h_soa + (size_t)f * n;
-        auto job = [=] {
-          memcpy(dst, src, 4 * n);
-          std::lock_guard<std::mutex> wl(st->mutex);
-          if (--st->pack_pending[k] == 0) st->cv.notify_all();
-        };
-        if (use_pool) HostPool::get().submit(job);
-        else job();
-      }
-      wait_zero(&st->pack_pending[k]);
-      CU(cudaMemcpyAsync(d_soa, h_soa, 32 * n, cudaMemcpyHostToDevice, q));
-    }
-    EcbLaunch L;
-    L.in = static_cast<const uint8_t*>(st->d_buf[k]);
-    L.in_stride = 0;
-    for (int f = 0; f < 8; f++) L.soa[f] = d_soa + (size_t)f * n;
-    L.out = nullptr;
-    L.out_stride = 0;
-    L.M = n;
-    L.instID = instID;
-    L.any_hit_exact = 0;
-    L.hit_geom = static_cast<uint32_t*>(st->d_cmp[k]);
-    L.hit_rec = reinterpret_cast<float4*>(static_cast<uint8_t*>(st->d_cmp[k]) + ((4 * n + 15) & ~size_t(15)));
-    L.hit_inst = inst ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
-    L.hit_ng = mixed ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(L.hit_rec) + 16 * n) : nullptr;
-    L.block_out = nullptr;
-    L.counters = nullptr;
-    L.queue = next_queue(r);
-    g_launches.fetch_add(1);
-    if (mixed) {
-      cudaError_t te = ecb_launch_triangles(r->tri_dev, r->device, L, occluded, q);
-      if (te != cudaSuccess) return cuda_fail(te, "kernel launch");
-      L.keep_results = 1;
-      g_launches.fetch_add(1);
-    }
-    cudaError_t le = inst ? ecb_launch_instanced(r->inst_dev, r->device, L, occluded, q)
-                     : occluded ? ecb_launch_occluded(r->dev, r->device, L, q)
-                                : ecb_launch_intersect(r->dev, r->device, L, q);
-    if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
-    CU(cudaMemcpyAsync(st->h_cmp[k], st->d_cmp[k], cmp_bytes(n), cudaMemcpyDeviceToHost, q));
-    CU(cudaEventRecord(st->done[k], q));
-  }
-  for (uint64_t c = n_chunks > (uint64_t)nst ? n_chunks - nst : 0; c < n_chunks; c++) {
-    err = finish(c);
-    if (err != ECB_SUCCESS) return err;
-  }
-  for (int k = 0; k < nst; k++) wait_zero(&st->pending[k]);
-  return ECB_SUCCESS;
+  return run_host_packed(s, r, lease.st, occluded, false, instID, nullptr, M, 0, &a, first);
 }
 
 ecbError run_host_np(ecbScene* s, bool occluded, uint32_t instID, const NpView& a, uint64_t M) {
@@ -1774,6 +1681,38 @@ ecbError ecbOccludedDeviceCompact(ecbScene* s, uint32_t instID, const void* d_ra
                                   void* stream) {
   if (!out) return ECB_ERROR_INVALID_ARGUMENT;
   return run_device(s, true, instID, const_cast<void*>(d_ray), M, byteStride, nullptr, stream, nullptr, false, out);
+}
+
+ecbError ecbIntersectDeviceSoA(ecbScene* s, uint32_t instID, const float* const d_soa[8], uint64_t M, const ecbDeviceHits* out, void* stream) {
+  if (!s || !d_soa || !out || !out->geomID || !out->hit) return ECB_ERROR_INVALID_ARGUMENT;
+  for (int k = 0; k < 8; k++)
+    if (!d_soa[k] && M) return ECB_ERROR_INVALID_ARGUMENT;
+  if (s->instanced || s->has_triangles()) {
+    g_last_error = "SoA device input is available on plain compressed-accel scenes";
+    return ECB_ERROR_INVALID_OPERATION;
+  }
+  Residency* r = nullptr;
+  ecbError err = residency_for_pointer(s, d_soa[0], &r);
+  if (err != ECB_SUCCESS) return err;
+  if (M == 0) return ECB_SUCCESS;
+  EcbLaunch L;
+  L.in = nullptr;
+  L.in_stride = 0;
+  for (int k = 0; k < 8; k++) L.soa[k] = d_soa[k];
+  L.out = nullptr;
+  L.out_stride = 0;
+  L.M = M;
+  L.instID = instID;
+  L.any_hit_exact = 0;
+  L.hit_geom = out->geomID;
+  L.hit_rec = reinterpret_cast<float4*>(out->hit);
+  L.block_out = nullptr;
+  L.counters = nullptr;
+  L.queue = next_queue(r);
+  cudaError_t le = ecb_launch_intersect(r->dev, r->device, L, static_cast<cudaStream_t>(stream));
+  if (le != cudaSuccess) return cuda_fail(le, "kernel launch");
+  g_launches.fetch_add(1);
+  return ECB_SUCCESS;
 }
 
 ecbError ecbDeviceAlloc(void** d_ptr, size_t bytes) {

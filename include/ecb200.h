@@ -182,9 +182,9 @@ ECB_API ecbError ecbOccluded1M(ecbScene* scene, uint32_t instID, void* ray, uint
 /* SoA streams: ecbIntersectNp <- rtcIntersectNp, ecbOccludedNp <- rtcOccludedNp (include/embree3/rtcore_scene.h:118,142;
  * kernels/common/rtcore.cpp:507-539,744-772).  The structs repeat RTCRayNp / RTCHitNp / RTCRayHitNp
  * (include/embree3/rtcore_ray.h:189-228) field for field, so an embree3 caller's struct can be passed as it is.  The eight
- * ray arrays this path reads (org, tnear, dir, tfar) are DMA'd as they are -- 32 bytes per ray, no host-side packing for pinned
- * caller memory -- and read coalesced by the kernels; hits are written into the hit arrays and tfar, a miss writes nothing;
- * time, mask, id and flags are never read. */
+ * ray arrays this path reads (org, tnear, dir, tfar) are packed by the library's host pool from eight sequential streams (32
+ * bytes read per ray instead of the 80-byte records of the AoS call); hits are written into the hit arrays and tfar, a miss
+ * writes nothing; time, mask, id and flags are never read. */
 typedef struct ecbRayNp {
   float *org_x, *org_y, *org_z, *tnear;
   float *dir_x, *dir_y, *dir_z, *time;
@@ -236,6 +236,11 @@ ECB_API ecbError ecbIntersectDeviceCompact(ecbScene* scene, uint32_t instID, con
                                            const ecbDeviceHits* out, void* stream);
 ECB_API ecbError ecbOccludedDeviceCompact(ecbScene* scene, uint32_t instID, const void* d_ray, uint64_t M, size_t byteStride,
                                           const ecbDeviceHits* out, void* stream);
+
+/* SoA ray input on the device (north_star: "SoA ray data coalesced"): d_soa = org_x, org_y, org_z, tnear, dir_x, dir_y, dir_z,
+ * tfar -- eight device arrays of M floats; consecutive lanes load consecutive words.  Plain compressed-accel scenes. */
+ECB_API ecbError ecbIntersectDeviceSoA(ecbScene* scene, uint32_t instID, const float* const d_soa[8], uint64_t M,
+                                       const ecbDeviceHits* out, void* stream);
 
 /* ---- multi-GPU, one process per GPU: the hit-record gather over NVLink -------------------------------
  * The gathering rank allocates the frame's result arrays with ecbDeviceAlloc and publishes their 64-byte handles

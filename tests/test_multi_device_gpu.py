@@ -182,3 +182,31 @@ def test_soa_stream_equals_the_aos_stream(ecb, name):
         scene.occludedNp(soa, n)
         assert (soa["tfar"][:n].view(np.uint32) == occ_want[:, 8].view(np.uint32)).all()
     scene.release()
+
+
+def test_device_soa_input_equals_the_aos_records(ecb):
+    """ecbIntersectDeviceSoA: eight device arrays read coalesced -- same hits as the AoS records, with both traversal kernels."""
+    import torch
+    scene = _scene(ecb).upload(0)
+    rays = _rays()
+    n = len(rays)
+    dev = torch.device("cuda", 0)
+    a = torch.from_numpy(rays).to(dev)
+    scene.intersect_device(a.data_ptr(), n)
+    torch.cuda.synchronize()
+    want = a.cpu().numpy()
+    cols = [0, 1, 2, 3, 4, 5, 6, 8]
+    soa = [torch.from_numpy(np.ascontiguousarray(rays[:, c])).to(dev) for c in cols]
+    try:
+        for mode in ("lane", "quad"):
+            ecb.set_traversal_kernel(mode)
+            geom = torch.full((n,), 9, dtype=torch.int32, device=dev)
+            hit = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+            scene.intersect_device_soa([t.data_ptr() for t in soa], n, geom.data_ptr(), hit.data_ptr())
+            torch.cuda.synchronize()
+            g, h = geom.cpu().numpy().view(np.uint32), hit.cpu().numpy()
+            assert (g == want.view(np.uint32)[:, 18]).all(), mode
+            m = g != 0xFFFFFFFF
+            assert (h[m].view(np.uint32) == want[m][:, [8, 15, 16, 17]].view(np.uint32)).all(), mode
+    finally:
+        ecb.set_traversal_kernel(None)

@@ -32,3 +32,25 @@ for mem in ("pinned", "pageable"):
     t = float(np.mean(ts[2:]))
     print("devices=%d ecbIntersectNp %-8s %7.1f Mrays/s (%.3f ms per step, best %.3f)  bit-identical to ecbIntersect1M: %s"
           % (n_dev, mem, n_rays / t / 1e6, t * 1e3, min(ts[2:]) * 1e3, bool(ok)), flush=True)
+
+# device-timed: SoA arrays vs AoS records as kernel input (compact results both)
+import torch
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream().cuda_stream
+single = ecb.Scene.from_image_file(bench.scene_path("leaf")).upload(0)
+for what, rays in (("primary", prim), ("bounce", bounce)):
+    n = len(rays)
+    aos = torch.from_numpy(rays).to(dev)
+    soa = [torch.from_numpy(np.ascontiguousarray(rays[:, c])).to(dev) for c in (0, 1, 2, 3, 4, 5, 6, 8)]
+    geom = torch.empty(n, dtype=torch.int32, device=dev); hit = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    res = {}
+    for mode, fn in (("AoS 80-byte records", lambda: single.intersect_device_compact(aos.data_ptr(), n, geom.data_ptr(), hit.data_ptr(), 80, stream)),
+                     ("SoA arrays", lambda: single.intersect_device_soa([t.data_ptr() for t in soa], n, geom.data_ptr(), hit.data_ptr(), stream))):
+        ts = []
+        for _ in range(8):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        res[mode] = float(np.median(ts[2:]))
+    print("device input %-8s: %s" % (what, ", ".join("%s %.4f ms" % kv for kv in res.items())), flush=True)
