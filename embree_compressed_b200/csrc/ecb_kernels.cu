@@ -1343,7 +1343,10 @@ static int grid_for(uint64_t M, int device) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     g_grid_cache[device] = sms;
   }
-  const uint64_t need = (M + ECB_THREADS - 1) / ECB_THREADS;
+  // small launches: at least `rays_per_thread` rays per thread, so that a warp's refill keeps its lanes busy instead of 8 CTAs
+  // per SM sharing a few chunks each (ECB200_RAYS_PER_THREAD, experiments)
+  static const uint64_t rays_per_thread = [] { const char* e = getenv("ECB200_RAYS_PER_THREAD"); const int v = e ? atoi(e) : 1; return (uint64_t)(v < 1 ? 1 : v); }();
+  const uint64_t need = (M + ECB_THREADS * rays_per_thread - 1) / (ECB_THREADS * rays_per_thread);
   const uint64_t cap = (uint64_t)g_grid_cache[device] * ECB_BLOCKS_PER_SM;
   return (int)(need < cap ? (need ? need : 1) : cap);
 }
