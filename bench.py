@@ -809,6 +809,9 @@ def run_ours(args, rank, world):
     # ---- ONE call per pass on a scene resident on all N devices (ecbSceneUploadMulti); the other ranks stay off their GPUs.
     if rank == 0:
         if world > 1:
+            # this leg is ONE process driving all N devices: give its host pool the whole host (the library's default divides
+            # the cores by LOCAL_WORLD_SIZE for one-process-per-GPU use; the other ranks are parked behind a gloo barrier)
+            os.environ.setdefault("ECB200_HOST_THREADS", str(max(2, min(24, (os.cpu_count() or 4) * 3 // 4))))
             multi = ecb.Scene.from_image_file(path).upload_multi(list(range(world)))
         else:
             multi = scene
@@ -852,6 +855,7 @@ def run_ours(args, rank, world):
                "call": "ecbIntersect1M (rtcIntersect1M drop-in), %s host RTCRayHit arrays (%d bytes), results written in place%s; %s"
                        % (args.e2e_memory, int(prim.nbytes + bounce.nbytes),
                           "; ONE call per pass in ONE process, the library cuts the ray range into one part per device (no gather step)" if world > 1 else "", how),
+               "host_pool_threads": os.environ.get("ECB200_HOST_THREADS", "library default"),
                "checked": "bit-identical to the device-buffer path"}
         if hp_ptr is not None:
             ecb.host_free(hp_ptr)
