@@ -259,7 +259,11 @@ struct Work {
 // ---------------------------------------------------------------------------------------------------------------
 // block traversal (CompressedBVHIntersector1::intersect)
 // ---------------------------------------------------------------------------------------------------------------
-template <int LEAF, bool STATS>
+// INLINE_LEAVES: the leaves below a lowest-level quadtree node are tested right at that node, in pop order, instead of being
+// pushed and popped one by one.  Same results bit for bit; it pays on deep blocks with many cell tests per entry (displaced
+// cube S6/C4: 15.5 node decodes + 9.1 cells per ray, 0.65 -> 0.58 ms) and costs on shallow ones (bomberman S6/C3: 2.6 + 0.9,
+// 0.389 -> 0.409 ms), so the launcher picks it for C >= 4 (profiles/r2r_leaves_inline_ab.txt).
+template <int LEAF, bool STATS, bool INLINE_LEAVES = false>
 __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const float* __restrict__ lut, uint32_t block_index,
                                                 const float rorg[3], const float rdir[3], float ray_tnear, Hit& hit, Work& work) {
   if (STATS) work.blocks++;
@@ -327,7 +331,208 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
 
   TravRay tr;
   travray_init(tr, org, dir, 0.f, tfar);
+  const uint32_t elems = sc.elems;
+  const uint32_t* node_words = reinterpret_cast<const uint32_t*>(blk + ECB_BLOCK_NODES_OFFSET);
 
+  if constexpr (INLINE_LEAVES) {
+  // ---- quadtree.  The stack holds INNER nodes only (3(C-1)+1 entries of {node, box}): the leaves below a lowest-level
+  // node are not pushed and popped one by one but tested right there, in the order the reference pops them (nearest box
+  // first, lower child index on ties, compressed.h:668-749) -- nothing else can come between them on the reference's stack.
+  // (A lane-interleaved shared-memory stack was measured too: slower on every scene, profiles/r2r_leaves_inline_ab.txt.)
+  uint32_t lstack[7 * (3 * (ECB_MAX_C - 1) + 1)];
+#define BST(e, w) lstack[7 * (e) + (w)]
+  int sp = 0;
+  BST(0, 0) = 0u;
+  BST(0, 1) = __float_as_uint(-1.f); BST(0, 2) = __float_as_uint(-1.f); BST(0, 3) = __float_as_uint(box[0]);
+  BST(0, 4) = __float_as_uint(1.f);  BST(0, 5) = __float_as_uint(1.f);  BST(0, 6) = __float_as_uint(box[1]);
+
+  while (sp >= 0) {
+    const unsigned curr = BST(sp, 0);
+    float pBox[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pBox[k] = __uint_as_float(BST(sp, 1 + k));
+    sp--;
+
+    // inner node: decode (Node::getNode), test 4 children
+    const unsigned next = curr * 4 + 1;
+    if (STATS) work.cnodes++;
+    ECB_CHECK(curr < elems, 4);
+    const uint32_t w = curr == 0 ? root_word : __ldg(node_words + (curr - 1));
+    const unsigned xz = w & 0xff, xb = (w >> 8) & 0xff, yz = (w >> 16) & 0xff, yb = w >> 24;
+    const float dimX = pBox[3] - pBox[0], dimY = pBox[4] - pBox[1], dimZ = pBox[5] - pBox[2];
+    const float lx02 = lut[(xz & 0xe0) >> 5] * dimX + pBox[0];
+    const float lx13 = lut[8 + ((xz & 0x1c) >> 2)] * dimX + pBox[0];
+    const float ux02 = lut[16 + ((xb & 0xe0) >> 5)] * dimX + pBox[0];
+    const float ux13 = lut[24 + ((xb & 0x1c) >> 2)] * dimX + pBox[0];
+    const float ly01 = lut[(yz & 0xe0) >> 5] * dimY + pBox[1];
+    const float ly23 = lut[8 + ((yz & 0x1c) >> 2)] * dimY + pBox[1];
+    const float uy01 = lut[16 + ((yb & 0xe0) >> 5)] * dimY + pBox[1];
+    const float uy23 = lut[24 + ((yb & 0x1c) >> 2)] * dimY + pBox[1];
+    const float lz = (0.25f * (float)(xz & 3)) * dimZ + pBox[2];
+    const float uz = (1.f - 0.25f * (float)(yz & 3)) * dimZ + pBox[2];
+
+    // the four children share their planes: x ranges A (children 0,2) / B (1,3), y ranges A (0,1) / B (2,3), one z range
+    // (compressed_node.h:488-510) -> 5 near + 5 far plane distances instead of 24; same operands, same floats
+    const float tnxA = ((tr.nu[0] ? ux02 : lx02) - tr.org[0]) * tr.rdn[0], tfxA = ((tr.nu[0] ? lx02 : ux02) - tr.org[0]) * tr.rdf[0];
+    const float tnxB = ((tr.nu[0] ? ux13 : lx13) - tr.org[0]) * tr.rdn[0], tfxB = ((tr.nu[0] ? lx13 : ux13) - tr.org[0]) * tr.rdf[0];
+    const float tnyA = ((tr.nu[1] ? uy01 : ly01) - tr.org[1]) * tr.rdn[1], tfyA = ((tr.nu[1] ? ly01 : uy01) - tr.org[1]) * tr.rdf[1];
+    const float tnyB = ((tr.nu[1] ? uy23 : ly23) - tr.org[1]) * tr.rdn[1], tfyB = ((tr.nu[1] ? ly23 : uy23) - tr.org[1]) * tr.rdf[1];
+    const float tnz = ((tr.nu[2] ? uz : lz) - tr.org[2]) * tr.rdn[2], tfz = ((tr.nu[2] ? lz : uz) - tr.org[2]) * tr.rdf[2];
+    const float tnzn = sse_max(tnz, tr.tnear), tfzf = sse_min(tfz, tr.tfar);
+    float tNear[4], tFar[4];
+    tNear[0] = sse_max(sse_max(tnxA, tnyA), tnzn); tFar[0] = sse_min(sse_min(tfxA, tfyA), tfzf);
+    tNear[1] = sse_max(sse_max(tnxB, tnyA), tnzn); tFar[1] = sse_min(sse_min(tfxB, tfyA), tfzf);
+    tNear[2] = sse_max(sse_max(tnxA, tnyB), tnzn); tFar[2] = sse_min(sse_min(tfxA, tfyB), tfzf);
+    tNear[3] = sse_max(sse_max(tnxB, tnyB), tnzn); tFar[3] = sse_min(sse_min(tfxB, tfyB), tfzf);
+    const unsigned mask = (tNear[0] <= tFar[0] ? 1u : 0u) | (tNear[1] <= tFar[1] ? 2u : 0u) | (tNear[2] <= tFar[2] ? 4u : 0u) |
+                          (tNear[3] <= tFar[3] ? 8u : 0u);
+    if (mask == 0) continue;
+
+    // below[r] = number of other hit children popped AFTER r (farther, or equal and higher index)   (compressed.h:668-749)
+    const int n = __popc(mask);
+    int below[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      below[r] = -1;
+      if (!(mask & (1u << r))) continue;
+      int cnt = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (q == r || !(mask & (1u << q))) continue;
+        const bool r_first = (q > r) ? (tNear[r] <= tNear[q]) : (tNear[r] < tNear[q]);
+        cnt += r_first ? 1 : 0;
+      }
+      below[r] = cnt;
+    }
+
+    if (next < elems) {  // children are inner nodes: push them, nearest on top
+      ECB_CHECK(sp + n < 3 * (int)sc.comp_level - 2, 3);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (below[r] < 0) continue;
+        const int pos = sp + 1 + below[r];
+        BST(pos, 0) = next + r;
+        BST(pos, 1) = __float_as_uint((r & 1) ? lx13 : lx02);
+        BST(pos, 2) = __float_as_uint((r & 2) ? ly23 : ly01);
+        BST(pos, 3) = __float_as_uint(lz);
+        BST(pos, 4) = __float_as_uint((r & 1) ? ux13 : ux02);
+        BST(pos, 5) = __float_as_uint((r & 2) ? uy23 : uy01);
+        BST(pos, 6) = __float_as_uint(uz);
+      }
+      sp += n;
+      continue;
+    }
+
+    // ---- children are leaves: test the hit ones in pop order (the one with the most children "below" it first) ----
+    for (int k = n - 1; k >= 0; k--) {
+      const int r = below[0] == k ? 0 : below[1] == k ? 1 : below[2] == k ? 2 : 3;
+      const unsigned idx = next + (unsigned)r - elems;
+      ECB_CHECK(idx < 3u * elems + 1u, 4);
+      if (STATS) work.cells++;
+      const float bl0 = (r & 1) ? lx13 : lx02, bl1 = (r & 2) ? ly23 : ly01, bu0 = (r & 1) ? ux13 : ux02, bu1 = (r & 2) ? uy23 : uy01;
+      const float box_near = r == 0 ? tNear[0] : r == 1 ? tNear[1] : r == 2 ? tNear[2] : tNear[3];
+      if (LEAF == 1) {
+        if (box_near >= tfar) continue;
+        const float box_far = r == 0 ? tFar[0] : r == 1 ? tFar[1] : r == 2 ? tFar[2] : tFar[3];
+        const float lbox[6] = {bl0, bl1, lz, bu0, bu1, uz};
+        const float cdimZ = uz - lz;
+        const float range = (1.f + 2.f * extent) * cdimZ;
+        const float dz = 0.0625f * range;
+        const float offset = lz - cdimZ * extent;
+        const float rcpF = 0.0625f * range;
+        const uint32_t zz = __ldg(reinterpret_cast<const unsigned short*>(blk + sc.leaf_offset) + idx);
+        const unsigned z12 = zz & 0xff, z34 = zz >> 8;
+        const float z1 = offset + rcpF * (float)((z12 & 0xf0) >> 4);
+        const float z2 = offset + rcpF * (float)(z12 & 0x0f);
+        const float z3 = offset + rcpF * (float)((z34 & 0xf0) >> 4);
+        const float z4 = offset + rcpF * (float)(z34 & 0x0f);
+        float u, v, t = tfar;
+        if (intersect_patch(idx, sc.rcp_edges, dz, box_near, box_far, z1, z2, z3, z4, lbox, org, dir, u, v, t)) {
+          float tw;
+          if (special) {
+            float ip[9], q[3], p[3];
+            inverse3(proj, ip);
+#pragma unroll
+            for (int c = 0; c < 3; c++) q[c] = org[c] + dir[c] * t;
+            project3(ip, q, p);
+            const float ex = p[0] - lOrg[0], ey = p[1] - lOrg[1], ez = p[2] - lOrg[2];
+            tw = sqrtf((ex * ex + ey * ey) + (ez * ez + 0.f));
+          } else {
+            tw = t / zFactor + near;
+          }
+          hit.u = uv0x + u * uvEx;
+          hit.v = uv0y + v * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+          tfar = t;
+          hit.tfar = tw;
+        }
+      } else if (LEAF == 0) {
+        const unsigned x = compact1by1(idx), y = compact1by1(idx >> 1);
+        const float* grid = reinterpret_cast<const float*>(blk + sc.leaf_offset);
+        const unsigned g0 = y * sc.grid_width + x, g2 = g0 + sc.grid_width;
+        float V[4][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          V[0][c] = __ldg(grid + 3 * g0 + c);
+          V[1][c] = __ldg(grid + 3 * g0 + 3 + c);
+          V[2][c] = __ldg(grid + 3 * g2 + c);
+          V[3][c] = __ldg(grid + 3 * g2 + 3 + c);
+        }
+        float tf = hit.tfar, uu = 0.f, vv = 0.f;
+        const bool hit1 = intersect_triangle(V[0], V[1], V[2], rorg, rdir, ray_tnear, tf, uu, vv);
+        const bool hit2 = intersect_triangle(V[3], V[2], V[1], rorg, rdir, ray_tnear, tf, uu, vv);
+        if (hit1 || hit2) {
+          float lu, lv;
+          if (hit2) {
+            lu = ((float)x + (1.f - uu)) * sc.rcp_edges;
+            lv = ((float)y + (1.f - vv)) * sc.rcp_edges;
+          } else {
+            lu = ((float)x + uu) * sc.rcp_edges;
+            lv = ((float)y + vv) * sc.rcp_edges;
+          }
+          hit.tfar = tf;
+          hit.u = uv0x + lu * uvEx;
+          hit.v = uv0y + lv * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+        }
+      } else {
+        const float is = box_near;
+        if (is <= tfar) {
+          const float mx = (float)compact1by1(idx), my = (float)compact1by1(idx >> 1);
+          const float x = (((org[0] + dir[0] * is) - bl0) / (bu0 - bl0) + mx) * sc.rcp_edges;
+          const float y = (((org[1] + dir[1] * is) - bl1) / (bu1 - bl1) + my) * sc.rcp_edges;
+          float tw;
+          if (special) {
+            float ip[9], q[3], p[3];
+            inverse3(proj, ip);
+#pragma unroll
+            for (int c = 0; c < 3; c++) q[c] = org[c] + dir[c] * is;
+            project3(ip, q, p);
+            const float ex = p[0] - lOrg[0], ey = p[1] - lOrg[1], ez = p[2] - lOrg[2];
+            tw = sqrtf((ex * ex + ey * ey) + (ez * ez + 0.f));
+          } else {
+            tw = is / zFactor + near;
+          }
+          hit.u = uv0x + x * uvEx;
+          hit.v = uv0y + y * uvEy;
+          hit.geomID = geomID;
+          hit.primID = primID;
+          hit.block = block_index;
+          tfar = is;
+          hit.tfar = tw;
+        }
+      }
+    }
+  }
+#undef BST
+    return;
+  }
+
+  // ---- quadtree, leaves pushed and popped like inner nodes (shallow blocks: C <= 3) ----
   unsigned stack[16];
   float boxStack[16][6];
   int sp = 0;
@@ -335,8 +540,6 @@ __device__ __forceinline__ void block_intersect(const EcbDeviceScene& sc, const 
   boxStack[0][0] = -1.f; boxStack[0][1] = -1.f; boxStack[0][2] = box[0];
   boxStack[0][3] = 1.f;  boxStack[0][4] = 1.f;  boxStack[0][5] = box[1];
   float tNear[4] = {0.f, 0.f, 0.f, 0.f}, tFar[4] = {0.f, 0.f, 0.f, 0.f};
-  const uint32_t elems = sc.elems;
-  const uint32_t* node_words = reinterpret_cast<const uint32_t*>(blk + ECB_BLOCK_NODES_OFFSET);
 
   while (sp >= 0) {
     const unsigned curr = stack[sp];
@@ -653,7 +856,7 @@ __device__ __forceinline__ bool trace_any(const EcbDeviceScene& sc, const float 
 //   * Rays are read from `in` (stride in_stride: RTCRayHit = 80, or a packed RTCRay copy = 48) and hits are written
 //     to `out` (the caller's RTCRayHit array; may be mapped pinned host memory -> no device-to-host copy at all).
 // ---------------------------------------------------------------------------------------------------------------
-template <int LEAF, bool STATS>
+template <int LEAF, bool STATS, bool DEEP>
 __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_kernel(EcbDeviceScene sc, EcbLaunch L) {
   __shared__ float lut[32];
   init_lut(lut);
@@ -764,7 +967,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
     const unsigned n_idle = __popc(__ballot_sync(0xffffffffu, !busy));
     if (n_pend >= ECB_BLOCK_MIN || (n_pend > 0 && (exhausted || n_idle < ECB_REFILL_IDLE_MIN))) {
       if (busy && pending != ECB_REF_EMPTY) {
-        block_intersect<LEAF, STATS>(sc, lut, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
+        block_intersect<LEAF, STATS, DEEP>(sc, lut, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
         tr.tfar = hit.tfar;  // bvh_intersector1.cpp:117
         pending = ECB_REF_EMPTY;
         if (L.any_hit_exact && hit.block != 0xFFFFFFFFu) {
@@ -1404,11 +1607,17 @@ cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const Ecb
   if (e != cudaSuccess) return e;
   if (ecb_kernel_mode() == 1) return launch_quad(sc, device, L, stream);
   const int grid = grid_for(L.M, device);
-#define ECB_LAUNCH(LEAF)                                                                  \
-  if (L.counters)                                                                         \
-    ecb_intersect_kernel<LEAF, true><<<grid, ECB_THREADS, 0, stream>>>(sc, L);            \
-  else                                                                                    \
-    ecb_intersect_kernel<LEAF, false><<<grid, ECB_THREADS, 0, stream>>>(sc, L)
+  // deep blocks (C >= 4) take the instantiation that tests leaves inline (block_intersect); ECB200_INLINE_LEAVES=0/1 forces one
+  static const int force_inline = [] { const char* e = getenv("ECB200_INLINE_LEAVES"); return e ? atoi(e) : -1; }();
+  const bool deep = force_inline >= 0 ? force_inline != 0 : sc.comp_level >= 4;
+#define ECB_LAUNCH(LEAF)                                                                                   \
+  if (L.counters) {                                                                                        \
+    if (deep) ecb_intersect_kernel<LEAF, true, true><<<grid, ECB_THREADS, 0, stream>>>(sc, L);              \
+    else ecb_intersect_kernel<LEAF, true, false><<<grid, ECB_THREADS, 0, stream>>>(sc, L);                  \
+  } else {                                                                                                 \
+    if (deep) ecb_intersect_kernel<LEAF, false, true><<<grid, ECB_THREADS, 0, stream>>>(sc, L);             \
+    else ecb_intersect_kernel<LEAF, false, false><<<grid, ECB_THREADS, 0, stream>>>(sc, L);                 \
+  }
   switch (sc.leaf_kind) {
     case 0: ECB_LAUNCH(0); break;
     case 1: ECB_LAUNCH(1); break;
