@@ -119,14 +119,58 @@ def not_ok_mask(x, truth):
     return m
 
 
+class InstancedCase:
+    """BASELINE config 4: the 25-instance scene of the benchmark (__graft_entry__.CONFIG4_SPEC) built by one ISA / library of
+    the reference; same interface as a RefScene for the report (intersect, bounds, hit_normals, free)."""
+
+    def __init__(self, isa=None, lib=None):
+        import __graft_entry__ as ge
+        from instancing_util import affine
+        spec = ge.CONFIG4_SPEC
+        cfg = spec["leaf"] + (",max_isa=" + isa if isa else "")
+        self.objs = []
+        for kind, S, C in spec["objects"]:
+            o = po.RefScene(cfg, S, C, lib_path=lib)
+            o.add_obj() if kind == "bomberman" else o.add_cube(1, 1.0)
+            o.commit()
+            self.objs.append(o)
+        self.top = po.RefScene(cfg, spec["objects"][0][1], spec["objects"][0][2], lib_path=lib)
+        k, g = 0, spec["grid"]
+        for ix in range(-g, g + 1):
+            for iz in range(-g, g + 1):
+                o = self.objs[(ix + iz) % len(self.objs)]
+                self.top.add_instance(o, affine(0.6 + 0.1 * ((ix * 5 + iz) % 3), 0.3 * k, (spec["spacing"] * ix, 0.2 * ((k % 4) - 1.5), spec["spacing"] * iz)))
+                k += 1
+        self.top.commit()
+
+    def intersect(self, rays, threads=None):
+        return self.top.intersect(rays, threads)
+
+    def bounds(self):
+        return self.top.bounds()
+
+    def port(self):
+        return po.PortInstancedScene(self.top, self.objs)
+
+    def free(self):
+        self.top.free()
+        for o in self.objs:
+            o.free()
+
+
 def case_report(name, kind, leaf, S, C, ray_sets, avx512=True, make_tracer=None):
     """ray_sets: callable(ref_avx2) -> list of (label, rays).  make_tracer(ref_avx2, port) -> function(rays) tracing them in
     place with the implementation under test (default: the oracle port; the -m gpu test passes the CUDA path)."""
     t0 = time.time()
-    ref = make_scene(kind, leaf, S, C)
-    sse = make_scene(kind, leaf, S, C, isa="sse4.2")
-    a512 = make_scene(kind, leaf, S, C, lib=po.REF_SO_AVX512) if (avx512 and po.have_avx512_reference()) else None
-    port = po.PortScene.from_ref(ref)
+    if kind == "instanced":
+        ref, sse = InstancedCase(), InstancedCase(isa="sse4.2")
+        a512 = InstancedCase(lib=po.REF_SO_AVX512) if (avx512 and po.have_avx512_reference()) else None
+        port = ref.port()
+    else:
+        ref = make_scene(kind, leaf, S, C)
+        sse = make_scene(kind, leaf, S, C, isa="sse4.2")
+        a512 = make_scene(kind, leaf, S, C, lib=po.REF_SO_AVX512) if (avx512 and po.have_avx512_reference()) else None
+        port = po.PortScene.from_ref(ref)
     trace = make_tracer(ref, port) if make_tracer else port.intersect
     out = {}
     for label, rays in ray_sets(ref):
@@ -192,6 +236,24 @@ def primary_and_bounce(W, H, cam, hits_file=None):
     return make
 
 
+def primary_only(W, H, cam):
+    return lambda ref: [("primary", rg.primary_rays(W, H, **cam))]
+
+
+def diffuse_samples(W, H, cam, samples):
+    """BASELINE config 5: cosine-diffuse rays leaving the primary hit points, several sample indices of the tutorial sampler."""
+    def make(ref):
+        prim = rg.primary_rays(W, H, **cam)
+        first = prim.copy()
+        ref.intersect(first)
+        b = ref.bounds()
+        xs, ys = np.meshgrid(np.arange(W, dtype=np.uint32), np.arange(H, dtype=np.uint32))
+        n = ref.hit_normals(first)
+        diag = float(np.linalg.norm(b[3:] - b[:3]))
+        return [("diffuse sample %d" % k, rg.diffuse_rays(first, n, diag, sample=k, pixel_xy=(xs.ravel(), ys.ravel()))) for k in samples]
+    return make
+
+
 def main():
     quick = "--quick" in sys.argv
     cases = []
@@ -204,6 +266,11 @@ def main():
     cases.append(("config1 cube+plane S6/C4 leaf %dx%d" % (c1, c1), "cubeplane", "leaf", 6, 4, primary_and_bounce(c1, c1, rg.CUBE_CAMERA)))
     if not quick:
         cases.append(("config3 cube S8/C4 leaf 1920x1080", "cube", "leaf", 8, 4, primary_and_bounce(1920, 1080, rg.CUBE_CAMERA)))
+    import __graft_entry__ as ge
+    c4 = (480, 270) if quick else (1920, 1080)
+    cases.append(("config4 25 instances grid %dx%d" % c4, "instanced", "grid", 6, 3, primary_only(c4[0], c4[1], ge.CONFIG4_CAMERA)))
+    c5 = (480, 270) if quick else (1920, 1080)
+    cases.append(("config5 bomberman S6/C3 leaf %dx%d" % c5, "bomberman", "leaf", 6, 3, diffuse_samples(c5[0], c5[1], rg.BOMBERMAN_CAMERA, (1, 17, 38))))
     report = {"generated_by": "tests/golden/make_parity_report.py", "tolerance": {"t_u_v": parity.TOL, "near_tie_eps": parity.EPS_TIE, "class_B_eps": EPS_B, "class_C_eps_uv": EPS_UV, "class_D_perturbation": PERTURB},
               "cases": {}}
     for name, kind, leaf, S, C, rays in cases:
