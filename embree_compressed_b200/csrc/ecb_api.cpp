@@ -34,6 +34,7 @@ constexpr int kStages = 8;
 constexpr int kSmallStages = 2;              // stages of a small staging context (calls of up to kInlineRaysMax rays)
 constexpr size_t kPackedBytes = 32;         // packed input record of the host-buffer path: {org.xyz,tnear},{dir.xyz,tfar}
 constexpr int kPackPartsDefault = 8;        // pack jobs per chunk (ECB200_PACK_PARTS overrides for experiments)
+constexpr int kDirectPercentDefault = 0;     // packed path, pinned caller memory: share of chunks uploaded as full records by DMA instead of packed (ECB200_DIRECT_PERCENT)
 constexpr int kPackAheadDefault = 3;        // chunks packed ahead of the one being issued to the GPU (ECB200_PACK_AHEAD)
 constexpr size_t kChunkRaysMax = 1u << 17;  // capacity of a staging buffer: 128 Ki rays
 constexpr int kScatterParts = 4;            // scatter jobs per chunk
@@ -605,8 +606,16 @@ void pack_rays_np(const NpView& a, size_t first, uint8_t* dst, size_t b, size_t 
 //   for the event, hands the scatter jobs to the pool -> pool: scatter into the caller's records.
 // Pool threads never wait on the GPU; the caller's thread stays kPackAhead chunks ahead with the pack jobs.
 ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, bool exact, uint32_t instID, uint8_t* base, uint64_t M, size_t stride,
-                         const NpView* np = nullptr, size_t np_first = 0) {
+                         const NpView* np = nullptr, size_t np_first = 0, bool direct_ok = false) {
   static const int kPackParts = env_int("ECB200_PACK_PARTS", kPackPartsDefault, 1, 64);
+  // Hybrid upload (pinned, densely packed caller records only): a fraction of the chunks is not packed by the pool but DMA'd
+  // straight from the caller's array as full records -- more bytes over the link (80 instead of 32 per ray), no host-core
+  // and less host-memory work for those chunks.  The pool and the link then both run at capacity instead of the link idling
+  // behind the pack jobs.  ECB200_DIRECT_PERCENT = share of direct chunks in percent (0 = always pack).
+  static const int kDirectPercent = env_int("ECB200_DIRECT_PERCENT", kDirectPercentDefault, 0, 100);
+  const bool hybrid = direct_ok && !np && kDirectPercent > 0 && M > kInlineRaysMax;
+  auto is_direct = [&](uint64_t c) { return hybrid && ((c + 1) * (uint64_t)kDirectPercent) / 100 > (c * (uint64_t)kDirectPercent) / 100; };
+  const size_t elem = occluded ? kRayBytes : kRayHitBytes;
   static const int kPackAheadCfg = env_int("ECB200_PACK_AHEAD", kPackAheadDefault, 1, kStages - 2);
   const int nst = st->n_stages;
   const int kPackAhead = kPackAheadCfg < nst - 1 ? kPackAheadCfg : (nst > 1 ? nst - 1 : 1);
@@ -630,11 +639,13 @@ ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, 
     const int k = (int)(c % nst);
     const size_t n = chunk_size(c);
     cudaStream_t q = st->stream[k];
-    CU(cudaMemcpyAsync(st->d_buf[k], st->h_pk[k], n * kPackedBytes, cudaMemcpyHostToDevice, q));
+    const bool direct = is_direct(c);
+    if (direct) CU(cudaMemcpyAsync(st->d_buf[k], base + c * chunk * stride, n * elem, cudaMemcpyHostToDevice, q));
+    else CU(cudaMemcpyAsync(st->d_buf[k], st->h_pk[k], n * kPackedBytes, cudaMemcpyHostToDevice, q));
     EcbLaunch L;
     L.in = static_cast<const uint8_t*>(st->d_buf[k]);
-    L.in_stride = kPackedBytes;
-    L.tfar_offset = 28;
+    L.in_stride = direct ? elem : kPackedBytes;
+    L.tfar_offset = direct ? 32 : 28;
     L.out = nullptr;
     L.out_stride = 0;
     L.M = n;
@@ -761,7 +772,7 @@ ecbError run_host_packed(ecbScene* s, Residency* r, Staging* st, bool occluded, 
     if (c < n_chunks) {
       const int k = (int)(c % nst);
       const size_t n = chunk_size(c);
-      const int parts = (int)(n / 4096 < 1 ? 1 : (n / 4096 > (size_t)kPackParts ? (size_t)kPackParts : n / 4096));  // >= 4 Ki rays per pack job
+      const int parts = is_direct(c) ? 0 : (int)(n / 4096 < 1 ? 1 : (n / 4096 > (size_t)kPackParts ? (size_t)kPackParts : n / 4096));  // >= 4 Ki rays per pack job; none for a direct chunk
       {
         std::unique_lock<std::mutex> wl(st->mutex);
         if (c >= (uint64_t)nst)  // the stage's previous chunk is done down to its last scatter job
@@ -840,7 +851,7 @@ ecbError run_host_on(ecbScene* s, Residency* r, bool occluded, uint32_t instID, 
   const bool pinned = is_pinned(rays);
   const bool compact = path != kPathCopy;
   const int extra = s->instanced ? kExtraInst : s->has_triangles() ? kExtraNg : kExtraNone;
-  if (path == kPathPacked) return run_host_packed(s, r, st, occluded, exact, instID, base, M, stride);
+  if (path == kPathPacked) return run_host_packed(s, r, st, occluded, exact, instID, base, M, stride, nullptr, 0, pinned && stride == elem);
   const bool use_pool = compact && M > 8192;  // small calls (rtcIntersect1, packets) scatter inline
 
   auto launch = [&](int k, size_t n) -> cudaError_t {

@@ -1092,8 +1092,11 @@ __device__ __forceinline__ void instance_ray(const EcbInstance* in, const float 
 
 // KIND: leaf kind shared by every object scene (the usual case: one subdiv_accel per device) -> the object traversal is
 // inlined; -1: mixed kinds, dispatched per visit through the out-of-line form
+#ifndef ECB_INST_MIN_BLOCKS
+#define ECB_INST_MIN_BLOCKS 1
+#endif
 template <bool ANYHIT, bool STATS, int KIND>
-__global__ void __launch_bounds__(ECB_THREADS) ecb_instanced_kernel(EcbDeviceInstScene is, EcbLaunch L) {
+__global__ void __launch_bounds__(ECB_THREADS, ECB_INST_MIN_BLOCKS) ecb_instanced_kernel(EcbDeviceInstScene is, EcbLaunch L) {
   __shared__ float lut[32];
   init_lut(lut);
   __syncthreads();
