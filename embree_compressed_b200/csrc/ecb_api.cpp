@@ -113,6 +113,7 @@ struct Residency {
   void* d_items = nullptr;
   void* d_instances = nullptr;
   void* d_objects = nullptr;
+  void* d_pre = nullptr;  // experiment: bfloat16 pre-test boxes (ecb_format.h)
   EcbDeviceInstScene inst_dev{};
   unsigned long long* d_queues = nullptr;  // ring of device words used as dynamic ray-fetch cursors, one per launch in flight
   std::atomic<uint32_t> next_queue{0};
@@ -125,7 +126,7 @@ struct Residency {
     if (device >= 0) cudaSetDevice(device);
     for (int k = 0; k < 2; k++)
       for (Staging* st : idle[k]) delete st;
-    void* ptrs[] = {d_top, d_blocks, d_tri_top, d_tri_blocks, d_items, d_instances, d_objects, d_queues};
+    void* ptrs[] = {d_top, d_blocks, d_tri_top, d_tri_blocks, d_items, d_instances, d_objects, d_queues, d_pre};
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
@@ -194,6 +195,27 @@ ecbError upload_plain(ecbScene* s, Residency* r) {
   d.grid_width = s->grid_width;
   d.rcp_edges = s->rcp_edges;
   d.top_depth = s->info.top_depth;
+  d.pre = nullptr;
+  if (const char* e = getenv("ECB200_PRETEST"); e && atoi(e) == 1 && !s->top.empty()) {  // experiment, see ecb_format.h
+    std::vector<uint16_t> pre(24 * s->top.size());
+    auto down = [](float f) {  // largest bfloat16 <= f
+      uint32_t u; memcpy(&u, &f, 4);
+      uint32_t h = u >> 16;
+      if ((u & 0xFFFFu) && (u >> 31)) h += 1;  // negative with dropped bits: one step away from zero
+      return (uint16_t)h;
+    };
+    auto up = [](float f) {  // smallest bfloat16 >= f
+      uint32_t u; memcpy(&u, &f, 4);
+      uint32_t h = u >> 16;
+      if ((u & 0xFFFFu) && !(u >> 31)) h += 1;
+      return (uint16_t)h;
+    };
+    for (size_t n = 0; n < s->top.size(); n++)
+      for (int p = 0; p < 6; p++)
+        for (int c = 0; c < 4; c++) pre[24 * n + 4 * p + c] = (p & 1) ? up(s->top[n].bounds[p][c]) : down(s->top[n].bounds[p][c]);
+    CU(upload_array(&r->d_pre, pre.data(), pre.size() * 2));
+    d.pre = r->d_pre;
+  }
   if (s->has_triangles()) {  // mixed scene: triangle accel next to the compressed one
     CU(upload_array(&r->d_tri_top, s->tri_top.data(), s->tri_top.size() * sizeof(EcbTopNode)));
     CU(upload_array(&r->d_tri_blocks, s->tri_blocks.data(), s->tri_blocks.size() * sizeof(EcbTriBlock)));
@@ -263,9 +285,9 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return v < lo ? lo : (v > hi ? hi : v);
 }
 
-Staging* create_staging(int device, bool large) {
+ecbError create_staging(int device, bool large, Staging** out) {
   Staging* st = new (std::nothrow) Staging;
-  if (!st) return nullptr;
+  if (!st) return ECB_ERROR_OUT_OF_MEMORY;
   st->device = device;
   st->n_stages = large ? kStages : kSmallStages;
   st->cap = large ? kChunkRaysMax : (size_t)kInlineRaysMax;
@@ -281,10 +303,10 @@ Staging* create_staging(int device, bool large) {
   }
   if (e != cudaSuccess) {
     delete st;
-    cuda_fail(e, "staging allocation");
-    return nullptr;
+    return cuda_fail(e, "staging allocation");
   }
-  return st;
+  *out = st;
+  return ECB_SUCCESS;
 }
 
 // Hands a staging context of the residency to the calling thread for the duration of one call.  Small contexts are
@@ -319,11 +341,12 @@ ecbError acquire_staging(Residency* r, bool large, StagingLease* lease) {
     if (r->created[kind] < limit) {
       r->created[kind]++;
       l.unlock();
-      Staging* st = create_staging(r->device, large);
-      if (!st) {
+      Staging* st = nullptr;
+      const ecbError ce = create_staging(r->device, large, &st);
+      if (ce != ECB_SUCCESS) {
         l.lock();
         r->created[kind]--;
-        return g_last_error.find("out of memory") != std::string::npos ? ECB_ERROR_OUT_OF_MEMORY : ECB_ERROR_CUDA;
+        return ce;
       }
       lease->st = st;
       return ECB_SUCCESS;

@@ -52,6 +52,10 @@ struct EcbDeviceScene {
   uint32_t grid_width;    // 2^C+1
   float rcp_edges;        // 1/2^C
   uint32_t top_depth;     // depth of the top-level BVH4 (sizes the shared-memory stack of the quad kernel: 3*depth+1 entries)
+  // experiment (-DECB_PRETEST builds with ECB200_PRETEST=1 only, NULL otherwise): per top-level node 48 bytes = the six planes of
+  // its four children as bfloat16, rounded OUTWARD.  A ray that misses all four widened boxes cannot hit the fp32 ones
+  // (IEEE subtraction, multiplication and min / max are monotone), so the 112-byte node need not be fetched.
+  const void* pre;
 };
 
 // ---- instanced scenes: a BVH4 over instances of object scenes ----

@@ -741,6 +741,34 @@ __device__ __forceinline__ unsigned top_node(const EcbTopNode* __restrict__ node
   return mask;
 }
 
+#ifdef ECB_PRETEST
+// experiment: can the ray hit ANY of the four children's outward-rounded bfloat16 boxes?  false => the exact
+// test cannot succeed either, the 112-byte node is not fetched
+__device__ __forceinline__ bool pretest_node(const uint4* __restrict__ pre, uint32_t index, const TravRay& tr) {
+  const uint4 qx = __ldg(pre + 3 * (size_t)index), qy = __ldg(pre + 3 * (size_t)index + 1), qz = __ldg(pre + 3 * (size_t)index + 2);
+  // q.x, q.y = lower planes of children 0..3 (two halfs per word), q.z, q.w = upper planes
+  const uint32_t nxw0 = tr.nu[0] ? qx.z : qx.x, nxw1 = tr.nu[0] ? qx.w : qx.y, fxw0 = tr.nu[0] ? qx.x : qx.z, fxw1 = tr.nu[0] ? qx.y : qx.w;
+  const uint32_t nyw0 = tr.nu[1] ? qy.z : qy.x, nyw1 = tr.nu[1] ? qy.w : qy.y, fyw0 = tr.nu[1] ? qy.x : qy.z, fyw1 = tr.nu[1] ? qy.y : qy.w;
+  const uint32_t nzw0 = tr.nu[2] ? qz.z : qz.x, nzw1 = tr.nu[2] ? qz.w : qz.y, fzw0 = tr.nu[2] ? qz.x : qz.z, fzw1 = tr.nu[2] ? qz.y : qz.w;
+  bool any = false;
+#define ECB_PRE_CHILD(w0, w1, hi)                                                                                                   \
+  {                                                                                                                                 \
+    const float nx = __uint_as_float(hi ? (nx##w0 & 0xFFFF0000u) : (nx##w0 << 16)), fx = __uint_as_float(hi ? (fx##w0 & 0xFFFF0000u) : (fx##w0 << 16)); \
+    const float ny = __uint_as_float(hi ? (ny##w0 & 0xFFFF0000u) : (ny##w0 << 16)), fy = __uint_as_float(hi ? (fy##w0 & 0xFFFF0000u) : (fy##w0 << 16)); \
+    const float nz = __uint_as_float(hi ? (nz##w0 & 0xFFFF0000u) : (nz##w0 << 16)), fz = __uint_as_float(hi ? (fz##w0 & 0xFFFF0000u) : (fz##w0 << 16)); \
+    const float tn = sse_max(sse_max((nx - tr.org[0]) * tr.rdn[0], (ny - tr.org[1]) * tr.rdn[1]), sse_max((nz - tr.org[2]) * tr.rdn[2], tr.tnear)); \
+    const float tf = sse_min(sse_min((fx - tr.org[0]) * tr.rdf[0], (fy - tr.org[1]) * tr.rdf[1]), sse_min((fz - tr.org[2]) * tr.rdf[2], tr.tfar));   \
+    any = any || tn <= tf;                                                                                                          \
+  }
+  ECB_PRE_CHILD(w0, w0, 0)
+  ECB_PRE_CHILD(w0, w0, 1)
+  ECB_PRE_CHILD(w1, w1, 0)
+  ECB_PRE_CHILD(w1, w1, 1)
+#undef ECB_PRE_CHILD
+  return any;
+}
+#endif
+
 __device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, uint32_t& db) {
   // if (b.dist < a.dist) xchg(b,a)   (stack_item.h:40-60)
   if (db < da) {
@@ -755,7 +783,7 @@ __device__ __forceinline__ void cswap(uint32_t& ra, uint32_t& da, uint32_t& rb, 
 // Restates the pop loop + down loop of bvh_intersector1.cpp:73-105 with traverseClosestHit (bvh_traverser1.h:436-506).
 template <bool STATS>
 __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ nodes, const TravRay& tr, uint32_t* stack_ref, uint32_t* stack_dist,
-                                               int& sp, float ray_tfar, Work& work, uint32_t n_nodes = 0xFFFFFFFFu) {
+                                               int& sp, float ray_tfar, Work& work, uint32_t n_nodes = 0xFFFFFFFFu, const uint4* pre = nullptr) {
   while (sp > 0) {
     sp--;
     uint32_t cur = stack_ref[sp];
@@ -765,6 +793,9 @@ __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ no
       if (STATS) work.top_nodes++;
       ECB_CHECK(cur < n_nodes, 1);
       ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
+#ifdef ECB_PRETEST
+      if (pre && !pretest_node(pre, cur, tr)) { popped = true; break; }
+#endif
       float tNear[4];
       uint32_t child[4];
       const unsigned mask = top_node(nodes, cur, tr, tNear, child);
@@ -940,7 +971,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
 
     // ---- top level: every traversing lane runs to its next block or terminates ----
     if (busy && pending == ECB_REF_EMPTY) {
-      pending = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work, sc.n_top);
+      pending = next_block<STATS>(sc.top, tr, stack_ref, stack_dist, sp, hit.tfar, work, sc.n_top, static_cast<const uint4*>(sc.pre));
       if (pending == ECB_REF_EMPTY) {
         // terminated: write the hit (a miss writes nothing: rtcIntersect contract)
         busy = false;
