@@ -894,6 +894,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned block_min = L.block_min ? L.block_min : ECB_BLOCK_MIN, refill_min = L.refill_min ? L.refill_min : ECB_REFILL_IDLE_MIN;
   Work work = {0u, 0u, 0u, 0u};
   uint32_t n_rays = 0, n_hits = 0;
 
@@ -924,7 +925,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
     const unsigned n_pend0 = __popc(__ballot_sync(0xffffffffu, busy && pending != ECB_REF_EMPTY));
 
     // ---- refill idle lanes (when enough are idle to make the ray set-up worth a pass, or nothing else can run) ----
-    if (!exhausted && idle_mask && (__popc(idle_mask) >= ECB_REFILL_IDLE_MIN || (n_trav0 == 0 && n_pend0 < ECB_BLOCK_MIN))) {
+    if (!exhausted && idle_mask && (__popc(idle_mask) >= refill_min || (n_trav0 == 0 && n_pend0 < block_min))) {
       unsigned need = idle_mask;
       while (need && !exhausted) {
         if (chunk_next == chunk_end) {
@@ -996,7 +997,7 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_MIN_BLOCKS) ecb_intersect_ker
     // ---- blocks: when enough lanes wait at one, or the idle lanes cannot be given other work ----
     const unsigned n_pend = __popc(__ballot_sync(0xffffffffu, busy && pending != ECB_REF_EMPTY));
     const unsigned n_idle = __popc(__ballot_sync(0xffffffffu, !busy));
-    if (n_pend >= ECB_BLOCK_MIN || (n_pend > 0 && (exhausted || n_idle < ECB_REFILL_IDLE_MIN))) {
+    if (n_pend >= block_min || (n_pend > 0 && (exhausted || n_idle < refill_min))) {
       if (busy && pending != ECB_REF_EMPTY) {
         block_intersect<LEAF, STATS, DEEP>(sc, lut, pending & ~ECB_REF_LEAF, org, dir, ray_tnear, hit, work);
         tr.tfar = hit.tfar;  // bvh_intersector1.cpp:117
@@ -1635,8 +1636,15 @@ static cudaError_t launch_quad(const EcbDeviceScene& sc, int device, const EcbLa
   return cudaGetLastError();
 }
 
-cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L, cudaStream_t stream) {
-  if (L.M == 0) return cudaSuccess;
+cudaError_t ecb_launch_intersect(const EcbDeviceScene& sc, int device, const EcbLaunch& L_in, cudaStream_t stream) {
+  if (L_in.M == 0) return cudaSuccess;
+  EcbLaunch L = L_in;
+  {  // experiments: ECB200_BLOCK_MIN / ECB200_REFILL_MIN override the batching thresholds of every launch
+    static const int bm = [] { const char* e = getenv("ECB200_BLOCK_MIN"); return e ? atoi(e) : 0; }();
+    static const int rm = [] { const char* e = getenv("ECB200_REFILL_MIN"); return e ? atoi(e) : 0; }();
+    if (bm > 0) L.block_min = (uint32_t)bm;
+    if (rm > 0) L.refill_min = (uint32_t)rm;
+  }
   cudaError_t e = cudaMemsetAsync(L.queue, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   if (ecb_kernel_mode() == 1) return launch_quad(sc, device, L, stream);

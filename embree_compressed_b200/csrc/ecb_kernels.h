@@ -54,6 +54,10 @@ struct EcbLaunch {
   float* hit_ng = nullptr;
   uint32_t keep_results = 0;
   uint32_t* hit_inst = nullptr;    // instancing scenes in compact result mode: instID[0] of the hit (geomID of the instance)
+  // batching thresholds of the lane kernel (0 = the built-in ECB_BLOCK_MIN / ECB_REFILL_IDLE_MIN): lanes wait at their block until
+  // block_min lanes have one; idle lanes are refilled once refill_min are idle.  Coherent rays want full block batches;
+  // incoherent ones (few rays reach a block, most end after one or two node tests) want their lanes back sooner.
+  uint32_t block_min = 0, refill_min = 0;
   uint32_t* block_out;            // optional: index of the block of the final hit per ray
   unsigned long long* counters;   // optional: instrumented variant (6 counters)
   unsigned long long* queue;      // device word used as the dynamic ray-fetch cursor (zeroed by the launcher)
