@@ -41,9 +41,46 @@ def orders(w, h):
     yield "morton", morton_order(w, h)
 
 
-def run(scene, rays_t, label, w, h):
+def spread3(v):
+    v = v.astype(np.uint64) & np.uint64(0x3FF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x030000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x0300F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x030C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x09249249)
+    return v
+
+
+def sorted_orders(rays, w, h):
+    """Orders computed from the rays themselves (what a sorting pre-pass on the device would produce)."""
+    org, d = rays[:, 0:3].astype(np.float64), rays[:, 4:7]
+    octant = ((d[:, 0] < 0).astype(np.uint64) | ((d[:, 1] < 0).astype(np.uint64) << np.uint64(1)) | ((d[:, 2] < 0).astype(np.uint64) << np.uint64(2)))
+    tile = np.empty(w * h, np.uint64)
+    tile[sh.tile_pixel_indices(w, sh.tile_grid(w, h, 8))] = np.arange(w * h, dtype=np.uint64)
+    yield "octant,8x8 tiles", np.argsort((octant << np.uint64(40)) | tile, kind="stable")
+    act = (rays[:, 3] <= rays[:, 8]) & np.isfinite(org).all(1)
+    lo, hi = org[act].min(0), org[act].max(0)
+    org = np.where(act[:, None], org, lo)
+    for bits in (4, 6):
+        q = np.clip(((org - lo) / np.maximum(hi - lo, 1e-30) * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+        m = spread3(q[:, 0]) | (spread3(q[:, 1]) << np.uint64(1)) | (spread3(q[:, 2]) << np.uint64(2))
+        yield "morton%d(org),octant" % bits, np.argsort((m << np.uint64(3)) | octant, kind="stable")
+        yield "octant,morton%d(org)" % bits, np.argsort((octant << np.uint64(40)) | m, kind="stable")
+    # direction cell (6 faces x 8x8) then origin morton
+    a = np.abs(d)
+    ax = np.argmax(a, 1)
+    face = (ax * 2 + (d[np.arange(len(d)), ax] < 0)).astype(np.uint64)
+    u = d[np.arange(len(d)), (ax + 1) % 3] / np.maximum(a[np.arange(len(d)), ax], 1e-30)
+    v = d[np.arange(len(d)), (ax + 2) % 3] / np.maximum(a[np.arange(len(d)), ax], 1e-30)
+    cu = np.clip(((u + 1) * 2).astype(np.int64), 0, 3).astype(np.uint64)
+    cv = np.clip(((v + 1) * 2).astype(np.int64), 0, 3).astype(np.uint64)
+    yield "dir cell(6x4x4),tiles", np.argsort((((face << np.uint64(4)) | (cu << np.uint64(2)) | cv) << np.uint64(40)) | tile, kind="stable")
+
+
+def run(scene, rays_t, label, w, h, by_ray=False):
     base = None
-    for name, idx in orders(w, h):
+    import itertools
+    extra = sorted_orders(rays_t.cpu().numpy(), w, h) if by_ray else ()
+    for name, idx in itertools.chain(orders(w, h), extra):
         it = torch.from_numpy(idx.astype(np.int64)).to(dev)
         src = rays_t[it].contiguous()
         ts = []
@@ -57,14 +94,14 @@ def run(scene, rays_t, label, w, h):
         crc = zlib.crc32(back.cpu().numpy().tobytes())
         base = crc if base is None else base
         ms = float(np.median(ts[1:]))
-        print("%-22s %-12s %8d rays %.4f ms %6.0f Mrays/s  %s" % (label, name, src.shape[0], ms, src.shape[0] / ms / 1e3,
+        print("%-22s %-24s %8d rays %.4f ms %6.0f Mrays/s  %s" % (label, name, src.shape[0], ms, src.shape[0] / ms / 1e3,
                                                                   "same bits" if crc == base else "DIFFERENT"), flush=True)
 
 
 prim, bounce, _ = bench.config2_rays(rg, "leaf")
 sc2 = ecb.Scene.from_image_file(os.path.join(ROOT, "scenes", "_built", "bomberman_s6c3_leaf.rimg")).upload(0)
 run(sc2, torch.from_numpy(prim).to(dev), "config 2 primary", 1920, 1080)
-run(sc2, torch.from_numpy(bounce).to(dev), "config 2 bounce", 1920, 1080)
+run(sc2, torch.from_numpy(bounce).to(dev), "config 2 bounce", 1920, 1080, by_ray=True)
 sc2.release()
 sc4 = ecb.Scene.load(os.path.join(ROOT, "scenes", "_built", ge.CONFIG4_BLOB)).upload(0)
 ys, xs = torch.meshgrid(torch.arange(0, 4320, 2, device=dev), torch.arange(0, 7680, 2, device=dev), indexing="ij")
