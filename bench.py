@@ -340,6 +340,26 @@ class ShardedPass:
                     dist.send(lh, dst=0)
 
 
+class FramePipeline:
+    """The two passes of a frame on two streams: bounce(k) is ordered after primary(k) by an event (the bounce rays of a
+    renderer are made from the primary hits), primary(k+1) is not ordered after bounce(k) (a double-buffered renderer has the
+    next frame's camera rays ready).  What it buys: the END of a persistent launch is a handful of warps finishing their
+    longest rays while the other SMs idle (`tools/overlap_probe.py`, `profiles/r2z_overlap.txt`: 0.675 -> 0.553 ms per
+    frame); with the next pass already queued on the other stream its CTAs take the SMs as they fall free."""
+
+    def __init__(self, torch, first_stream):
+        self.torch = torch
+        self.streams = [first_stream, torch.cuda.Stream()]
+
+    def frame(self, primary, bounce):
+        a, b = self.streams
+        primary(a)
+        e = self.torch.cuda.Event()
+        e.record(a)
+        b.wait_event(e)
+        bounce(b)
+
+
 def interleaved_tiles(width, height, rank, world, sh):
     """Pixel indices of this rank's tiles (tile t belongs to rank t mod world: sky and geometry tiles spread evenly),
     tile after tile, row-major inside a tile; and the offset of this rank's records in the rank-major frame arrays."""
@@ -719,20 +739,33 @@ def run_ours(args, rank, world):
     n_local = len(idx)
 
     sampler = ClockSampler(local)
+    pipe = None if args.one_stream else FramePipeline(torch, stream_t)
+    timed_streams = [stream_t] if pipe is None else pipe.streams
+    ms_one = None
     gather_info = None
     value_with_gather = None
     if world == 1:
         # ---- device-timed value: a fresh copy of the ray buffers for every step, results written in place (rtcIntersect1M semantics) ----
         bufs = [(d_prim0.clone(), d_bounce0.clone()) for _ in range(K + W)]
 
-        def step(i):
+        def step_one_stream(i):
             p, b = bufs[i]
             scene.intersect_device(p.data_ptr(), n_local, 80, stream)
             scene.intersect_device(b.data_ptr(), n_local, 80, stream)
 
+        def step(i):   # the frame pipeline (FramePipeline): bounce(k) after primary(k), primary(k+1) may start meanwhile
+            p, b = bufs[i]
+            pipe.frame(lambda st: scene.intersect_device(p.data_ptr(), n_local, 80, st.cuda_stream),
+                       lambda st: scene.intersect_device(b.data_ptr(), n_local, 80, st.cuda_stream))
+
+        if pipe is None:
+            step = step_one_stream
+        else:   # the same frames back to back on one stream first (reported next to the value; also leaves the buffers traced once)
+            ms_one = timed_steps(torch, None, dev, K, W, step_one_stream, [stream_t])
+            bufs = [(d_prim0.clone(), d_bounce0.clone()) for _ in range(K + W)]
         sampler.start()
         launches0 = ecb.launch_count()
-        ms_max = timed_steps(torch, None, dev, K, W, step, [stream_t])
+        ms_max = timed_steps(torch, None, dev, K, W, step, timed_streams)
         launches = ecb.launch_count() - launches0 - 2 * W
         clocks = sampler.stop()
         result_mode = "in place (the RTCRayHit records on the device are updated, a fresh copy of both buffers every step)"
@@ -743,21 +776,31 @@ def run_ours(args, rank, world):
         p_prim = ShardedPass(ecb, torch, scene, d_prim0, offset, g_prim, counts=counts)
         p_bounce = ShardedPass(ecb, torch, scene, d_bounce0, offset, g_bounce, counts=counts)
 
-        def step(i):
+        def step_one_stream(i):
             p_prim.launch(stream_t)
             p_bounce.launch(stream_t)
 
-        def step_gather(i):
-            p_prim.launch(stream_t, gather=True)
-            p_bounce.launch(stream_t, gather=True)
+        def step(i):
+            pipe.frame(lambda st: p_prim.launch(st), lambda st: p_bounce.launch(st))
 
+        def step_gather(i):
+            if pipe is None:
+                p_prim.launch(stream_t, gather=True)
+                p_bounce.launch(stream_t, gather=True)
+            else:
+                pipe.frame(lambda st: p_prim.launch(st, gather=True), lambda st: p_bounce.launch(st, gather=True))
+
+        if pipe is None:
+            step = step_one_stream
+        else:
+            ms_one = timed_steps(torch, dist, dev, K, W, step_one_stream, [stream_t])
         if rank == 0:
             sampler.start()
         launches0 = ecb.launch_count()
-        ms_max = timed_steps(torch, dist, dev, K, W, step, [stream_t])
+        ms_max = timed_steps(torch, dist, dev, K, W, step, timed_streams)
         launches = ecb.launch_count() - launches0 - 2 * W
         clocks = sampler.stop() if rank == 0 else None
-        ms_gather = timed_steps(torch, dist, dev, K, W, step_gather, [stream_t])
+        ms_gather = timed_steps(torch, dist, dev, K, W, step_gather, timed_streams)
         value_with_gather = rays_per_step * K / (ms_gather * 1e-3) / 1e6
         # the gathered frame must hold exactly what a single device leaves (rank 0 re-traces the whole frame to check)
         if rank == 0 and not g_prim.fallback:
@@ -882,6 +925,10 @@ def run_ours(args, rank, world):
                                "no data-path collective; with gather the kernels store their hit records straight into rank 0's frame buffer over NVLink" % (WIDTH, HEIGHT, world, TILE, TILE))
                if world > 1 else "single GPU (at --gpus N the frame is sharded by tiles: strong scaling)"}
         out["roofline"] = roofline
+        if ms_one is not None:
+            out["pipeline"] = {"what": "the two passes of a frame run on two streams: bounce(k) ordered after primary(k) by an event, primary(k+1) free to start "
+                                       "while bounce(k) drains (the tail of a persistent launch = a few warps on their longest rays); --one-stream times the old order",
+                               "one_stream": {"value": round(rays_per_step * K / (ms_one * 1e-3) / 1e6, 1), "ms_per_step": round(ms_one / K, 4)}}
         if value_with_gather is not None:
             out["value_with_gather"] = round(value_with_gather, 1)
             out["gather"] = gather_info
@@ -1016,6 +1063,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--leaf", default="leaf", choices=["leaf", "grid", "box"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-stream", action="store_true", help="time the two passes of every frame back to back on one stream (no frame pipeline)")
     ap.add_argument("--configs", default="all", help="which of the other BASELINE configs to measure into the `configs` object: all | none | "
                                                      "comma list of 1,3,4,5 (N > 1 measures the sharded ones, 4 and 5)")
     ap.add_argument("--e2e-memory", default="pinned", choices=["pinned", "pageable"],
