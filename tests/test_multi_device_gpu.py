@@ -85,6 +85,37 @@ def test_concurrent_host_callers_get_their_own_staging_context(ecb):
     assert not errors, errors
 
 
+def test_frame_pipeline_over_two_streams_leaves_the_one_stream_bits(ecb):
+    """bench.py's FramePipeline: bounce(k) on a second stream behind an event, primary(k+1) overlapping it.  Launches of one
+    scene that overlap on the device take their own ray-fetch cursors; every frame must hold the serial result."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    scene = _scene(ecb).upload(0)
+    prim = _rays(768)
+    n = len(prim)
+    dev = torch.device("cuda", 0)
+    first = torch.from_numpy(prim).to(dev)
+    scene.intersect_device(first.data_ptr(), n)
+    torch.cuda.synchronize()
+    hits = first.cpu().numpy()
+    bounce = rg.diffuse_rays(hits, -hits[:, 4:7], 10.0, sample=0)
+    want_b = torch.from_numpy(bounce).to(dev)
+    scene.intersect_device(want_b.data_ptr(), n)
+    torch.cuda.synchronize()
+    pipe = bench.FramePipeline(torch, torch.cuda.current_stream())
+    frames = [(torch.from_numpy(prim).to(dev), torch.from_numpy(bounce).to(dev)) for _ in range(12)]
+    torch.cuda.synchronize()
+    for p, b in frames:
+        pipe.frame(lambda st, p=p: scene.intersect_device(p.data_ptr(), n, 80, st.cuda_stream),
+                   lambda st, b=b: scene.intersect_device(b.data_ptr(), n, 80, st.cuda_stream))
+    torch.cuda.synchronize()
+    for k, (p, b) in enumerate(frames):
+        assert bool((p.view(torch.int32) == first.view(torch.int32)).all()), "primary pass of frame %d" % k
+        assert bool((b.view(torch.int32) == want_b.view(torch.int32)).all()), "bounce pass of frame %d" % k
+
+
 def _two_gpus():
     import torch
     return torch.cuda.device_count() >= 2
