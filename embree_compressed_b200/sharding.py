@@ -40,6 +40,22 @@ def tile_pixel_indices(width, tiles):
     return np.concatenate(out) if out else np.zeros(0, np.int64)
 
 
+def interleaved_tile_indices(width, height, rank, world, tile=64):
+    """Interleaved tile sharding (tile t of the row-major tile grid belongs to rank t mod world: sky and geometry tiles
+    spread evenly over the ranks).  Returns (flat pixel indices of this rank, tile after tile and row-major inside a
+    tile; offset of this rank's records in the rank-major frame arrays; records per rank)."""
+    if width % tile == 0 and height % tile == 0:   # no partial tiles: one transpose instead of a loop over the tiles
+        ty, tx = height // tile, width // tile
+        by_tile = np.arange(width * height, dtype=np.int64).reshape(ty, tile, tx, tile).transpose(0, 2, 1, 3).reshape(ty * tx, tile * tile)
+        counts = [len(range(r, ty * tx, world)) * tile * tile for r in range(world)]
+        idx = by_tile[rank::world].reshape(-1)
+    else:
+        tiles = tile_grid(width, height, tile)
+        counts = [sum(w * h for (_, _, w, h) in tiles[r::world]) for r in range(world)]
+        idx = tile_pixel_indices(width, tiles[rank::world])
+    return idx, int(sum(counts[:rank])), counts
+
+
 def shard_frame(width, height, rank, world, tile=64):
     """(tiles of this rank, flat pixel indices of this rank)."""
     tiles = tile_grid(width, height, tile)

@@ -124,3 +124,18 @@ def test_gather_of_hit_records_over_gloo(world):
         b, e = sh.tile_range(len(tiles), r, world)
         owner[sh.tile_pixel_indices(W, tiles[b:e])] = r
     assert (frame[:, 4] == owner).all()
+
+
+def test_interleaved_tiles_cover_the_frame_once_and_match_the_tile_loop():
+    """bench.py's sharding of a frame (tile t -> rank t mod N): the transposed fast path for frames without partial tiles and
+    the tile loop give the same pixel order; the ranks' index sets partition the frame; offsets are rank-major."""
+    for (w, h, t) in ((128, 64, 16), (100, 70, 16), (1920, 1080, 64)):
+        for world in (1, 2, 3, 8):
+            tiles = sh.tile_grid(w, h, t)
+            seen = np.zeros(w * h, np.int64)
+            for r in range(world):
+                idx, off, counts = sh.interleaved_tile_indices(w, h, r, world, t)
+                assert (idx == sh.tile_pixel_indices(w, tiles[r::world])).all()
+                assert off == sum(counts[:r]) and counts[r] == len(idx)
+                seen[idx] += 1
+            assert (seen == 1).all() and sum(counts) == w * h
