@@ -800,6 +800,10 @@ __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ no
       uint32_t child[4];
       const unsigned mask = top_node(nodes, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
+      if ((mask & (mask - 1u)) == 0u) {  // one child hit (the common case): no compaction, no distances
+        cur = (mask & 1u) ? child[0] : (mask & 2u) ? child[1] : (mask & 4u) ? child[2] : child[3];
+        continue;
+      }
       uint32_t c[4], d[4];
       int nh = 0;
 #pragma unroll
@@ -1169,6 +1173,10 @@ __global__ void __launch_bounds__(ECB_THREADS, ECB_INST_MIN_BLOCKS) ecb_instance
         ECB_CHECK(sp + 3 <= (int)ECB_MAX_TOP_STACK, 0);
         const unsigned mask = fast_node(is.nodes, cur, tr, tNear, child);
         if (mask == 0) { popped = true; break; }
+        if ((mask & (mask - 1u)) == 0u) {  // one child hit: no compaction, no distances (closest-hit and any-hit alike)
+          cur = (mask & 1u) ? child[0] : (mask & 2u) ? child[1] : (mask & 4u) ? child[2] : child[3];
+          continue;
+        }
         uint32_t c[4], d[4];
         int nh = 0;
 #pragma unroll
