@@ -24,6 +24,7 @@
 
 #include "ecb_format.h"
 #include "ecb_kernels.h"
+#include "ecb_order.h"
 
 // ---------------------------------------------------------------------------------------------------------------
 // -DECB_BOUNDS_CHECK: every index the kernels derive from scene data (node / block / item / instance references, stack
@@ -800,48 +801,7 @@ __device__ __forceinline__ uint32_t next_block(const EcbTopNode* __restrict__ no
       uint32_t child[4];
       const unsigned mask = top_node(nodes, cur, tr, tNear, child);
       if (mask == 0) { popped = true; break; }
-      if ((mask & (mask - 1u)) == 0u) {  // one child hit (the common case): no compaction, no distances
-        cur = (mask & 1u) ? child[0] : (mask & 2u) ? child[1] : (mask & 4u) ? child[2] : child[3];
-        continue;
-      }
-      if (__popc(mask) == 2) {  // two: the lower-index one (a) and the higher-index one (b), picked without the compaction loop
-        const bool b0 = mask & 1u, b1 = mask & 2u, b2 = mask & 4u, b3 = mask & 8u;
-        const uint32_t ca = b0 ? child[0] : b1 ? child[1] : child[2], da = __float_as_uint(b0 ? tNear[0] : b1 ? tNear[1] : tNear[2]);
-        const uint32_t cb = b3 ? child[3] : b2 ? child[2] : child[1], db = __float_as_uint(b3 ? tNear[3] : b2 ? tNear[2] : tNear[1]);
-        const bool a_first = da < db;  // bvh_traverser1.h:452-456: the farther one is pushed, ties keep the higher index on top
-        stack_ref[sp] = a_first ? cb : ca;
-        stack_dist[sp] = a_first ? db : da;
-        sp++;
-        cur = a_first ? ca : cb;
-        continue;
-      }
-      if (mask != 15u) {  // three: the hit children in index order are {0 or 1, 1 or 2, 2 or 3}
-        const bool b0 = mask & 1u, b01 = (mask & 3u) == 3u, b3 = mask & 8u;
-        uint32_t r3 = b0 ? child[0] : child[1], d3 = __float_as_uint(b0 ? tNear[0] : tNear[1]);
-        uint32_t r2 = b01 ? child[1] : child[2], d2 = __float_as_uint(b01 ? tNear[1] : tNear[2]);
-        uint32_t r1 = b3 ? child[3] : child[2], d1 = __float_as_uint(b3 ? tNear[3] : tNear[2]);
-        // items pushed in order c0,c1,c2 ; sort(s1=top(c2), s2=c1, s3=c0)  (stack_item.h:45-50)
-        cswap(r1, d1, r2, d2);
-        cswap(r2, d2, r3, d3);
-        cswap(r1, d1, r2, d2);
-        stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
-        stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
-        cur = r1;
-        continue;
-      }
-      {  // all four (stack_item.h:53-60)
-        uint32_t r1 = child[3], d1 = __float_as_uint(tNear[3]), r2 = child[2], d2 = __float_as_uint(tNear[2]);
-        uint32_t r3 = child[1], d3 = __float_as_uint(tNear[1]), r4 = child[0], d4 = __float_as_uint(tNear[0]);
-        cswap(r1, d1, r2, d2);
-        cswap(r3, d3, r4, d4);
-        cswap(r1, d1, r3, d3);
-        cswap(r2, d2, r4, d4);
-        cswap(r2, d2, r3, d3);
-        stack_ref[sp] = r4; stack_dist[sp] = d4; sp++;
-        stack_ref[sp] = r3; stack_dist[sp] = d3; sp++;
-        stack_ref[sp] = r2; stack_dist[sp] = d2; sp++;
-        cur = r1;
-      }
+      cur = ecb_order_hit_children(mask, child, tNear, stack_ref, stack_dist, sp);  // traverseClosestHit + sort networks
     }
     if (popped || cur == ECB_REF_EMPTY) continue;
     return cur;
