@@ -50,3 +50,24 @@ def test_kernels_keep_the_register_budgets_their_occupancy_rests_on():
     for k, (reg, stack, shared, local) in res.items():
         if "ecb_occluded_kernel" in k or "ecb_triangle_kernel" in k:
             assert reg <= 96 and local == 0, (k, reg)
+
+
+def test_lane_kernel_reads_nodes_and_block_headers_with_128_bit_read_only_loads():
+    """north_star: "nodes read with vectorised 128-bit __ldg".  SASS of the shipping lane kernel (cLeaf): the seven 16-byte loads
+    of a top-level node and the nine of a block header are LDG.E.128.CONSTANT; the ray records, which an in-place call writes
+    back, do not go through the non-coherent path."""
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or libecb200.so missing")
+    sass = subprocess.run([exe, "-sass", LIB], capture_output=True, text=True).stdout
+    body, on = [], False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            on = "ecb_intersect_kernelILi1ELb0ELb0E" in line
+        elif on:
+            body.append(line)
+    text = "\n".join(body)
+    assert text.count("LDG.E.128.CONSTANT") >= 16, text.count("LDG.E.128.CONSTANT")
+    ray_loads = [l for l in body if re.search(r"\bLDG\.E(\.\d+)?\.STRONG\.GPU\b", l)]
+    assert len(ray_loads) >= 3, "ray records are read with ld.global.cg (coherent at L2)"
+    assert "ATOMG" in text or "ATOM" in text   # the dynamic ray-fetch cursor
