@@ -761,7 +761,10 @@ def run_ours(args, rank, world):
             step = step_one_stream
         else:   # the same frames back to back on one stream first (reported next to the value; also leaves the buffers traced once)
             ms_one = timed_steps(torch, None, dev, K, W, step_one_stream, [stream_t])
-            bufs = [(d_prim0.clone(), d_bounce0.clone()) for _ in range(K + W)]
+            for p, b in bufs:   # fresh rays again, in the same buffers
+                p.copy_(d_prim0)
+                b.copy_(d_bounce0)
+            torch.cuda.synchronize()
         sampler.start()
         launches0 = ecb.launch_count()
         ms_max = timed_steps(torch, None, dev, K, W, step, timed_streams)
